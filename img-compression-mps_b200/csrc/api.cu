@@ -1,0 +1,143 @@
+// Context, workspace arena and error plumbing of libndmps_sm100.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ndmps {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void Arena::release() {
+    for (auto& c : chunks) cudaFree(c.base);
+    chunks.clear();
+}
+
+int Arena::reset(cudaStream_t stream) {
+    if (cur_total > high_water) high_water = cur_total;
+    cur_total = 0;
+    if (chunks.size() > 1) {
+        // merge: everything issued against the old chunks must have finished first
+        NDMPS_CUDA_TRY(cudaStreamSynchronize(stream));
+        size_t total = 0;
+        for (auto& c : chunks) total += c.cap;
+        release();
+        char* p = nullptr;
+        NDMPS_CUDA_TRY(cudaMalloc(&p, total));
+        chunks.push_back({p, total, 0});
+    }
+    for (auto& c : chunks) c.used = 0;
+    return NDMPS_OK;
+}
+
+int Arena::alloc(size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    for (auto& c : chunks) {
+        if (c.cap - c.used >= bytes) {
+            *out = c.base + c.used;
+            c.used += bytes;
+            cur_total += bytes;
+            return NDMPS_OK;
+        }
+    }
+    size_t cap = bytes < (size_t(64) << 20) ? (size_t(64) << 20) : bytes;
+    char* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+        set_error("workspace cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+        return NDMPS_ERR_NOMEM;
+    }
+    chunks.push_back({p, cap, bytes});
+    cur_total += bytes;
+    *out = p;
+    return NDMPS_OK;
+}
+
+int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
+    if (ctx->pinned_doubles >= doubles) return NDMPS_OK;
+    if (ctx->pinned) {
+        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_doubles = 0;
+    }
+    size_t want = doubles < 16384 ? 16384 : doubles;
+    NDMPS_CUDA_TRY(cudaMallocHost(&ctx->pinned, want * sizeof(double)));
+    ctx->pinned_doubles = want;
+    return NDMPS_OK;
+}
+
+}  // namespace ndmps
+
+using namespace ndmps;
+
+extern "C" {
+
+int ndmps_version(void) { return 100; }
+
+const char* ndmps_last_error(void) { return g_err; }
+
+int ndmps_ctx_create(ndmps_ctx_t** out) {
+    NDMPS_REQUIRE(out != nullptr, "ndmps_ctx_create: out is NULL");
+    int dev = 0;
+    NDMPS_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    NDMPS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error("libndmps_sm100 needs a compute capability 10.x device (B200); found %d.%d (%s)", prop.major,
+                  prop.minor, prop.name);
+        return NDMPS_ERR_CUDA;
+    }
+    ndmps_ctx* ctx = new ndmps_ctx();
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return NDMPS_OK;
+}
+
+int ndmps_ctx_destroy(ndmps_ctx_t* ctx) {
+    if (!ctx) return NDMPS_OK;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->ws.release();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+    return NDMPS_OK;
+}
+
+int ndmps_ctx_set_stream(ndmps_ctx_t* ctx, void* cuda_stream) {
+    NDMPS_REQUIRE(ctx != nullptr, "ndmps_ctx_set_stream: ctx is NULL");
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return NDMPS_OK;
+}
+
+int ndmps_ctx_sync(ndmps_ctx_t* ctx) {
+    NDMPS_REQUIRE(ctx != nullptr, "ndmps_ctx_sync: ctx is NULL");
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return NDMPS_OK;
+}
+
+int64_t ndmps_ctx_launch_count(const ndmps_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
+    NDMPS_REQUIRE(ctx != nullptr && name != nullptr, "ndmps_ctx_set_option: NULL argument");
+    if (!strcmp(name, "gram_path")) ctx->opt_gram_path = value;
+    else if (!strcmp(name, "jacobi_block")) ctx->opt_jacobi_block = value;
+    else if (!strcmp(name, "merge_cap")) ctx->opt_merge_cap = value;
+    else if (!strcmp(name, "jacobi_max_sweeps")) ctx->opt_jacobi_max_sweeps = value;
+    else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
+    else {
+        set_error("ndmps_ctx_set_option: unknown option '%s'", name);
+        return NDMPS_ERR_INVALID;
+    }
+    return NDMPS_OK;
+}
+
+}  // extern "C"

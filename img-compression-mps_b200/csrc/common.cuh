@@ -1,0 +1,186 @@
+// Shared host/device plumbing of libndmps_sm100.so (context, workspace arena,
+// error reporting, warp/block reductions).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ndmps.h"
+
+#define NDMPS_MAX_DIGITS 40
+
+struct DigitList {
+    int n;                              // number of digits (after dropping extent-1 and merging)
+    uint32_t extent[NDMPS_MAX_DIGITS];  // destination extents, outermost first
+    int64_t stride[NDMPS_MAX_DIGITS];   // source stride (elements) of each digit
+    int32_t shift[NDMPS_MAX_DIGITS];    // log2(extent) if power of two else -1
+};
+
+struct ndmps_plan {
+    int ndim, levels;
+    int64_t shape[8];
+    int64_t factors[NDMPS_MAX_DIGITS];  // (levels, ndim)
+    int64_t site_dims[NDMPS_MAX_DIGITS];
+    int64_t total;
+    DigitList enc;                      // destination = site order, source = volume
+    DigitList dec;                      // destination = volume, source = site order
+    bool identity;
+};
+
+namespace ndmps {
+
+void set_error(const char* fmt, ...);
+
+#define NDMPS_CUDA_TRY(expr)                                                                 \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::ndmps::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return NDMPS_ERR_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+
+#define NDMPS_TRY(expr)                 \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != NDMPS_OK) return _rc; \
+    } while (0)
+
+#define NDMPS_REQUIRE(cond, ...)                    \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::ndmps::set_error(__VA_ARGS__);        \
+            return NDMPS_ERR_INVALID;               \
+        }                                           \
+    } while (0)
+
+// check the launch that was just issued
+#define NDMPS_LAUNCH_CHECK(ctx)                                                              \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            ::ndmps::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return NDMPS_ERR_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+
+// Grow-only device arena.  alloc() is a bump pointer; when a chunk runs out a new
+// one is added (cudaMalloc) and on the next reset() the chunks are merged into
+// one allocation of the total size, so steady state never allocates.
+struct Arena {
+    struct Chunk { char* base; size_t cap; size_t used; };
+    std::vector<Chunk> chunks;
+    size_t high_water = 0;
+    size_t cur_total = 0;
+
+    int reset(cudaStream_t stream);
+    int alloc(size_t bytes, void** out);
+    void release();
+    template <class T> int get(size_t count, T** out) {
+        void* p = nullptr;
+        int rc = alloc(count * sizeof(T), &p);
+        *out = static_cast<T*>(p);
+        return rc;
+    }
+};
+
+}  // namespace ndmps
+
+struct ndmps_ctx {
+    cudaStream_t stream = nullptr;
+    ndmps::Arena ws;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    // pinned host scratch for small D2H readbacks (eigenvalues, flags, scalars)
+    double* pinned = nullptr;
+    size_t pinned_doubles = 0;
+    // options
+    int64_t opt_gram_path = 0;      // 0: SIMT f64-accumulate, 1: tcgen05 split-TF32 (when available)
+    int64_t opt_jacobi_block = 0;   // 0: auto
+    int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
+    int64_t opt_jacobi_max_sweeps = 40;
+    int64_t opt_verbose = 0;
+    // stats of the last eigensolve / sweep (for tests and profiling)
+    int last_eig_sweeps = 0;
+};
+
+namespace ndmps {
+
+int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
+
+static inline size_t dtype_size(int dtype) { return dtype == NDMPS_F64 ? 8 : 4; }
+static inline bool dtype_ok(int dtype) { return dtype == NDMPS_F32 || dtype == NDMPS_F64; }
+
+// ---- internal entry points shared between translation units -------------------
+// generic strided GEMM, float64 accumulation; C row-major with ldc.
+int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
+         const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,
+         const void* b, int dtype_b, int64_t b_rs, int64_t b_cs,
+         void* c, int dtype_c, int64_t ldc);
+int gram(ndmps_ctx* ctx, const void* m, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev);
+int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev);
+int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block reductions; `scratch` must hold 32 doubles; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < nw ? scratch[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+__device__ __forceinline__ double block_max(double v, double* scratch) {
+    v = warp_max(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < nw ? scratch[lane] : -INFINITY;
+        v = warp_max(v);
+    }
+    return v;
+}
+__device__ __forceinline__ double block_min(double v, double* scratch) {
+    v = warp_min(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < nw ? scratch[lane] : INFINITY;
+        v = warp_min(v);
+    }
+    return v;
+}
+#endif
+
+}  // namespace ndmps

@@ -1,0 +1,200 @@
+// Streaming reductions and element-wise helpers: sum of squares (Frobenius norm,
+// core/ndmps.py:61), per-core [min, max] (boundary_list, core/ndmps.py:75,82),
+// PSNR terms (utils/metrics.py:143-146), min-max quantisation
+// (utils/filetools.py:20-39).  All accumulate in float64; two-stage
+// (per-block partials, then one block) so results are run-to-run deterministic.
+#include "common.cuh"
+
+namespace ndmps {
+
+static inline int reduce_grid(const ndmps_ctx* ctx, int64_t n, int per_thread) {
+    int64_t want = (n + 256 * (int64_t)per_thread - 1) / (256 * (int64_t)per_thread);
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// mode 0: sum x^2        -> out[0]
+// mode 1: min, max       -> out[0], out[1]
+// mode 2: sum (a-b)^2, max a -> out[0], out[1]
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) reduce_stage1(const T* __restrict__ a, const T* __restrict__ b, int64_t n,
+                                                      double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    double acc0 = MODE == 1 ? INFINITY : 0.0;
+    double acc1 = -INFINITY;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double x = (double)a[i];
+        if (MODE == 0) {
+            acc0 += x * x;
+        } else if (MODE == 1) {
+            acc0 = fmin(acc0, x);
+            acc1 = fmax(acc1, x);
+        } else {
+            double d = x - (double)b[i];
+            acc0 += d * d;
+            acc1 = fmax(acc1, x);
+        }
+    }
+    double r0 = MODE == 1 ? block_min(acc0, scratch) : block_sum(acc0, scratch);
+    double r1 = MODE == 0 ? 0.0 : block_max(acc1, scratch);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = r0;
+        partial[2 * blockIdx.x + 1] = r1;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_stage2(const double* __restrict__ partial, int nblocks,
+                                                      double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double acc0 = MODE == 1 ? INFINITY : 0.0;
+    double acc1 = -INFINITY;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        double p0 = partial[2 * i], p1 = partial[2 * i + 1];
+        if (MODE == 1) acc0 = fmin(acc0, p0); else acc0 += p0;
+        acc1 = fmax(acc1, p1);
+    }
+    double r0 = MODE == 1 ? block_min(acc0, scratch) : block_sum(acc0, scratch);
+    double r1 = block_max(acc1, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = r0;
+        out[1] = r1;
+    }
+}
+
+template <class T, int MODE>
+static int reduce_to_device(ndmps_ctx* ctx, const T* a, const T* b, int64_t n, double* out_dev2) {
+    int grid = reduce_grid(ctx, n, 8);
+    double* partial = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2 * (size_t)grid, &partial));
+    reduce_stage1<T, MODE><<<grid, 256, 0, ctx->stream>>>(a, b, n, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    reduce_stage2<MODE><<<1, 256, 0, ctx->stream>>>(partial, grid, out_dev2);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+template <int MODE>
+static int reduce_dispatch(ndmps_ctx* ctx, const void* a, const void* b, int64_t n, int dtype, double* out_dev2) {
+    if (dtype == NDMPS_F32) return reduce_to_device<float, MODE>(ctx, (const float*)a, (const float*)b, n, out_dev2);
+    return reduce_to_device<double, MODE>(ctx, (const double*)a, (const double*)b, n, out_dev2);
+}
+
+// ---- quantisation -------------------------------------------------------------
+template <class T, class Q>
+__global__ void __launch_bounds__(256) quantize_kernel(const T* __restrict__ x, int64_t n, double lo, double span,
+                                                        double qmax, Q* __restrict__ q) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // filetools.py:24-26: (x - min) / max(x - min) * iinfo.max, cast truncates toward zero
+        double u = ((double)x[i] - lo) / span;
+        double v = u * qmax;
+        q[i] = (Q)(long long)v;
+    }
+}
+
+template <class T, class Q>
+__global__ void __launch_bounds__(256) dequantize_kernel(const Q* __restrict__ q, int64_t n, double lo, double hi,
+                                                          double qmax, T* __restrict__ x) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // filetools.py:38-39: q / iinfo.max * (max - min) + min
+        double u = (double)q[i] / qmax;
+        x[i] = (T)(u * (hi - lo) + lo);
+    }
+}
+
+}  // namespace ndmps
+
+using namespace ndmps;
+
+extern "C" {
+
+int ndmps_sumsq(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double* out_host) {
+    NDMPS_REQUIRE(ctx && x && out_host, "ndmps_sumsq: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && n >= 0, "ndmps_sumsq: bad dtype or size");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    NDMPS_TRY(ensure_pinned(ctx, 2));
+    double* out_dev = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
+    NDMPS_TRY(reduce_dispatch<0>(ctx, x, nullptr, n, dtype, out_dev));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out_host[0] = ctx->pinned[0];
+    return NDMPS_OK;
+}
+
+int ndmps_minmax(ndmps_ctx_t* ctx, const void* const* arrays, const int64_t* sizes, int count, int dtype,
+                 double* out_host) {
+    NDMPS_REQUIRE(ctx && arrays && sizes && out_host, "ndmps_minmax: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && count >= 0, "ndmps_minmax: bad dtype or count");
+    if (count == 0) return NDMPS_OK;
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    NDMPS_TRY(ensure_pinned(ctx, 2 * (size_t)count));
+    double* out_dev = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2 * (size_t)count, &out_dev));
+    for (int i = 0; i < count; i++) {
+        NDMPS_REQUIRE(arrays[i] && sizes[i] > 0, "ndmps_minmax: array %d is empty", i);
+        NDMPS_TRY(reduce_dispatch<1>(ctx, arrays[i], nullptr, sizes[i], dtype, out_dev + 2 * i));
+    }
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * (size_t)count * sizeof(double), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host, ctx->pinned, 2 * (size_t)count * sizeof(double));
+    return NDMPS_OK;
+}
+
+int ndmps_psnr_terms(ndmps_ctx_t* ctx, const void* a, const void* b, int64_t n, int dtype, double* out_host) {
+    NDMPS_REQUIRE(ctx && a && b && out_host, "ndmps_psnr_terms: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && n > 0, "ndmps_psnr_terms: bad dtype or size");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    NDMPS_TRY(ensure_pinned(ctx, 2));
+    double* out_dev = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
+    NDMPS_TRY(reduce_dispatch<2>(ctx, a, b, n, dtype, out_dev));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out_host[0] = ctx->pinned[0];
+    out_host[1] = ctx->pinned[1];
+    return NDMPS_OK;
+}
+
+int ndmps_quantize(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double lo, double hi, int bits, void* q_out) {
+    NDMPS_REQUIRE(ctx && x && q_out, "ndmps_quantize: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && n >= 0, "ndmps_quantize: bad dtype or size");
+    NDMPS_REQUIRE(bits == 8 || bits == 16, "ndmps_quantize: bits must be 8 or 16, got %d", bits);
+    if (n == 0) return NDMPS_OK;
+    int grid = reduce_grid(ctx, n, 4);
+    double span = hi - lo, qmax = bits == 8 ? 255.0 : 65535.0;
+    if (dtype == NDMPS_F32) {
+        if (bits == 8) quantize_kernel<float, uint8_t><<<grid, 256, 0, ctx->stream>>>((const float*)x, n, lo, span, qmax, (uint8_t*)q_out);
+        else quantize_kernel<float, uint16_t><<<grid, 256, 0, ctx->stream>>>((const float*)x, n, lo, span, qmax, (uint16_t*)q_out);
+    } else {
+        if (bits == 8) quantize_kernel<double, uint8_t><<<grid, 256, 0, ctx->stream>>>((const double*)x, n, lo, span, qmax, (uint8_t*)q_out);
+        else quantize_kernel<double, uint16_t><<<grid, 256, 0, ctx->stream>>>((const double*)x, n, lo, span, qmax, (uint16_t*)q_out);
+    }
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+int ndmps_dequantize(ndmps_ctx_t* ctx, const void* q, int64_t n, int bits, double lo, double hi, int dtype, void* x_out) {
+    NDMPS_REQUIRE(ctx && q && x_out, "ndmps_dequantize: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && n >= 0, "ndmps_dequantize: bad dtype or size");
+    NDMPS_REQUIRE(bits == 8 || bits == 16, "ndmps_dequantize: bits must be 8 or 16, got %d", bits);
+    if (n == 0) return NDMPS_OK;
+    int grid = reduce_grid(ctx, n, 4);
+    double qmax = bits == 8 ? 255.0 : 65535.0;
+    if (dtype == NDMPS_F32) {
+        if (bits == 8) dequantize_kernel<float, uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)q, n, lo, hi, qmax, (float*)x_out);
+        else dequantize_kernel<float, uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)q, n, lo, hi, qmax, (float*)x_out);
+    } else {
+        if (bits == 8) dequantize_kernel<double, uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)q, n, lo, hi, qmax, (double*)x_out);
+        else dequantize_kernel<double, uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)q, n, lo, hi, qmax, (double*)x_out);
+    }
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+}  // extern "C"

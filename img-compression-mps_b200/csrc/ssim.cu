@@ -1,0 +1,283 @@
+// K9: SSIM exactly as the reference defines it (utils/metrics.py:11-129 on top of
+// scikit-image's uniform-window structural_similarity).
+//
+// The reference's 3-D / 4-D SSIM is NOT a 3-D stencil: it is the mean over the three
+// slicing axes of the mean over 2-D slices, each slice with its own data range and a
+// 7x7 box window (min(7, smallest side) forced odd), the second argument clipped at 0,
+// sample covariance, borders cropped.  A "family" below is one slicing axis; a 4-D
+// array contributes frames x slices per family.
+//
+// Pass 1: per-slice data range.  Pass 2: tiles of TILE_H x TILE_W interior pixels,
+// separable box sums of x, y, xx, yy, xy in float64 from a shared-memory patch, one
+// partial sum per tile.  Pass 3: fixed-order reduction (deterministic).
+#include "common.cuh"
+
+namespace ndmps {
+
+struct SliceFamily {
+    int64_t S;        // slices (times frames)
+    int64_t H, W;     // slice extent
+    int64_t sh, sw;   // element strides of the slice's rows / columns
+    int64_t nT;       // frames (1 for 2-D / 3-D)
+    int64_t s_axis;   // stride of the slicing axis
+    int64_t s_t;      // stride of the frame axis
+    int win;          // window (odd)
+};
+
+constexpr int TILE_W = 32, TILE_H = 16, MAXWIN = 7;
+constexpr int PATCH_W = TILE_W + MAXWIN - 1, PATCH_H = TILE_H + MAXWIN - 1;
+
+__device__ __forceinline__ int64_t slice_base(const SliceFamily& f, int64_t s) {
+    int64_t i = s / f.nT, t = s - i * f.nT;
+    return i * f.s_axis + t * f.s_t;
+}
+
+// one CTA per slice: R = max(max a, max clip(b)) - min(min a, min clip(b))   (metrics.py:23-24)
+template <class T>
+__global__ void __launch_bounds__(256) ssim_range_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
+                                                          double* __restrict__ range) {
+    __shared__ double scratch[32];
+    const int64_t s = blockIdx.x;
+    const int64_t base = slice_base(f, s);
+    double lo = INFINITY, hi = -INFINITY;
+    const int64_t total = f.H * f.W;
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        int64_t h = e / f.W, w = e - h * f.W;
+        int64_t off = base + h * f.sh + w * f.sw;
+        double x = (double)a[off];
+        double y = fmax((double)b[off], 0.0);
+        lo = fmin(lo, fmin(x, y));
+        hi = fmax(hi, fmax(x, y));
+    }
+    lo = block_min(lo, scratch);
+    hi = block_max(hi, scratch);
+    if (threadIdx.x == 0) range[s] = hi - lo;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
+                 int tiles_y, int tiles_x, double* __restrict__ partial) {
+    __shared__ T pa[PATCH_H][PATCH_W + 1];
+    __shared__ T pb[PATCH_H][PATCH_W + 1];
+    __shared__ double hs[5][PATCH_H][TILE_W];
+    __shared__ double scratch[32];
+    const int win = f.win, pad = (win - 1) / 2;
+    int64_t bid = blockIdx.x;
+    const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+    const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+    const int64_t s = bid;
+    const int64_t base = slice_base(f, s);
+    const int64_t oy = (int64_t)ty * TILE_H, ox = (int64_t)tx * TILE_W;   // interior coordinates
+    const int ph = TILE_H + win - 1, pw = TILE_W + win - 1;
+    for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
+        int r = e / pw, c = e - r * pw;
+        int64_t h = oy + r, w = ox + c;
+        T va = (T)0, vb = (T)0;
+        if (h < f.H && w < f.W) {
+            int64_t off = base + h * f.sh + w * f.sw;
+            va = a[off];
+            vb = b[off];
+            vb = vb > (T)0 ? vb : (T)0;
+        }
+        pa[r][c] = va;
+        pb[r][c] = vb;
+    }
+    __syncthreads();
+    // horizontal box sums
+    for (int e = threadIdx.x; e < ph * TILE_W; e += blockDim.x) {
+        int r = e / TILE_W, c = e - r * TILE_W;
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        for (int j = 0; j < win; j++) {
+            double x = (double)pa[r][c + j], y = (double)pb[r][c + j];
+            sx += x; sy += y;
+            sxx = fma(x, x, sxx); syy = fma(y, y, syy); sxy = fma(x, y, sxy);
+        }
+        hs[0][r][c] = sx; hs[1][r][c] = sy; hs[2][r][c] = sxx; hs[3][r][c] = syy; hs[4][r][c] = sxy;
+    }
+    __syncthreads();
+    const double R = range[s];
+    const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
+    const double np = (double)(win * win);
+    const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+    const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;   // interior extent
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < TILE_H * TILE_W; e += blockDim.x) {
+        int y = e / TILE_W, x = e - y * TILE_W;
+        if (oy + y >= ih || ox + x >= iw) continue;
+        double v[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            double t = 0.0;
+            for (int i = 0; i < win; i++) t += hs[q][y + i][x];
+            v[q] = t * inv_np;
+        }
+        double ux = v[0], uy = v[1];
+        double vx = cov_norm * (v[2] - ux * ux), vy = cov_norm * (v[3] - uy * uy), vxy = cov_norm * (v[4] - ux * uy);
+        double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
+        double den = (ux * ux + uy * uy + c1) * (vx + vy + c2);
+        acc += num / den;
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// out[fam] = sum(partial[begin..end)) * scale, one CTA per family
+__global__ void __launch_bounds__(256) ssim_final_kernel(const double* __restrict__ partial, const int64_t* __restrict__ bounds,
+                                                          const double* __restrict__ scale, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    const int fam = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t i = bounds[fam] + threadIdx.x; i < bounds[fam + 1]; i += blockDim.x) acc += partial[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[fam] = acc * scale[fam];
+}
+
+// scores[s] = sum of the slice's tile partials * scale, one CTA per slice
+__global__ void __launch_bounds__(128) ssim_slice_kernel(const double* __restrict__ partial, int tiles_per_slice, double scale,
+                                                          double* __restrict__ scores) {
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < tiles_per_slice; i += blockDim.x) acc += partial[(int64_t)blockIdx.x * tiles_per_slice + i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) scores[blockIdx.x] = acc * scale;
+}
+
+template <class T>
+static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, double* scores_host) {
+    NDMPS_TRY(ensure_pinned(ctx, (size_t)f.S + 64));
+    int pad = (f.win - 1) / 2;
+    int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
+    int ty = (int)((ih + TILE_H - 1) / TILE_H), tx = (int)((iw + TILE_W - 1) / TILE_W);
+    int64_t nt = f.S * ty * tx;
+    NDMPS_REQUIRE(nt < (int64_t(1) << 31), "ssim: too many tiles");
+    double *range = nullptr, *partial = nullptr, *scores = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &range));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)nt, &partial));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &scores));
+    ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range);
+    NDMPS_LAUNCH_CHECK(ctx);
+    ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range, ty, tx, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    ssim_slice_kernel<<<(unsigned)f.S, 128, 0, ctx->stream>>>(partial, ty * tx, 1.0 / ((double)ih * (double)iw), scores);
+    NDMPS_LAUNCH_CHECK(ctx);
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, scores, (size_t)f.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(scores_host, ctx->pinned, (size_t)f.S * sizeof(double));
+    return NDMPS_OK;
+}
+
+template <class T>
+static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const SliceFamily* fams, double* out_host) {
+    NDMPS_TRY(ensure_pinned(ctx, 64));
+    int64_t bounds_h[4] = {0, 0, 0, 0};
+    double scale_h[3] = {0, 0, 0};
+    int tiles_y[3], tiles_x[3];
+    int64_t total_tiles = 0, total_slices = 0;
+    for (int k = 0; k < nfam; k++) {
+        const SliceFamily& f = fams[k];
+        int pad = (f.win - 1) / 2;
+        int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
+        tiles_y[k] = (int)((ih + TILE_H - 1) / TILE_H);
+        tiles_x[k] = (int)((iw + TILE_W - 1) / TILE_W);
+        int64_t nt = f.S * tiles_y[k] * tiles_x[k];
+        NDMPS_REQUIRE(nt < (int64_t(1) << 31), "ssim: too many tiles");
+        bounds_h[k] = total_tiles;
+        total_tiles += nt;
+        bounds_h[k + 1] = total_tiles;
+        scale_h[k] = 1.0 / ((double)f.S * (double)ih * (double)iw);
+        total_slices += f.S;
+    }
+    double *range = nullptr, *partial = nullptr, *out_dev = nullptr, *scale_dev = nullptr;
+    int64_t* bounds_dev = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)total_slices, &range));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)total_tiles, &partial));
+    NDMPS_TRY(ctx->ws.get<double>(4, &out_dev));
+    NDMPS_TRY(ctx->ws.get<double>(4, &scale_dev));
+    NDMPS_TRY(ctx->ws.get<int64_t>(4, &bounds_dev));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(bounds_dev, bounds_h, sizeof(bounds_h), cudaMemcpyHostToDevice, ctx->stream));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(scale_dev, scale_h, sizeof(scale_h), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t slice_off = 0;
+    for (int k = 0; k < nfam; k++) {
+        const SliceFamily& f = fams[k];
+        ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
+        NDMPS_LAUNCH_CHECK(ctx);
+        int64_t nt = bounds_h[k + 1] - bounds_h[k];
+        ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
+                                                                  partial + bounds_h[k]);
+        NDMPS_LAUNCH_CHECK(ctx);
+        slice_off += f.S;
+    }
+    ssim_final_kernel<<<nfam, 256, 0, ctx->stream>>>(partial, bounds_dev, scale_dev, out_dev);
+    NDMPS_LAUNCH_CHECK(ctx);
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // also covers the two small H2D copies from the stack
+    double m = 0.0;
+    for (int k = 0; k < nfam; k++) m += ctx->pinned[k];
+    out_host[0] = m / nfam;
+    return NDMPS_OK;
+}
+
+static int pick_win(int64_t h, int64_t w) {
+    int64_t m = h < w ? h : w;
+    int win = (int)(m < 7 ? m : 7);
+    if (win % 2 == 0) win -= 1;
+    return win;
+}
+
+}  // namespace ndmps
+
+using namespace ndmps;
+
+extern "C" {
+
+int ndmps_ssim(ndmps_ctx_t* ctx, const void* a, const void* b, int dtype, int ndim, const int64_t* shape, double* out_host) {
+    NDMPS_REQUIRE(ctx && a && b && shape && out_host, "ndmps_ssim: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype), "ndmps_ssim: bad dtype");
+    NDMPS_REQUIRE(ndim >= 2 && ndim <= 4, "Unsupported tensor dimension for SSIM: %d", ndim);
+    for (int i = 0; i < ndim; i++) NDMPS_REQUIRE(shape[i] >= 1, "ndmps_ssim: non-positive extent");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    SliceFamily fams[3];
+    int nfam = 0;
+    if (ndim == 2) {
+        SliceFamily f{1, shape[0], shape[1], shape[1], 1, 1, 0, 0, pick_win(shape[0], shape[1])};
+        fams[nfam++] = f;
+    } else {
+        const int64_t n0 = shape[0], n1 = shape[1], n2 = shape[2], nT = ndim == 4 ? shape[3] : 1;
+        const int64_t s2 = nT, s1 = n2 * nT, s0 = n1 * n2 * nT;
+        fams[nfam++] = SliceFamily{n0 * nT, n1, n2, s1, s2, nT, s0, 1, pick_win(n1, n2)};   // original[i]
+        fams[nfam++] = SliceFamily{n1 * nT, n0, n2, s0, s2, nT, s1, 1, pick_win(n0, n2)};   // original[:, i, :]
+        fams[nfam++] = SliceFamily{n2 * nT, n0, n1, s0, s1, nT, s2, 1, pick_win(n0, n1)};   // original[:, :, i]
+    }
+    for (int k = 0; k < nfam; k++) {
+        if (fams[k].win < 3) {   // a 1x1 window has no sample covariance: the reference yields NaN
+            out_host[0] = NAN;
+            return NDMPS_OK;
+        }
+    }
+    if (dtype == NDMPS_F32) return ssim_typed<float>(ctx, (const float*)a, (const float*)b, nfam, fams, out_host);
+    return ssim_typed<double>(ctx, (const double*)a, (const double*)b, nfam, fams, out_host);
+}
+
+int ndmps_ssim_slices(ndmps_ctx_t* ctx, const void* a, const void* b, int dtype, const int64_t* shape, int axis,
+                      double* scores_out_host) {
+    NDMPS_REQUIRE(ctx && a && b && shape && scores_out_host, "ndmps_ssim_slices: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype), "ndmps_ssim_slices: bad dtype");
+    NDMPS_REQUIRE(axis >= 0 && axis <= 2, "Invalid axis %d for 3D SSIM.", axis);
+    for (int i = 0; i < 3; i++) NDMPS_REQUIRE(shape[i] >= 1, "ndmps_ssim_slices: non-positive extent");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    const int64_t n0 = shape[0], n1 = shape[1], n2 = shape[2];
+    const int64_t s2 = 1, s1 = n2, s0 = n1 * n2;
+    SliceFamily f;
+    if (axis == 0) f = SliceFamily{n0, n1, n2, s1, s2, 1, s0, 1, pick_win(n1, n2)};
+    else if (axis == 1) f = SliceFamily{n1, n0, n2, s0, s2, 1, s1, 1, pick_win(n0, n2)};
+    else f = SliceFamily{n2, n0, n1, s0, s1, 1, s2, 1, pick_win(n0, n1)};
+    if (f.win < 3) {
+        for (int64_t i = 0; i < f.S; i++) scores_out_host[i] = NAN;
+        return NDMPS_OK;
+    }
+    if (dtype == NDMPS_F32) return ssim_slices_typed<float>(ctx, (const float*)a, (const float*)b, f, scores_out_host);
+    return ssim_slices_typed<double>(ctx, (const double*)a, (const double*)b, f, scores_out_host);
+}
+
+}  // extern "C"

@@ -1,0 +1,580 @@
+// K2-K8 drivers: left -> right TT-SVD sweep, pairwise bond truncation, MPS -> dense
+// contraction and MPS overlap, built from gram / eigh / gemm.
+//
+// Sweep (qtn.MatrixProductState.from_dense at core/ndmps.py:74):
+// step i factorises the unfolding M_i ((r_{i-1} d_i) x C_i).  Here:
+//
+//   * left factor from the Gram matrix G = M M^T (float64 accumulation) and a
+//     float64 Jacobi eigensolve: U = eigenvectors, s = sqrt(lambda); the remainder
+//     is T = U_r^T M (= diag(s) V^T, weight absorbed right as quimb does).
+//   * FRONT MERGING: consecutive sites whose fused row count stays <= merge_cap
+//     share ONE Gram pass and ONE projection pass over the big unfolding.  With
+//     rows (a, s_i, .., s_{i+k-1}) fused, the Gram of sub-step j is
+//         G_j = (P_j (x) I)^T  Tr_rest(G)  (P_j (x) I)
+//     where P_j is the accumulated isometry of the earlier sub-steps and Tr_rest the
+//     partial trace over the not-yet-split row digits, so every core of the group
+//     comes from small float64 algebra on G and the data is read twice in total.
+//     This is exactly the sequential algorithm (truncation and renorm included).
+//   * when an unfolding has more rows than columns (late steps) the Gram is taken
+//     on the column side: G' = M^T M = V s^2 V^T, U = M V / s.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ndmps {
+
+// ---------------------------------------------------------------------------------
+// small float64 glue kernels
+// ---------------------------------------------------------------------------------
+// Gt[x, y] = sum_t G[(x*rest + t), (y*rest + t)]     G: D x D, D = X*rest
+__global__ void __launch_bounds__(256) partial_trace_kernel(const double* __restrict__ G, int64_t D, int64_t X, int64_t rest,
+                                                             double* __restrict__ Gt) {
+    int64_t total = X * X, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t x = i / X, y = i - x * X;
+        double s = 0.0;
+        for (int64_t t = 0; t < rest; t++) s += G[(x * rest + t) * D + (y * rest + t)];
+        Gt[i] = s;
+    }
+}
+
+// K = P (x) I_d : K[(p*d + s), (b*d + s')] = P[p, b] * delta(s, s');  P: pd x r
+__global__ void __launch_bounds__(256) kron_identity_kernel(const double* __restrict__ P, int64_t pd, int64_t r, int64_t d,
+                                                             double* __restrict__ K) {
+    int64_t rows = pd * d, cols = r * d, total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t row = i / cols, col = i - row * cols;
+        int64_t p = row / d, s = row - p * d, b = col / d, s2 = col - b * d;
+        K[i] = s == s2 ? P[p * r + b] : 0.0;
+    }
+}
+
+// per-column scale vector from eigenvalues:  out[j] = f(lambda_j)
+//   mode 0: sqrt(l)   mode 1: 1/sqrt(l)   mode 2: l^(-1/4)   mode 3: l^(-3/4)
+// times `factor`; entries whose sqrt(l) <= floor_rel * sqrt(l_0) give 0 for the inverse modes.
+__global__ void col_scale_kernel(const double* __restrict__ evals, int64_t n, int mode, double factor, double floor_rel,
+                                 double* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double l0 = evals[0] > 0.0 ? evals[0] : 0.0;
+    double l = evals[j] > 0.0 ? evals[j] : 0.0;
+    double s = sqrt(l), s0 = sqrt(l0);
+    double v;
+    if (mode == 0) v = s;
+    else if (s <= floor_rel * s0 || s == 0.0) v = 0.0;
+    else if (mode == 1) v = 1.0 / s;
+    else if (mode == 2) v = 1.0 / sqrt(s);
+    else v = 1.0 / (s * sqrt(s));
+    out[j] = v * factor;
+}
+
+// dst[i, j] = src[i*ld_src + j] * (colscale ? colscale[j] : 1) * (rowscale ? rowscale[i] : 1) * alpha, converted
+template <class T>
+__global__ void __launch_bounds__(256)
+scale_convert_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
+                     const double* __restrict__ rowscale, const double* __restrict__ colscale, double alpha,
+                     T* __restrict__ dst, int64_t ld_dst) {
+    int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t r = i / cols, c = i - r * cols;
+        double v = src[r * ld_src + c] * alpha;
+        if (rowscale) v *= rowscale[r];
+        if (colscale) v *= colscale[c];
+        dst[r * ld_dst + c] = (T)v;
+    }
+}
+
+// dst[j, c] = src[c*ld_src + j] * rowscale[j] * alpha   (j < n rows of dst, c < cols)
+template <class T>
+__global__ void __launch_bounds__(256)
+scaled_transpose_kernel(const double* __restrict__ src, int64_t n, int64_t cols, int64_t ld_src,
+                        const double* __restrict__ rowscale, double alpha, T* __restrict__ dst) {
+    int64_t total = n * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t j = i / cols, c = i - j * cols;
+        dst[i] = (T)(src[c * ld_src + j] * rowscale[j] * alpha);
+    }
+}
+
+template <class TA, class TB>
+__global__ void __launch_bounds__(256) dot_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t n,
+                                                   double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma((double)a[i], (double)b[i], s);
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+static inline int ew_grid(const ndmps_ctx* ctx, int64_t total) {
+    int64_t want = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+static int scale_convert(ndmps_ctx* ctx, const double* src, int64_t rows, int64_t cols, int64_t ld_src,
+                         const double* rowscale, const double* colscale, double alpha, void* dst, int dtype, int64_t ld_dst) {
+    if (rows * cols == 0) return NDMPS_OK;
+    int g = ew_grid(ctx, rows * cols);
+    if (dtype == NDMPS_F32)
+        scale_convert_kernel<float><<<g, 256, 0, ctx->stream>>>(src, rows, cols, ld_src, rowscale, colscale, alpha, (float*)dst, ld_dst);
+    else
+        scale_convert_kernel<double><<<g, 256, 0, ctx->stream>>>(src, rows, cols, ld_src, rowscale, colscale, alpha, (double*)dst, ld_dst);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+static int scaled_transpose(ndmps_ctx* ctx, const double* src, int64_t n, int64_t cols, int64_t ld_src,
+                            const double* rowscale, double alpha, void* dst, int dtype) {
+    if (n * cols == 0) return NDMPS_OK;
+    int g = ew_grid(ctx, n * cols);
+    if (dtype == NDMPS_F32)
+        scaled_transpose_kernel<float><<<g, 256, 0, ctx->stream>>>(src, n, cols, ld_src, rowscale, alpha, (float*)dst);
+    else
+        scaled_transpose_kernel<double><<<g, 256, 0, ctx->stream>>>(src, n, cols, ld_src, rowscale, alpha, (double*)dst);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+static int col_scale(ndmps_ctx* ctx, const double* evals, int64_t n, int mode, double factor, double floor_rel, double* out) {
+    col_scale_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(evals, n, mode, factor, floor_rel, out);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// singular-value trimming on the host (quimb.tensor.decomp semantics, Appendix A.1/A.2)
+// ---------------------------------------------------------------------------------
+static int64_t n_keep(const double* s, int64_t n, double cutoff, int mode, int64_t max_bond) {
+    int64_t keep = n;
+    if (cutoff > 0.0) {
+        if (mode == NDMPS_CUT_ABS) {
+            keep = 0;
+            for (int64_t i = 0; i < n; i++) keep += s[i] > cutoff;
+        } else if (mode == NDMPS_CUT_REL) {
+            keep = 0;
+            for (int64_t i = 0; i < n; i++) keep += s[i] > cutoff * s[0];
+        } else {
+            int pw = (mode == NDMPS_CUT_SUM2 || mode == NDMPS_CUT_RSUM2) ? 2 : 1;
+            bool rel = (mode == NDMPS_CUT_RSUM2 || mode == NDMPS_CUT_RSUM1);
+            double target = cutoff;
+            if (rel) {
+                double tot = 0.0;
+                for (int64_t i = 0; i < n; i++) tot += pw == 2 ? s[i] * s[i] : s[i];
+                target *= tot;
+            }
+            double run = 0.0;
+            keep = n;
+            for (int64_t i = n - 1; i >= 0; i--) {
+                run += pw == 2 ? s[i] * s[i] : s[i];
+                if (run > target) break;
+                keep--;
+            }
+        }
+        if (keep < 1) keep = 1;
+    }
+    if (max_bond > 0 && keep > max_bond) keep = max_bond;
+    return keep;
+}
+
+static double renorm_factor(const double* s, int64_t n, int64_t keep, int power) {
+    if (keep >= n || power <= 0) return 1.0;
+    double k = 0.0, l = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        double v = power == 2 ? s[i] * s[i] : (power == 1 ? s[i] : pow(s[i], power));
+        if (i < keep) k += v; else l += v;
+    }
+    if (!(k > 0.0)) return 1.0;
+    return pow((k + l) / k, 1.0 / power);
+}
+
+// copy n eigenvalues to the host, return sqrt(max(l, 0)) in sv (host vector)
+static int fetch_svals(ndmps_ctx* ctx, const double* evals_dev, int64_t n, std::vector<double>& sv) {
+    NDMPS_TRY(ensure_pinned(ctx, (size_t)n + 64));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, evals_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    sv.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) sv[i] = ctx->pinned[i] > 0.0 ? sqrt(ctx->pinned[i]) : 0.0;
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// the sweep
+// ---------------------------------------------------------------------------------
+struct TrimOpts {
+    double cutoff;
+    int mode;
+    int64_t max_bond;
+    int renorm;
+};
+
+static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int64_t* dims, const TrimOpts& opt,
+                 void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out, double* svals_out,
+                 int64_t svals_stride) {
+    const size_t esz = dtype_size(dtype);
+    int64_t total = 1;
+    for (int i = 0; i < L; i++) total *= dims[i];
+    if (svals_out)
+        for (int64_t i = 0; i < (int64_t)(L - 1) * svals_stride; i++) svals_out[i] = 0.0;
+    if (L == 1) {
+        NDMPS_REQUIRE(core_cap[0] >= total, "ttsvd: core 0 capacity too small");
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(cores_out[0], dense, (size_t)total * esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        return NDMPS_OK;
+    }
+    const void* M = dense;         // current remainder, (r_prev * remaining) elements
+    int64_t r_prev = 1;
+    int64_t remaining = total;     // elements of the remainder divided by r_prev
+    std::vector<double> sv;
+    int site = 0;
+    while (site < L - 1) {
+        // ---- choose the group of sites sharing one Gram pass ----
+        int64_t D = r_prev * dims[site];
+        int64_t C = remaining / dims[site];
+        int k = 1;
+        while (site + k < L - 1) {
+            int64_t Dn = D * dims[site + k], Cn = C / dims[site + k];
+            if (Dn <= ctx->opt_merge_cap && Dn <= Cn) { D = Dn; C = Cn; k++; } else break;
+        }
+        if (ctx->opt_verbose)
+            fprintf(stderr, "[ndmps] sweep site %d: group of %d, unfolding %lld x %lld (%s Gram)\n", site, k,
+                    (long long)D, (long long)C, D <= C ? "row" : "column");
+        int64_t r_out = 0;
+        void* T = nullptr;
+        if (D <= C) {
+            double* G = nullptr;
+            NDMPS_TRY(ctx->ws.get<double>((size_t)(D * D), &G));
+            NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 0, G));
+            double* P = nullptr;       // (pd x rc) accumulated isometry (times renorm factors); nullptr = identity
+            int64_t pd = r_prev, rc = r_prev;
+            for (int j = 0; j < k; j++) {
+                const int64_t d = dims[site + j];
+                const int64_t X = pd * d, rest = D / X, mj = rc * d;
+                double* Gt = G;
+                if (rest > 1) {
+                    NDMPS_TRY(ctx->ws.get<double>((size_t)(X * X), &Gt));
+                    partial_trace_kernel<<<ew_grid(ctx, X * X), 256, 0, ctx->stream>>>(G, D, X, rest, Gt);
+                    NDMPS_LAUNCH_CHECK(ctx);
+                }
+                double* Gj = Gt;
+                double* K = nullptr;
+                if (P != nullptr) {
+                    NDMPS_TRY(ctx->ws.get<double>((size_t)(X * mj), &K));
+                    kron_identity_kernel<<<ew_grid(ctx, X * mj), 256, 0, ctx->stream>>>(P, pd, rc, d, K);
+                    NDMPS_LAUNCH_CHECK(ctx);
+                    double* tmp = nullptr;
+                    NDMPS_TRY(ctx->ws.get<double>((size_t)(X * mj), &tmp));
+                    NDMPS_TRY(gemm(ctx, X, mj, X, 1.0, Gt, NDMPS_F64, X, 1, K, NDMPS_F64, mj, 1, tmp, NDMPS_F64, mj));
+                    NDMPS_TRY(ctx->ws.get<double>((size_t)(mj * mj), &Gj));
+                    NDMPS_TRY(gemm(ctx, mj, mj, X, 1.0, K, NDMPS_F64, 1, mj, tmp, NDMPS_F64, mj, 1, Gj, NDMPS_F64, mj));
+                }
+                double *evals = nullptr, *U = nullptr;
+                NDMPS_TRY(ctx->ws.get<double>((size_t)mj, &evals));
+                NDMPS_TRY(ctx->ws.get<double>((size_t)(mj * mj), &U));
+                NDMPS_TRY(eigh(ctx, Gj, mj, evals, U));
+                NDMPS_TRY(fetch_svals(ctx, evals, mj, sv));
+                // rank of this unfolding is at most min(rows, cols)
+                int64_t cols_j = C * rest;
+                int64_t nmax = mj < cols_j ? mj : cols_j;
+                int64_t n = n_keep(sv.data(), nmax, opt.cutoff, opt.mode, opt.max_bond);
+                double f = renorm_factor(sv.data(), nmax, n, opt.renorm);
+                const int s_idx = site + j;
+                ranks_out[s_idx] = n;
+                if (svals_out)
+                    for (int64_t t = 0; t < n && t < svals_stride; t++) svals_out[(int64_t)s_idx * svals_stride + t] = sv[t] * f;
+                if (core_cap[s_idx] < mj * n) {
+                    set_error("ttsvd: core %d needs %lld elements, capacity %lld", s_idx, (long long)(mj * n), (long long)core_cap[s_idx]);
+                    return NDMPS_ERR_CAPACITY;
+                }
+                NDMPS_TRY(scale_convert(ctx, U, mj, n, mj, nullptr, nullptr, 1.0, cores_out[s_idx], dtype, n));
+                // P_next = f * K * U[:, :n]   (X x n)
+                double* Pn = nullptr;
+                NDMPS_TRY(ctx->ws.get<double>((size_t)(X * n), &Pn));
+                if (K == nullptr) NDMPS_TRY(scale_convert(ctx, U, X, n, mj, nullptr, nullptr, f, Pn, NDMPS_F64, n));
+                else NDMPS_TRY(gemm(ctx, X, n, mj, f, K, NDMPS_F64, mj, 1, U, NDMPS_F64, mj, 1, Pn, NDMPS_F64, n));
+                P = Pn;
+                pd = X;
+                rc = n;
+            }
+            // T = P^T M   (rc x C)
+            r_out = rc;
+            NDMPS_TRY(ctx->ws.alloc((size_t)(r_out * C) * esz, &T));
+            NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, P, NDMPS_F64, 1, r_out, M, dtype, C, 1, T, dtype, C));
+        } else {
+            // more rows than columns: Gram on the column side, G' = M^T M = V s^2 V^T
+            double *G = nullptr, *evals = nullptr, *V = nullptr;
+            NDMPS_TRY(ctx->ws.get<double>((size_t)(C * C), &G));
+            NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 1, G));
+            NDMPS_TRY(ctx->ws.get<double>((size_t)C, &evals));
+            NDMPS_TRY(ctx->ws.get<double>((size_t)(C * C), &V));
+            NDMPS_TRY(eigh(ctx, G, C, evals, V));
+            NDMPS_TRY(fetch_svals(ctx, evals, C, sv));
+            int64_t n = n_keep(sv.data(), C, opt.cutoff, opt.mode, opt.max_bond);
+            double f = renorm_factor(sv.data(), C, n, opt.renorm);
+            ranks_out[site] = n;
+            if (svals_out)
+                for (int64_t t = 0; t < n && t < svals_stride; t++) svals_out[(int64_t)site * svals_stride + t] = sv[t] * f;
+            if (core_cap[site] < D * n) {
+                set_error("ttsvd: core %d needs %lld elements, capacity %lld", site, (long long)(D * n), (long long)core_cap[site]);
+                return NDMPS_ERR_CAPACITY;
+            }
+            double *inv_s = nullptr, *s_f = nullptr, *MV = nullptr;
+            NDMPS_TRY(ctx->ws.get<double>((size_t)C, &inv_s));
+            NDMPS_TRY(ctx->ws.get<double>((size_t)C, &s_f));
+            NDMPS_TRY(col_scale(ctx, evals, C, 1, 1.0, 1e-14, inv_s));
+            NDMPS_TRY(col_scale(ctx, evals, C, 0, f, 0.0, s_f));
+            // U = M V[:, :n] / s   (D x n)
+            NDMPS_TRY(ctx->ws.get<double>((size_t)(D * n), &MV));
+            NDMPS_TRY(gemm(ctx, D, n, C, 1.0, M, dtype, C, 1, V, NDMPS_F64, C, 1, MV, NDMPS_F64, n));
+            NDMPS_TRY(scale_convert(ctx, MV, D, n, n, nullptr, inv_s, 1.0, cores_out[site], dtype, n));
+            // T = f diag(s) V[:, :n]^T   (n x C)
+            r_out = n;
+            NDMPS_TRY(ctx->ws.alloc((size_t)(r_out * C) * esz, &T));
+            NDMPS_TRY(scaled_transpose(ctx, V, n, C, C, s_f, 1.0, T, dtype));
+        }
+        M = T;
+        r_prev = r_out;
+        remaining = C;
+        site += k;
+    }
+    // last core = final remainder (r_{L-2} x d_{L-1})
+    int64_t last = r_prev * dims[L - 1];
+    if (core_cap[L - 1] < last) {
+        set_error("ttsvd: last core needs %lld elements, capacity %lld", (long long)last, (long long)core_cap[L - 1]);
+        return NDMPS_ERR_CAPACITY;
+    }
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(cores_out[L - 1], M, (size_t)last * esz, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// pairwise bond truncation (tensor_compress_bond, Appendix A.2) without QR:
+//   G1 = T1^T T1 = X L X^T,  S1 = L^(1/2) X^T  (so T1 = Q1 S1 with Q1 an isometry)
+//   H  = S1 (T2 T2^T) S1^T = U' s^2 U'^T       (left Gram of S1 T2, same s as R.L)
+//   Y  = S1^T U'[:, :n]
+//   T2' = s^(-1/2) Y^T T2,   T1' = T1 (T2 T2^T) Y s^(-3/2)
+// Only kept singular values are inverted; values below 1e-13 s_0 give zero rows/columns.
+// ---------------------------------------------------------------------------------
+static int compress_bond(ndmps_ctx* ctx, const void* t1, const void* t2, int dtype, int64_t a, int64_t r, int64_t b,
+                         const TrimOpts& opt, void* t1_out, void* t2_out, int64_t* new_rank, double* svals_out) {
+    double *G1 = nullptr, *l1 = nullptr, *X = nullptr, *S1 = nullptr, *G2 = nullptr, *tmp = nullptr, *H = nullptr;
+    double *sig2 = nullptr, *Up = nullptr, *Y = nullptr, *Z = nullptr, *sc = nullptr, *root1 = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &G1));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)r, &l1));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &X));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &S1));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &G2));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &tmp));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &H));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)r, &sig2));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * r), &Up));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)r, &sc));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)r, &root1));
+    NDMPS_TRY(gram(ctx, t1, a, r, r, dtype, 1, G1));
+    NDMPS_TRY(eigh(ctx, G1, r, l1, X));
+    NDMPS_TRY(col_scale(ctx, l1, r, 0, 1.0, 0.0, root1));
+    NDMPS_TRY(scaled_transpose(ctx, X, r, r, r, root1, 1.0, S1, NDMPS_F64));          // S1[i, :] = sqrt(l_i) X[:, i]
+    NDMPS_TRY(gram(ctx, t2, r, b, b, dtype, 0, G2));
+    NDMPS_TRY(gemm(ctx, r, r, r, 1.0, S1, NDMPS_F64, r, 1, G2, NDMPS_F64, r, 1, tmp, NDMPS_F64, r));
+    NDMPS_TRY(gemm(ctx, r, r, r, 1.0, tmp, NDMPS_F64, r, 1, S1, NDMPS_F64, 1, r, H, NDMPS_F64, r));
+    NDMPS_TRY(eigh(ctx, H, r, sig2, Up));
+    std::vector<double> sv;
+    NDMPS_TRY(fetch_svals(ctx, sig2, r, sv));
+    int64_t nmax = r < a ? r : a;
+    if (b < nmax) nmax = b;
+    int64_t n = n_keep(sv.data(), nmax, opt.cutoff, opt.mode, opt.max_bond);
+    double f = renorm_factor(sv.data(), nmax, n, opt.renorm);
+    *new_rank = n;
+    if (svals_out)
+        for (int64_t t = 0; t < r; t++) svals_out[t] = t < n ? sv[t] * f : 0.0;
+    const double rf = sqrt(f);
+    // Y = S1^T U'[:, :n]   (r x n)
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * n), &Y));
+    NDMPS_TRY(gemm(ctx, r, n, r, 1.0, S1, NDMPS_F64, 1, r, Up, NDMPS_F64, r, 1, Y, NDMPS_F64, n));
+    // Z = G2 Y s^(-3/2) sqrt(f)   (r x n), computed before T2 is overwritten
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(r * n), &Z));
+    NDMPS_TRY(gemm(ctx, r, n, r, 1.0, G2, NDMPS_F64, r, 1, Y, NDMPS_F64, n, 1, tmp, NDMPS_F64, n));
+    NDMPS_TRY(col_scale(ctx, sig2, r, 3, rf, 1e-8, sc));
+    NDMPS_TRY(scale_convert(ctx, tmp, r, n, n, nullptr, sc, 1.0, Z, NDMPS_F64, n));
+    // T2' = s^(-1/2) sqrt(f) Y^T T2   (n x b)
+    double* t2tmp = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(n * b), &t2tmp));
+    NDMPS_TRY(gemm(ctx, n, b, r, 1.0, Y, NDMPS_F64, 1, n, t2, dtype, b, 1, t2tmp, NDMPS_F64, b));
+    // T1' = T1 Z   (a x n)
+    void* t1tmp = nullptr;
+    NDMPS_TRY(ctx->ws.alloc((size_t)(a * n) * dtype_size(dtype), &t1tmp));
+    NDMPS_TRY(gemm(ctx, a, n, r, 1.0, t1, dtype, r, 1, Z, NDMPS_F64, n, 1, t1tmp, dtype, n));
+    NDMPS_TRY(col_scale(ctx, sig2, r, 2, rf, 1e-8, sc));
+    NDMPS_TRY(scale_convert(ctx, t2tmp, n, b, b, sc, nullptr, 1.0, t2_out, dtype, b));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(t1_out, t1tmp, (size_t)(a * n) * dtype_size(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// MPS -> dense (cumulative left -> right, Appendix A.3)
+// ---------------------------------------------------------------------------------
+static int contract_dense(ndmps_ctx* ctx, const void* const* cores, int dtype, int L, const int64_t* dims,
+                          const int64_t* ranks, void* dense_out) {
+    const size_t esz = dtype_size(dtype);
+    if (L == 1) {
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(dense_out, cores[0], (size_t)dims[0] * esz, cudaMemcpyDeviceToDevice, ctx->stream));
+        return NDMPS_OK;
+    }
+    const void* X = cores[0];        // (rows x r)
+    int64_t rows = dims[0];
+    for (int k = 1; k < L; k++) {
+        int64_t rin = ranks[k - 1];
+        int64_t rout = k < L - 1 ? ranks[k] : 1;
+        int64_t ncols = dims[k] * rout;
+        void* out = dense_out;
+        if (k < L - 1) NDMPS_TRY(ctx->ws.alloc((size_t)(rows * ncols) * esz, &out));
+        NDMPS_TRY(gemm(ctx, rows, ncols, rin, 1.0, X, dtype, rin, 1, cores[k], dtype, ncols, 1, out, dtype, ncols));
+        X = out;
+        rows *= dims[k];
+    }
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// <a|b> by transfer matrices (float64)
+// ---------------------------------------------------------------------------------
+static int overlap(ndmps_ctx* ctx, const void* const* ca, const int64_t* ra, int da, const void* const* cb,
+                   const int64_t* rb, int db, int L, const int64_t* dims, double* out_dev) {
+    auto dot = [&](const void* x, int dx, const void* y, int dy, int64_t n) -> int {
+        if (dx == NDMPS_F32 && dy == NDMPS_F32) dot_kernel<float, float><<<1, 256, 0, ctx->stream>>>((const float*)x, (const float*)y, n, out_dev);
+        else if (dx == NDMPS_F32) dot_kernel<float, double><<<1, 256, 0, ctx->stream>>>((const float*)x, (const double*)y, n, out_dev);
+        else if (dy == NDMPS_F32) dot_kernel<double, float><<<1, 256, 0, ctx->stream>>>((const double*)x, (const float*)y, n, out_dev);
+        else dot_kernel<double, double><<<1, 256, 0, ctx->stream>>>((const double*)x, (const double*)y, n, out_dev);
+        NDMPS_LAUNCH_CHECK(ctx);
+        return NDMPS_OK;
+    };
+    if (L == 1) return dot(ca[0], da, cb[0], db, dims[0]);
+    // E0 = A0^T B0   (ra0 x rb0)
+    double* E = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(ra[0] * rb[0]), &E));
+    NDMPS_TRY(gemm(ctx, ra[0], rb[0], dims[0], 1.0, ca[0], da, 1, ra[0], cb[0], db, rb[0], 1, E, NDMPS_F64, rb[0]));
+    for (int k = 1; k < L - 1; k++) {
+        int64_t al = ra[k - 1], ar = ra[k], bl = rb[k - 1], br = rb[k], d = dims[k];
+        double *T1 = nullptr, *E2 = nullptr;
+        NDMPS_TRY(ctx->ws.get<double>((size_t)(al * d * br), &T1));
+        // T1 = E (al x bl) . B_k (bl x d*br)
+        NDMPS_TRY(gemm(ctx, al, d * br, bl, 1.0, E, NDMPS_F64, bl, 1, cb[k], db, d * br, 1, T1, NDMPS_F64, d * br));
+        // E' = A_k^T (ar x al*d) . T1 (al*d x br)
+        NDMPS_TRY(ctx->ws.get<double>((size_t)(ar * br), &E2));
+        NDMPS_TRY(gemm(ctx, ar, br, al * d, 1.0, ca[k], da, 1, ar, T1, NDMPS_F64, br, 1, E2, NDMPS_F64, br));
+        E = E2;
+    }
+    // result = sum (E . B_last) o A_last
+    int64_t al = ra[L - 2], bl = rb[L - 2], d = dims[L - 1];
+    double* F = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(al * d), &F));
+    NDMPS_TRY(gemm(ctx, al, d, bl, 1.0, E, NDMPS_F64, bl, 1, cb[L - 1], db, d, 1, F, NDMPS_F64, d));
+    return dot(ca[L - 1], da, F, NDMPS_F64, al * d);
+}
+
+}  // namespace ndmps
+
+using namespace ndmps;
+
+extern "C" {
+
+int ndmps_ttsvd(ndmps_ctx_t* ctx, const void* dense, int dtype, int levels, const int64_t* dims,
+                double cutoff, int cutoff_mode, int64_t max_bond, int renorm,
+                void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out_host,
+                double* svals_out_host, int64_t svals_stride) {
+    NDMPS_REQUIRE(ctx && dense && dims && cores_out && core_cap, "ndmps_ttsvd: NULL argument");
+    NDMPS_REQUIRE(levels >= 1 && dtype_ok(dtype), "ndmps_ttsvd: bad levels or dtype");
+    NDMPS_REQUIRE(levels == 1 || ranks_out_host, "ndmps_ttsvd: ranks_out_host is NULL");
+    NDMPS_REQUIRE(cutoff_mode >= NDMPS_CUT_ABS && cutoff_mode <= NDMPS_CUT_RSUM1, "ndmps_ttsvd: bad cutoff_mode %d", cutoff_mode);
+    for (int i = 0; i < levels; i++) NDMPS_REQUIRE(dims[i] >= 1 && cores_out[i], "ndmps_ttsvd: bad dims or core pointer at %d", i);
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
+    NDMPS_TRY(ttsvd(ctx, dense, dtype, levels, dims, opt, cores_out, core_cap, ranks_out_host, svals_out_host, svals_stride));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return NDMPS_OK;
+}
+
+int ndmps_compress_bond(ndmps_ctx_t* ctx, const void* t1, const void* t2, int dtype, int64_t a, int64_t r, int64_t b,
+                        double cutoff, int cutoff_mode, int64_t max_bond, int renorm,
+                        void* t1_out, void* t2_out, int64_t* new_rank_host, double* svals_out_host) {
+    NDMPS_REQUIRE(ctx && t1 && t2 && t1_out && t2_out && new_rank_host, "ndmps_compress_bond: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && a >= 1 && r >= 1 && b >= 1, "ndmps_compress_bond: bad shape or dtype");
+    NDMPS_REQUIRE(cutoff_mode >= NDMPS_CUT_ABS && cutoff_mode <= NDMPS_CUT_RSUM1, "ndmps_compress_bond: bad cutoff_mode %d", cutoff_mode);
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
+    NDMPS_TRY(compress_bond(ctx, t1, t2, dtype, a, r, b, opt, t1_out, t2_out, new_rank_host, svals_out_host));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return NDMPS_OK;
+}
+
+int ndmps_contract_dense(ndmps_ctx_t* ctx, const void* const* cores, int dtype, int levels, const int64_t* dims,
+                         const int64_t* ranks, void* dense_out) {
+    NDMPS_REQUIRE(ctx && cores && dims && dense_out, "ndmps_contract_dense: NULL argument");
+    NDMPS_REQUIRE(levels >= 1 && dtype_ok(dtype), "ndmps_contract_dense: bad levels or dtype");
+    NDMPS_REQUIRE(levels == 1 || ranks, "ndmps_contract_dense: ranks is NULL");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    return contract_dense(ctx, cores, dtype, levels, dims, ranks, dense_out);
+}
+
+int ndmps_overlap(ndmps_ctx_t* ctx, const void* const* cores_a, const int64_t* ranks_a, int dtype_a,
+                  const void* const* cores_b, const int64_t* ranks_b, int dtype_b, int levels, const int64_t* dims,
+                  double* out_host) {
+    NDMPS_REQUIRE(ctx && cores_a && cores_b && dims && out_host, "ndmps_overlap: NULL argument");
+    NDMPS_REQUIRE(levels >= 1 && dtype_ok(dtype_a) && dtype_ok(dtype_b), "ndmps_overlap: bad levels or dtype");
+    NDMPS_REQUIRE(levels == 1 || (ranks_a && ranks_b), "ndmps_overlap: ranks is NULL");
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    NDMPS_TRY(ensure_pinned(ctx, 2));
+    double* out_dev = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
+    NDMPS_TRY(overlap(ctx, cores_a, ranks_a, dtype_a, cores_b, ranks_b, dtype_b, levels, dims, out_dev));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out_host[0] = ctx->pinned[0];
+    return NDMPS_OK;
+}
+
+int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void* src_host, void* dst_host, int dtype,
+                         double cutoff, int cutoff_mode, int64_t max_bond, int renorm, int64_t* ranks_out_host) {
+    NDMPS_REQUIRE(ctx && plan && src_host && dst_host, "ndmps_roundtrip_host: NULL argument");
+    NDMPS_REQUIRE(dtype_ok(dtype), "ndmps_roundtrip_host: bad dtype");
+    NDMPS_REQUIRE(cutoff_mode >= NDMPS_CUT_ABS && cutoff_mode <= NDMPS_CUT_RSUM1, "ndmps_roundtrip_host: bad cutoff_mode %d", cutoff_mode);
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    const int L = plan->levels;
+    const int64_t N = plan->total;
+    const size_t esz = dtype_size(dtype);
+    void *vol = nullptr, *dense = nullptr;
+    NDMPS_TRY(ctx->ws.alloc((size_t)N * esz, &vol));
+    NDMPS_TRY(ctx->ws.alloc((size_t)N * esz, &dense));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(vol, src_host, (size_t)N * esz, cudaMemcpyHostToDevice, ctx->stream));
+    NDMPS_TRY(permute(ctx, plan, false, vol, dense, dtype, 1.0));
+    // core capacities from the bond bounds min(max_bond, prod left, prod right)
+    std::vector<int64_t> bound((size_t)(L > 1 ? L - 1 : 0)), cap((size_t)L), ranks((size_t)(L > 1 ? L - 1 : 1));
+    std::vector<void*> cores((size_t)L);
+    {
+        double left = 1.0;
+        for (int i = 0; i < L - 1; i++) {
+            left *= (double)plan->site_dims[i];
+            double right = 1.0;
+            for (int j = i + 1; j < L; j++) right *= (double)plan->site_dims[j];
+            double bd = left < right ? left : right;
+            if (max_bond > 0 && (double)max_bond < bd) bd = (double)max_bond;
+            bound[(size_t)i] = (int64_t)bd;
+        }
+        for (int i = 0; i < L; i++) {
+            int64_t l = i == 0 ? 1 : bound[(size_t)i - 1], r = i == L - 1 ? 1 : bound[(size_t)i];
+            // a bond can never exceed (left bond * d): tighten so lossless capacities stay finite
+            cap[(size_t)i] = l * plan->site_dims[i] * r;
+            NDMPS_TRY(ctx->ws.alloc((size_t)cap[(size_t)i] * esz, &cores[(size_t)i]));
+        }
+    }
+    TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
+    NDMPS_TRY(ttsvd(ctx, dense, dtype, L, plan->site_dims, opt, cores.data(), cap.data(), ranks.data(), nullptr, 0));
+    if (ranks_out_host)
+        for (int i = 0; i < L - 1; i++) ranks_out_host[i] = ranks[(size_t)i];
+    NDMPS_TRY(contract_dense(ctx, (const void* const*)cores.data(), dtype, L, plan->site_dims, ranks.data(), dense));
+    NDMPS_TRY(permute(ctx, plan, true, dense, vol, dtype, 1.0));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return NDMPS_OK;
+}
+
+}  // extern "C"
