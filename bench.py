@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: NDMPS encode + truncate-to-chi + reconstruct voxels/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg3] [--chi 64]
+
+A step is one pass of the hot path over one synthetic volume:
+``NDMPS.from_tensor(vol, max_bond=chi)`` (permute to site order, TT-SVD sweep, boundary
+list, norm) followed by ``to_tensor`` (contract, inverse permute).  Default workload is
+BASELINE.json configs[1]: a 256^3 float32 synthetic MRI volume at chi = 64; ``cfg3`` is
+the 512^3 volume of the north-star target.
+
+* ``value``  : device-resident - the volume already sits in HBM, the reconstruction stays
+  in HBM.  K steps timed with CUDA events, L2 flushed between steps (outside the event
+  pairs), barrier + synchronize on both sides, max over ranks.
+* ``e2e``    : the same step through the C ABI on HOST buffers (``ndmps_roundtrip_host``:
+  H2D copy, encode, sweep, contract, decode, D2H copy inside the timed region).
+* N > 1     : one process per GPU (torchrun); every rank runs the whole path on its own
+  volume - independent volumes shard with no data-path collective (weak scaling).
+* ``--impl reference``: the CPU oracle (numpy/LAPACK float64 restatement of the reference
+  path - the reference itself cannot be imported without quimb / scikit-image) on a bounded
+  sample, all host threads, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "img-compression-mps_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "ndmps_encode_truncate_reconstruct_voxels_per_s"
+UNIT = "voxels/s"
+WORKLOADS = {
+    "cfg2": {"shape": (256, 256, 256), "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume"},
+    "cfg3": {"shape": (512, 512, 512), "name": "configs[2]: 512x512x512 fp32 synthetic volume (north-star target)"},
+}
+CPU_SAMPLE_SHAPE = (128, 128, 128)
+
+
+def synthetic_volume(shape, seed):
+    """Ellipsoid phantom + smooth texture + 0.02 noise inside the object, exact-zero background
+    (SURVEY section 8d).  Built per z-slab to keep host memory flat."""
+    rng = np.random.default_rng(seed)
+    params = [(rng.uniform(-0.25, 0.25, 3), rng.uniform(0.35, 0.8, 3) * (1.0 - 0.18 * k), 0.25 + 0.1 * k) for k in range(4)]
+    axes = [np.linspace(-1, 1, n, dtype=np.float32) for n in shape]
+    out = np.empty(shape, dtype=np.float32)
+    gy, gz = np.meshgrid(axes[1], axes[2], indexing="ij")
+    for i, xv in enumerate(axes[0]):
+        sl = np.zeros(shape[1:], dtype=np.float32)
+        for c, r, amp in params:
+            r2 = ((xv - c[0]) / r[0]) ** 2 + ((gy - c[1]) / r[1]) ** 2 + ((gz - c[2]) / r[2]) ** 2
+            sl += amp / (1.0 + np.exp(np.clip((r2 - 1.0) * 12.0, -60, 60)))
+        inside = sl > 0.05
+        sl += 0.05 * np.cos(3 * xv) * np.cos(3 * gy + 1) * np.cos(3 * gz + 2) * inside
+        sl += 0.02 * rng.random(shape[1:], dtype=np.float32) * inside
+        sl[sl < 0.02] = 0.0
+        out[i] = sl
+    return out
+
+
+def algorithmic_work(dims, ranks):
+    """Bytes / flops of the stages per SURVEY section 8(d) for float32 payloads (4 B)."""
+    L, n = len(dims), int(np.prod(dims))
+    r = [1] + list(ranks) + [1]
+    sweep_bytes = gram_flops = proj_flops = 0.0
+    cols = n
+    for i in range(L - 1):
+        m = r[i] * dims[i]
+        cols //= dims[i]
+        sweep_bytes += 4.0 * (2 * m * cols + r[i + 1] * cols)
+        gram_flops += 2.0 * m * m * cols
+        proj_flops += 2.0 * m * r[i + 1] * cols
+    recon_bytes = recon_flops = 0.0
+    p = 1
+    for k in range(L):
+        recon_bytes += 4.0 * (p * r[k] + p * dims[k] * r[k + 1])
+        recon_flops += 2.0 * p * r[k] * dims[k] * r[k + 1]
+        p *= dims[k]
+    return {"encode_bytes": 8.0 * n, "decode_bytes": 8.0 * n, "sweep_bytes": sweep_bytes, "gram_flops": gram_flops,
+            "project_flops": proj_flops, "recon_bytes": recon_bytes, "recon_flops": recon_flops}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(sample, chi, repeats):
+    """voxels/s of the CPU oracle (numpy float64, LAPACK gesdd, all BLAS threads) on `sample`."""
+    from oracle.ndmps import OracleNDMPS
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        OracleNDMPS.from_tensor(sample, max_bond=chi).to_tensor()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample.size / best, best
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    sample = synthetic_volume(CPU_SAMPLE_SHAPE, 2026)
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(sample, args.chi, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_rate(sample, args.chi, 1)
+    dt = time.perf_counter() - t0
+    value = sample.size * args.steps / dt
+    cores = host_threads()
+    sample_txt = (f"{'x'.join(map(str, CPU_SAMPLE_SHAPE))} float32 phantom of the same family per step (bounded sample "
+                  f"of {wl['name']}), from_tensor(max_bond={args.chi}) + to_tensor, numpy/LAPACK float64")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "chi": args.chi, "mode": "Std", "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be imported (quimb, scikit-image absent): oracle port timed on host cores",
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from imgcompressionmps import _native, _ops
+    from imgcompressionmps.core.ndmps import NDMPS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for --impl ours")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[args.workload]
+    shape = wl["shape"]
+    nvox = int(np.prod(shape))
+    host = synthetic_volume(shape, 2026 + rank)                    # every rank its own volume
+    pinned = torch.from_numpy(host).pin_memory()
+    vol = pinned.cuda(non_blocking=False)
+    ctx = _native.context()
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step():
+        obj = NDMPS.from_tensor(vol, max_bond=args.chi)
+        rec = obj.to_tensor_device()
+        return obj, rec
+
+    for _ in range(max(args.warmup, 3)):
+        obj, rec = step()
+    torch.cuda.synchronize()
+    ranks = obj.bond_sizes()
+    dims = obj.mps.site_dims
+    err = float(torch.linalg.vector_norm((rec - vol).double()) / torch.linalg.vector_norm(vol.double()))
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ctx.profile(True)
+    ctx.stage_times(reset=True)
+    launches0 = ctx.launch_count()
+    barrier()
+    with ClockSampler(local) as clocks:
+        for i in range(args.steps):
+            flush_buf.fill_(i & 0xFF)                                # evict L2 (outside the event pair)
+            starts[i].record()
+            step()
+            stops[i].record()
+        barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    launches = ctx.launch_count() - launches0
+    stages = ctx.stage_times(reset=True)
+    ctx.profile(False)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * nvox * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI on host buffers ----------------------------------------------
+    src = pinned.numpy()
+    dst = torch.empty_like(pinned).pin_memory().numpy()
+    for _ in range(2):
+        _ops.roundtrip_host(src, max_bond=args.chi, out=dst)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _ops.roundtrip_host(src, max_bond=args.chi, out=dst)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * nvox * args.steps / e2e_s
+    e2e_err = float(np.linalg.norm(dst.astype(np.float64) - src) / np.linalg.norm(src.astype(np.float64)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the stages (algorithmic work / measured device time) ---------------------------
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        m = json.loads(pk.read_text())
+        peaks = {"hbm_gbs": m["hbm_gbs"], "bf16_tflops": m.get("bf16_tflops_sustained", m["bf16_tflops"]), "source": "measured"}
+    work = algorithmic_work(dims, ranks)
+    per_step = {k: (v[0] / args.steps, v[1] // max(args.steps, 1)) for k, v in stages.items()}
+    step_ms = total_ms / args.steps
+    shares = {k: round(v[0] / step_ms, 4) for k, v in per_step.items() if v[1]}
+    gram_ms, gram_calls = per_step["gram"]
+    perm_ms, perm_calls = per_step["permute"]
+    rooflines = {}
+    if gram_calls:
+        ach = work["gram_flops"] / (gram_ms * 1e-3) / 1e12
+        rooflines["gram"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": ach / peaks["bf16_tflops"], "traffic": None, "ms_per_step": gram_ms,
+                             "launch_groups_per_step": gram_calls}
+    if perm_calls:
+        ach = (work["encode_bytes"] + work["decode_bytes"]) / (perm_ms * 1e-3) / 1e9
+        rooflines["permute"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_step": perm_ms,
+                                "launches_per_step": perm_calls}
+    dominant = max(shares, key=shares.get) if shares else None
+    roof = dict(rooflines.get("gram") or rooflines.get("permute") or {})
+    roof.update({"kernel": "gram (float64-accumulate SIMT, fp32-equivalent flops)", "peak_source": peaks["source"],
+                 "dominant_stage_by_time": dominant, "stage_share_of_step": shares, "all": rooflines})
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "shape": list(shape), "chi": args.chi, "mode": "Std", "site_dims": dims,
+                   "bond_dims": ranks, "volumes_per_gpu": 1, "l2_flush_between_steps": True,
+                   "parallelism": f"{world} independent volume(s), one per GPU, no data-path collective",
+                   "reconstruction_rel_error_vs_input": err},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvox * 4, "d2h_bytes_per_step": nvox * 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "entry": "ndmps_roundtrip_host (C ABI, pinned host buffers)",
+                "reconstruction_rel_error_vs_input": e2e_err},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "stage_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items() if v[1]},
+    }
+    if world == 1 and not args.no_cpu:
+        sample = synthetic_volume(CPU_SAMPLE_SHAPE, 2026)
+        rate, best = cpu_oracle_rate(sample, args.chi, 3)
+        result["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": host_threads(), "kind": "port",
+            "sample": f"{'x'.join(map(str, CPU_SAMPLE_SHAPE))} float32 phantom (bounded sample of the workload), "
+                      f"from_tensor(max_bond={args.chi}) + to_tensor, numpy/LAPACK float64, best of 3 ({best:.2f} s)"}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chi", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,22 @@ int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
     return NDMPS_OK;
 }
 
+int profile_collect(ndmps_ctx* ctx) {
+    if (ctx->pending.empty()) return NDMPS_OK;
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.beg, p.end) == cudaSuccess) {
+            ctx->stage_ms[p.stage] += ms;
+            ctx->stage_calls[p.stage] += 1;
+        }
+        cudaEventDestroy(p.beg);
+        cudaEventDestroy(p.end);
+    }
+    ctx->pending.clear();
+    return NDMPS_OK;
+}
+
 }  // namespace ndmps
 
 using namespace ndmps;
@@ -125,6 +141,30 @@ int ndmps_ctx_sync(ndmps_ctx_t* ctx) {
 }
 
 int64_t ndmps_ctx_launch_count(const ndmps_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+static const char* kStageNames[ST_COUNT] = {"permute", "gram", "eig", "project", "glue", "contract", "dct", "metric"};
+
+int ndmps_ctx_profile(ndmps_ctx_t* ctx, int enable) {
+    NDMPS_REQUIRE(ctx != nullptr, "ndmps_ctx_profile: ctx is NULL");
+    NDMPS_TRY(profile_collect(ctx));
+    ctx->profile = enable != 0;
+    return NDMPS_OK;
+}
+
+int ndmps_stage_count(void) { return ST_COUNT; }
+
+const char* ndmps_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? kStageNames[stage] : ""; }
+
+int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, int reset) {
+    NDMPS_REQUIRE(ctx && ms_out && calls_out, "ndmps_ctx_stage_times: NULL argument");
+    NDMPS_TRY(profile_collect(ctx));
+    for (int i = 0; i < ST_COUNT; i++) {
+        ms_out[i] = ctx->stage_ms[i];
+        calls_out[i] = ctx->stage_calls[i];
+        if (reset) { ctx->stage_ms[i] = 0.0; ctx->stage_calls[i] = 0; }
+    }
+    return NDMPS_OK;
+}
 
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     NDMPS_REQUIRE(ctx != nullptr && name != nullptr, "ndmps_ctx_set_option: NULL argument");

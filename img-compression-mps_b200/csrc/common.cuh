@@ -91,6 +91,9 @@ struct Arena {
 
 }  // namespace ndmps
 
+// ---- per-stage device timing (CUDA events on the launching stream; off by default) ----
+enum NdmpsStage { ST_PERMUTE = 0, ST_GRAM, ST_EIG, ST_PROJECT, ST_GLUE, ST_CONTRACT, ST_DCT, ST_METRIC, ST_COUNT };
+
 struct ndmps_ctx {
     cudaStream_t stream = nullptr;
     ndmps::Arena ws;
@@ -109,11 +112,36 @@ struct ndmps_ctx {
     int64_t opt_verbose = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;
+    // stage profiler
+    bool profile = false;
+    struct Pending { int stage; cudaEvent_t beg, end; };
+    std::vector<Pending> pending;
+    double stage_ms[ST_COUNT] = {0};
+    int64_t stage_calls[ST_COUNT] = {0};
 };
 
 namespace ndmps {
 
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
+
+// RAII stage marker: records an event pair around a leaf stage when profiling is on
+struct StageScope {
+    ndmps_ctx* ctx;
+    cudaEvent_t beg = nullptr, end = nullptr;
+    int stage;
+    StageScope(ndmps_ctx* c, int st) : ctx(c), stage(st) {
+        if (!ctx->profile) return;
+        cudaEventCreate(&beg);
+        cudaEventCreate(&end);
+        cudaEventRecord(beg, ctx->stream);
+    }
+    ~StageScope() {
+        if (!beg) return;
+        cudaEventRecord(end, ctx->stream);
+        ctx->pending.push_back({stage, beg, end});
+    }
+};
+int profile_collect(ndmps_ctx* ctx);
 
 static inline size_t dtype_size(int dtype) { return dtype == NDMPS_F64 ? 8 : 4; }
 static inline bool dtype_ok(int dtype) { return dtype == NDMPS_F32 || dtype == NDMPS_F64; }

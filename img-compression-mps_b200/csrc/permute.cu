@@ -108,6 +108,7 @@ static int permute_typed(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, c
 }
 
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale) {
+    StageScope sc(ctx, ST_PERMUTE);
     if (dtype == NDMPS_F32) return permute_typed<float>(ctx, plan, inverse, (const float*)src, (float*)dst, scale);
     return permute_typed<double>(ctx, plan, inverse, (const double*)src, (double*)dst, scale);
 }

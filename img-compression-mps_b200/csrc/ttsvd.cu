@@ -243,7 +243,7 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
         if (D <= C) {
             double* G = nullptr;
             NDMPS_TRY(ctx->ws.get<double>((size_t)(D * D), &G));
-            NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 0, G));
+            { StageScope sc(ctx, ST_GRAM); NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 0, G)); }
             double* P = nullptr;       // (pd x rc) accumulated isometry (times renorm factors); nullptr = identity
             int64_t pd = r_prev, rc = r_prev;
             for (int j = 0; j < k; j++) {
@@ -270,7 +270,7 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
                 double *evals = nullptr, *U = nullptr;
                 NDMPS_TRY(ctx->ws.get<double>((size_t)mj, &evals));
                 NDMPS_TRY(ctx->ws.get<double>((size_t)(mj * mj), &U));
-                NDMPS_TRY(eigh(ctx, Gj, mj, evals, U));
+                { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, Gj, mj, evals, U)); }
                 NDMPS_TRY(fetch_svals(ctx, evals, mj, sv));
                 // rank of this unfolding is at most min(rows, cols)
                 int64_t cols_j = C * rest;
@@ -298,15 +298,15 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             // T = P^T M   (rc x C)
             r_out = rc;
             NDMPS_TRY(ctx->ws.alloc((size_t)(r_out * C) * esz, &T));
-            NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, P, NDMPS_F64, 1, r_out, M, dtype, C, 1, T, dtype, C));
+            { StageScope sc(ctx, ST_PROJECT); NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, P, NDMPS_F64, 1, r_out, M, dtype, C, 1, T, dtype, C)); }
         } else {
             // more rows than columns: Gram on the column side, G' = M^T M = V s^2 V^T
             double *G = nullptr, *evals = nullptr, *V = nullptr;
             NDMPS_TRY(ctx->ws.get<double>((size_t)(C * C), &G));
-            NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 1, G));
+            { StageScope sc(ctx, ST_GRAM); NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 1, G)); }
             NDMPS_TRY(ctx->ws.get<double>((size_t)C, &evals));
             NDMPS_TRY(ctx->ws.get<double>((size_t)(C * C), &V));
-            NDMPS_TRY(eigh(ctx, G, C, evals, V));
+            { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, G, C, evals, V)); }
             NDMPS_TRY(fetch_svals(ctx, evals, C, sv));
             int64_t n = n_keep(sv.data(), C, opt.cutoff, opt.mode, opt.max_bond);
             double f = renorm_factor(sv.data(), C, n, opt.renorm);
@@ -419,6 +419,7 @@ static int contract_dense(ndmps_ctx* ctx, const void* const* cores, int dtype, i
         NDMPS_CUDA_TRY(cudaMemcpyAsync(dense_out, cores[0], (size_t)dims[0] * esz, cudaMemcpyDeviceToDevice, ctx->stream));
         return NDMPS_OK;
     }
+    StageScope sc(ctx, ST_CONTRACT);
     const void* X = cores[0];        // (rows x r)
     int64_t rows = dims[0];
     for (int k = 1; k < L; k++) {

@@ -36,6 +36,10 @@ PROTOTYPES = {
     "ndmps_ctx_sync": (ci, [vp]),
     "ndmps_ctx_launch_count": (i64, [vp]),
     "ndmps_ctx_set_option": (ci, [vp, C.c_char_p, i64]),
+    "ndmps_ctx_profile": (ci, [vp, ci]),
+    "ndmps_stage_count": (ci, []),
+    "ndmps_stage_name": (C.c_char_p, [ci]),
+    "ndmps_ctx_stage_times": (ci, [vp, p_f64, p_i64, ci]),
     "ndmps_plan_create": (ci, [ci, p_i64, ci, p_i64, p_vp]),
     "ndmps_plan_destroy": (ci, [vp]),
     "ndmps_plan_site_dims": (ci, [vp, p_i64]),
@@ -126,6 +130,17 @@ class Context:
 
     def set_option(self, name: str, value: int):
         check(self.lib.ndmps_ctx_set_option(self.handle, name.encode(), int(value)), "ndmps_ctx_set_option")
+
+    def profile(self, enable: bool):
+        check(self.lib.ndmps_ctx_profile(self.handle, int(bool(enable))), "ndmps_ctx_profile")
+
+    def stage_times(self, reset: bool = True) -> dict:
+        """{stage: (ms, calls)} accumulated since the last reset (device time, CUDA events)."""
+        n = self.lib.ndmps_stage_count()
+        ms = (C.c_double * n)()
+        calls = (C.c_int64 * n)()
+        check(self.lib.ndmps_ctx_stage_times(self.handle, ms, calls, int(bool(reset))), "ndmps_ctx_stage_times")
+        return {self.lib.ndmps_stage_name(i).decode(): (ms[i], int(calls[i])) for i in range(n)}
 
     def launch_count(self) -> int:
         return int(self.lib.ndmps_ctx_launch_count(self.handle))

@@ -62,6 +62,13 @@ int ndmps_ctx_set_stream(ndmps_ctx_t* ctx, void* cuda_stream);
 int ndmps_ctx_sync(ndmps_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ndmps_ctx_launch_count(const ndmps_ctx_t* ctx);
+/* per-stage device time (CUDA events on the context's stream).  profile(1) turns the
+ * event pairs on; stage_times() synchronises and returns accumulated ms / call counts
+ * for the ndmps_stage_count() stages named by ndmps_stage_name(). */
+int ndmps_ctx_profile(ndmps_ctx_t* ctx, int enable);
+int ndmps_stage_count(void);
+const char* ndmps_stage_name(int stage);
+int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, int reset);
 /* tuning knobs, e.g. "gram_path" 0=SIMT f64 1=tcgen05 split-TF32, "jacobi_block" */
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value);
 

@@ -43,8 +43,9 @@ class OracleNDMPS:
             tensor = dct(tensor, type=2, axis=-1, norm="ortho")
         dense = enc.encode(tensor)
         dims = list(dense.shape)
-        cores = M.tt_svd(dense, dims, cutoff=cutoff, max_bond=max_bond)
+        cores, svals = M.tt_svd(dense, dims, cutoff=cutoff, max_bond=max_bond, return_svals=True)
         obj = cls(cores, np.array(dims), shape, norm, None, mode, [[c.min(), c.max()] for c in cores])
+        obj.singular_values = svals
         obj.update_norm()
         return obj
 

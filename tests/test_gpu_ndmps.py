@@ -1,0 +1,233 @@
+"""The reference's own tests/core/test_ndmps.py, run against the B200 drop-in through
+the same import path, plus parity of the whole path against the oracle: bond
+dimensions and compression ratios exact, singular values and reconstructions within
+1e-5 relative (float32), SSIM / PSNR / fidelity within 1e-4 (BASELINE.json north_star)."""
+import copy
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from conftest import phantom                              # noqa: E402
+from oracle import metrics as OM                          # noqa: E402
+from oracle import mps as OMPS                            # noqa: E402
+from oracle.ndmps import OracleNDMPS                      # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def NDMPS():
+    from imgcompressionmps.core.ndmps import NDMPS
+    return NDMPS
+
+
+# ---------------------------------------------------------------------------------------------
+# mirror of the reference's tests/core/test_ndmps.py (float64 inputs -> float64 path)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rng():
+    return np.random.default_rng(2025)
+
+
+@pytest.fixture(scope="module", params=[(512, 680), (8, 512, 680)], ids=lambda s: f"shape={s}")
+def tensor(request, rng):
+    return rng.random(request.param)
+
+
+@pytest.fixture(params=["Std", "DCT"])
+def mode(request):
+    return request.param
+
+
+@pytest.fixture
+def ndmps_obj(NDMPS, tensor, mode):
+    return NDMPS.from_tensor(tensor, norm=False, mode=mode)
+
+
+def test_roundtrip_exact(ndmps_obj, tensor):
+    out = ndmps_obj.to_tensor()
+    assert np.allclose(out, tensor, atol=1e-10), f"Round-trip mismatch {np.abs(out - tensor).max()}"
+
+
+def test_norm_option(NDMPS, tensor):
+    obj = NDMPS.from_tensor(tensor, norm=True)
+    assert math.isclose(obj.norm_value, 1.0, rel_tol=1e-12)
+
+
+def test_compression_reduces_elements(ndmps_obj):
+    before = ndmps_obj.number_elements_in_MPS()
+    ndmps_obj.compress(cutoff=0.1)
+    assert ndmps_obj.number_elements_in_MPS() < before
+
+
+def test_boundary_and_norm_refresh(ndmps_obj):
+    ndmps_obj.mps.arrays[0][:] *= 10
+    ndmps_obj.update_boundary_list()
+    ndmps_obj.update_norm()
+    new_min, new_max = ndmps_obj.boundary_list[0]
+    assert new_min <= np.min(ndmps_obj.mps.arrays[0]) and new_max >= np.max(ndmps_obj.mps.arrays[0])
+    assert math.isclose(ndmps_obj.norm_value ** 2, ndmps_obj.mps @ ndmps_obj.mps, rel_tol=1e-12)
+
+
+def test_disk_compression_ratio(ndmps_obj):
+    ndmps_obj.compress(cutoff=0.4)
+    r = ndmps_obj.compression_ratio_on_disk(dtype=np.uint16, replace=False)
+    assert 0 < r < 1
+
+
+def test_continuous_compress_prints(ndmps_obj, capsys):
+    ndmps_obj.continuous_compress(cutoff=0.05, print_ratio=True)
+    assert capsys.readouterr().out.count("Compression ratio at") == 20
+
+
+# ---------------------------------------------------------------------------------------------
+# parity against the oracle
+# ---------------------------------------------------------------------------------------------
+def test_appendix_a4_probe_parity(NDMPS, rng):
+    """Same numbers as the oracle's probe table (bond dims exact, gzip ratio to 2 decimals)."""
+    x = np.random.default_rng(2025).random((512, 680))
+    g = NDMPS.from_tensor(x)
+    o = OracleNDMPS.from_tensor(x)
+    assert g.bond_sizes() == o.bond_sizes() == [34, 512, 64, 8]
+    assert g.number_elements_in_MPS() == o.number_elements_in_MPS()
+    assert g.compression_ratio() == o.compression_ratio()
+    for cutoff in (0.1, 0.4):
+        gc, oc = copy.deepcopy(g), copy.deepcopy(o)
+        gc.compress(cutoff)
+        oc.compress(cutoff)
+        assert gc.bond_sizes() == oc.bond_sizes(), cutoff
+        assert gc.compression_ratio() == oc.compression_ratio()
+        assert gc.norm_value == pytest.approx(oc.norm_value, rel=1e-9)
+        for sg, so in zip(gc.singular_values, oc.last_svals):
+            assert np.allclose(sg, so, rtol=0, atol=1e-9 * so[0])
+        assert np.allclose(gc.to_tensor(), oc.to_tensor(), atol=1e-8)
+        assert gc.compression_ratio_on_disk() == pytest.approx(oc.compression_ratio_on_disk(), rel=0.02)
+
+
+CASES = [((64, 64), 16, "Std"), ((256, 256), 32, "Std"), ((32, 32, 32), 16, "Std"), ((64, 64, 64), 32, "Std"),
+         ((48, 40, 36), 12, "Std"), ((16, 16, 8, 20), 8, "Std"), ((64, 64, 64), 32, "DCT"), ((30, 40, 50), 10, "DCT")]
+
+
+@pytest.mark.parametrize("shape,chi,mode", CASES, ids=lambda v: str(v).replace(" ", ""))
+def test_fixed_chi_parity_float32(NDMPS, shape, chi, mode):
+    x = phantom(shape, seed=2026).astype(np.float32)
+    g = NDMPS.from_tensor(x, mode=mode, max_bond=chi)
+    o = OracleNDMPS.from_tensor(x, mode=mode, max_bond=chi)
+    assert g.mps.dtype == torch.float32
+    assert g.bond_sizes() == o.bond_sizes()
+    assert g.number_elements_in_MPS() == o.number_elements_in_MPS()
+    assert g.compression_ratio() == o.compression_ratio()
+    for sg, so in zip(g.singular_values, o.singular_values):
+        assert np.allclose(sg, so, rtol=0, atol=1e-5 * so[0])               # singular values: 1e-5 relative
+    rg, ro = g.to_tensor().astype(np.float64), o.to_tensor()
+    rel = np.linalg.norm(rg - ro) / np.linalg.norm(ro)
+    print(f"{shape} chi={chi} {mode}: bonds {g.bond_sizes()} recon rel diff {rel:.2e}")
+    assert rel < 1e-5                                                        # reconstruction: 1e-5 relative
+    assert g.norm_value == pytest.approx(o.norm_value, rel=1e-5)
+    # metrics on the two reconstructions agree to 1e-4
+    x64 = x.astype(np.float64)
+    assert OM.compute_psnr(rg, x64) == pytest.approx(OM.compute_psnr(ro, x64), abs=1e-4)
+    if len(shape) <= 4 and min(shape) >= 7:
+        assert OM.compute_ssim_by_dim(rg, x64) == pytest.approx(OM.compute_ssim_by_dim(ro, x64), abs=1e-4)
+
+
+def test_metrics_through_the_drop_in_api(NDMPS):
+    """compute_* functions of the package on a truncated reconstruction vs the oracle's definitions."""
+    from imgcompressionmps.utils.metrics import (avg_ssim_3d, compute_overlap, compute_psnr, compute_ssim_2d,
+                                                 compute_ssim_by_dim, ssim_3d_axis)
+    x = phantom((64, 64, 64), seed=7).astype(np.float32)
+    full = NDMPS.from_tensor(x)
+    trunc = NDMPS.from_tensor(x, max_bond=16)
+    rec = trunc.to_tensor()
+    x64, r64 = x.astype(np.float64), rec.astype(np.float64)
+    # argument order as benchmark.py:129-130 uses it: reconstruction first
+    assert compute_ssim_by_dim(rec, x) == pytest.approx(OM.compute_ssim_by_dim(r64, x64), abs=1e-9)
+    assert compute_psnr(rec, x) == pytest.approx(OM.compute_psnr(r64, x64), abs=1e-9)
+    assert avg_ssim_3d(x, rec) == pytest.approx(OM.avg_ssim_3d(x64, r64), abs=1e-9)
+    assert np.allclose(ssim_3d_axis(x, rec, axis=1), OM.ssim_3d_axis(x64, r64, axis=1), atol=1e-9)
+    assert compute_ssim_2d(x[3], rec[3]) == pytest.approx(OM.compute_ssim_2d(x64[3], r64[3]), abs=1e-9)
+    # same on device tensors (no host round trip)
+    assert compute_psnr(trunc.to_tensor_device(), torch.from_numpy(x).cuda()) == pytest.approx(OM.compute_psnr(r64, x64), abs=1e-9)
+    # fidelity of the truncated state against the untruncated one
+    o_full = OracleNDMPS.from_tensor(x)
+    o_trunc = OracleNDMPS.from_tensor(x, max_bond=16)
+    want = OM.compute_overlap(o_trunc.cores, o_trunc.norm_value, o_full.cores, o_full.norm_value)
+    assert compute_overlap(trunc, full) == pytest.approx(want, abs=1e-4)
+    # error behaviour
+    with pytest.raises(ValueError):
+        compute_ssim_by_dim(np.zeros(5), np.zeros(5))
+    with pytest.raises(ValueError):
+        avg_ssim_3d(np.zeros((8, 8, 8)), np.zeros((8, 8, 9)))
+    with pytest.raises(ValueError):
+        ssim_3d_axis(np.zeros((8, 8, 8)), np.zeros((8, 8, 8)), axis=3)
+    assert ssim_3d_axis(x, rec, axis=-1) == []
+
+
+def test_lossless_float32_smooth_ranks(NDMPS):
+    """Reference default (cutoff 1e-10 rsum2, no max_bond) on smooth data: ranks are decided at
+    lambda/lambda_max ~ 1e-10 - they must match the float64 oracle run on the same float32 values."""
+    g1, g2 = np.meshgrid(np.linspace(0, 1, 64), np.linspace(0, 1, 96), indexing="ij")
+    x = (np.sin(3 * g1) * np.cos(2 * g2) + 0.5 * g1 * g2 + 0.1 * np.exp(-g1 * g2)).astype(np.float32)
+    g = NDMPS.from_tensor(x)
+    o = OracleNDMPS.from_tensor(x)
+    print("smooth ranks", g.bond_sizes(), o.bond_sizes())
+    assert g.bond_sizes() == o.bond_sizes()
+    assert np.allclose(g.to_tensor(), x, atol=2e-6)
+
+
+def test_quantise_and_replace(NDMPS):
+    x = phantom((32, 32, 32), seed=3).astype(np.float32)
+    g = NDMPS.from_tensor(x, max_bond=8)
+    o = OracleNDMPS.from_tensor(x, max_bond=8)
+    # quantised cores depend on the gauge (signs) of each core, so compare through gauge-free numbers
+    ints = g.compress_to_dtype(np.uint16)
+    assert [i.shape for i in ints] == [tuple(c.shape) for c in o.cores] and ints[0].dtype == np.uint16
+    assert all(i.max() == 65535 and i.min() == 0 for i in ints)
+    assert g.get_storage_space(np.uint16) == o.get_storage_space(np.uint16)
+    before = g.to_tensor().copy()
+    r = g.compression_ratio_on_disk(np.uint16, replace=True)
+    assert 0 < r < 1
+    after = g.to_tensor()
+    assert 0 < np.abs(after - before).max() < 1e-2          # quantisation noise was injected
+    with pytest.raises(ValueError):
+        g.compress_to_dtype(np.float32)
+    with pytest.raises(AssertionError):
+        g.replace_tensordata([np.zeros((1, 1))] * len(g.mps.arrays))
+
+
+def test_api_surface(NDMPS):
+    x = np.random.default_rng(0).random((8, 9))
+    g = NDMPS.from_tensor(x)
+    assert list(g.qubit_size) == [6, 12] and g.dim == 2 and g.mode == "Std" and g.norm is False
+    assert g.encoding_map.shape == (8, 9, 2)
+    assert g.mps.sites == (0, 1) and len(list(g.mps)) == 2 and g.mps[0].size == g.mps.arrays[0].size
+    dense = g.mps ^ ...
+    assert dense.inds == ("k0", "k1")
+    dense.moveindex("k1", 0, inplace=True)
+    assert dense.inds == ("k1", "k0") and dense.data.shape == (12, 6)
+    data = g.return_tensors_data()
+    g.replace_tensordata([np.asarray(d) * 2 for d in data])
+    assert np.allclose(g.to_tensor(), 2 * x, atol=1e-12)
+    h = copy.deepcopy(g)
+    h.mps.arrays[0][:] *= 0
+    assert np.abs(g.to_tensor()).max() > 0                   # deep copy does not alias
+    g.mode = "other"
+    assert g.to_tensor() is None                             # core/ndmps.py:150-153
+    one = NDMPS.from_tensor(np.arange(7.0))                  # one-site MPS: compress is a no-op
+    one.compress(0.5)
+    assert one.bond_sizes() == [] and np.array_equal(one.to_tensor(), np.arange(7.0))
+    with pytest.raises(ValueError):
+        NDMPS.from_tensor(np.zeros((0, 4)))
+
+
+def test_roundtrip_host_entry():
+    from imgcompressionmps import _ops
+    x = phantom((64, 64, 64), seed=5).astype(np.float32)
+    rec, ranks = _ops.roundtrip_host(x, max_bond=16)
+    o = OracleNDMPS.from_tensor(x, max_bond=16)
+    assert ranks == o.bond_sizes()
+    ro = o.to_tensor()
+    assert np.linalg.norm(rec - ro) / np.linalg.norm(ro) < 1e-5
