@@ -26,7 +26,7 @@ static inline double jacobi_tol(int n) { return sqrt((double)n) * 4.440892098500
 // NR > 0: n <= 32*NR, columns staged in registers.  NR == 0: generic n, two passes.
 template <int NR>
 __device__ __forceinline__ bool rotate_pair(double* __restrict__ x, double* __restrict__ y, int n, int lane,
-                                            double tol) {
+                                            double tol, double floor2) {
     double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
     double app = 0.0, aqq = 0.0, apq = 0.0;
     if (NR > 0) {
@@ -50,6 +50,9 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ x, double* __re
     app = warp_sum(app);
     aqq = warp_sum(aqq);
     apq = warp_sum(apq);
+    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
+    // round-off and would keep the sweep from ever reporting convergence
+    if (app <= floor2 || aqq <= floor2) return false;
     if (apq == 0.0 || fabs(apq) <= tol * sqrt(app) * sqrt(aqq)) return false;
     double zeta = (aqq - app) / (2.0 * apq);
     double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -91,8 +94,10 @@ __device__ __forceinline__ void tournament_pair(int P, int lr, int w, int& s1, i
 // (the input is symmetric, so row-major == column-major).
 template <int NR>
 __global__ void __launch_bounds__(512)
-jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int* __restrict__ rotated, double tol) {
+jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int* __restrict__ rotated, double tol,
+                    const double* __restrict__ floor2_ptr) {
     extern __shared__ double S[];
+    const double floor2 = *floor2_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int p, q;
     tournament_pair(nb, round, blockIdx.x, p, q);
@@ -118,13 +123,13 @@ jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int
             tournament_pair(P, lr, warp, s1, s2);
             bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
             bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
-            if (v1 && v2) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol);
+            if (v1 && v2) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol, floor2);
             __syncthreads();
         }
     } else {
         for (int k = 0; k < b; k++) {
             int j = warp + k; j = j >= b ? j - b : j;
-            if (warp < cntp && j < cntq) any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol);
+            if (warp < cntp && j < cntq) any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol, floor2);
             __syncthreads();
         }
     }
@@ -144,8 +149,10 @@ jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int
 // dynamic smem = n*n doubles.  sweeps_out[0] = sweeps used (negative: not converged).
 template <int NR>
 __global__ void __launch_bounds__(1024)
-jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restrict__ sweeps_out, double tol) {
+jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restrict__ sweeps_out, double tol,
+                     const double* __restrict__ floor2_ptr) {
     extern __shared__ double S[];
+    const double floor2 = *floor2_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[i] = A[i];
     __syncthreads();
@@ -159,7 +166,7 @@ jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restr
             for (int w = warp; w < matches; w += W) {
                 int s1, s2;
                 tournament_pair(P, lr, w, s1, s2);
-                if (s1 < n && s2 < n) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol);
+                if (s1 < n && s2 < n) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol, floor2);
             }
             __syncthreads();
         }
@@ -179,6 +186,18 @@ __global__ void __launch_bounds__(256) column_norms_kernel(const double* __restr
     for (int i = lane; i < n; i += 32) s = fma(col[i], col[i], s);
     s = warp_sum(s);
     if (lane == 0) norms[warp] = sqrt(s);
+}
+
+// floor2 = (n * eps * max_j |column j|)^2 : squared norm below which a column counts as null
+__global__ void __launch_bounds__(256) null_floor_kernel(const double* __restrict__ norms, int n, double* __restrict__ floor2) {
+    __shared__ double scratch[32];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, norms[i]);
+    m = block_max(m, scratch);
+    if (threadIdx.x == 0) {
+        double f = (double)n * 2.220446049250313e-16 * m;
+        floor2[0] = f * f;
+    }
 }
 
 // descending rank of every column by counting (ties broken by index), then write
@@ -204,27 +223,29 @@ sort_extract_kernel(const double* __restrict__ A, const double* __restrict__ nor
 }
 
 template <int NR>
-static int launch_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round, int* flag, size_t smem) {
+static int launch_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round, int* flag, size_t smem,
+                        const double* floor2) {
     static bool attr_set = false;
     if (!attr_set) {
         NDMPS_CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)ctx->smem_optin));
         attr_set = true;
     }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, jacobi_tol(n));
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, jacobi_tol(n), floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
 
 template <int NR>
-static int launch_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweeps, int* sweeps_dev, size_t smem) {
+static int launch_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweeps, int* sweeps_dev, size_t smem,
+                         const double* floor2) {
     static bool attr_set = false;
     if (!attr_set) {
         NDMPS_CUDA_TRY(cudaFuncSetAttribute(jacobi_single_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)ctx->smem_optin));
         attr_set = true;
     }
-    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, sweeps_dev, jacobi_tol(n));
+    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, sweeps_dev, jacobi_tol(n), floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -240,6 +261,15 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
     NDMPS_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)max_sweeps + 2) * sizeof(int), ctx->stream));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     int sweeps_used = 0;
+    double* norms = nullptr;
+    double* floor2 = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)n, &norms));
+    NDMPS_TRY(ctx->ws.get<double>(1, &floor2));
+    const int ngrid = (n * 32 + 255) / 256;
+    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, n, norms);
+    NDMPS_LAUNCH_CHECK(ctx);
+    null_floor_kernel<<<1, 256, 0, ctx->stream>>>(norms, n, floor2);
+    NDMPS_LAUNCH_CHECK(ctx);
     const int nr = n <= 64 ? 2 : n <= 128 ? 4 : n <= 256 ? 8 : n <= 512 ? 16 : 0;
 
     const size_t single_bytes = (size_t)n * n * sizeof(double);
@@ -247,8 +277,8 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
         int matches = (n + 1) / 2;
         int warps = matches < 32 ? matches : 32;
         switch (nr) {
-            case 2: NDMPS_TRY(launch_single<2>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes)); break;
-            default: NDMPS_TRY(launch_single<4>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes)); break;
+            case 2: NDMPS_TRY(launch_single<2>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes, floor2)); break;
+            default: NDMPS_TRY(launch_single<4>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes, floor2)); break;
         }
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -272,10 +302,10 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
             int* flag = flags + 1 + s;
             for (int round = 0; round < nb - 1; round++) {
                 switch (nr) {
-                    case 4: NDMPS_TRY(launch_round<4>(ctx, a_dev, n, b, nb, round, flag, smem)); break;
-                    case 8: NDMPS_TRY(launch_round<8>(ctx, a_dev, n, b, nb, round, flag, smem)); break;
-                    case 16: NDMPS_TRY(launch_round<16>(ctx, a_dev, n, b, nb, round, flag, smem)); break;
-                    default: NDMPS_TRY(launch_round<0>(ctx, a_dev, n, b, nb, round, flag, smem)); break;
+                    case 4: NDMPS_TRY(launch_round<4>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
+                    case 8: NDMPS_TRY(launch_round<8>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
+                    case 16: NDMPS_TRY(launch_round<16>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
+                    default: NDMPS_TRY(launch_round<0>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
                 }
             }
             sweeps_used = s + 1;
@@ -291,9 +321,7 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
         }
     }
     ctx->last_eig_sweeps = sweeps_used;
-    double* norms = nullptr;
-    NDMPS_TRY(ctx->ws.get<double>((size_t)n, &norms));
-    int grid = (n * 32 + 255) / 256;
+    int grid = ngrid;
     column_norms_kernel<<<grid, 256, 0, ctx->stream>>>(a_dev, n, norms);
     NDMPS_LAUNCH_CHECK(ctx);
     sort_extract_kernel<<<grid, 256, 0, ctx->stream>>>(a_dev, norms, n, evals_dev, evecs_dev);

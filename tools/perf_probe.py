@@ -1,0 +1,88 @@
+"""Device-time probe of the building blocks (CUDA events, warm-up, L2-sized inputs).
+Run on the GPU box:  python tools/perf_probe.py [what ...]"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "img-compression-mps_b200"))
+sys.path.insert(0, str(ROOT))
+from imgcompressionmps import _native, _ops  # noqa: E402
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2]
+
+
+def main(which):
+    torch.cuda.set_device(0)
+    ctx = _native.context()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    if "eigh" in which:
+        for n in (8, 64, 128, 256, 512, 1024):
+            a = torch.randn(n, 4 * n, dtype=torch.float64, device="cuda", generator=g)
+            gm = a @ a.T
+            ms = timeit(lambda: _ops.eigh(gm), reps=3, warm=1)
+            _, _, sw = _ops.eigh(gm)
+            print(f"eigh n={n}: {ms:.3f} ms, {sw} sweeps", flush=True)
+    if "gram" in which:
+        for rows, cols in ((8, 1 << 21), (64, 1 << 18), (512, 1 << 15), (512, 1 << 12), (512, 512), (512, 1 << 18)):
+            m = torch.randn(rows, cols, dtype=torch.float32, device="cuda", generator=g)
+            ms = timeit(lambda: _ops.gram(m, 0))
+            fl = 2.0 * rows * rows * cols
+            print(f"gram {rows}x{cols}: {ms:.3f} ms, {fl / ms / 1e9:.2f} TFLOP/s (fp32-equivalent), "
+                  f"{rows * cols * 4 / ms / 1e6:.1f} GB/s read", flush=True)
+    if "proj" in which:
+        for r, rows, cols in ((64, 512, 1 << 15), (64, 512, 1 << 18), (8, 8, 1 << 21)):
+            p = torch.randn(rows, r, dtype=torch.float64, device="cuda", generator=g)
+            m = torch.randn(rows, cols, dtype=torch.float32, device="cuda", generator=g)
+            ms = timeit(lambda: _ops.gemm(p.t(), m, out_dtype=torch.float32))
+            print(f"project {r}x{rows} . {rows}x{cols}: {ms:.3f} ms, {2.0 * r * rows * cols / ms / 1e9:.2f} TFLOP/s", flush=True)
+    if "permute" in which:
+        for shape in ((256, 256, 256), (512, 512, 512), (64, 64, 32, 400)):
+            x = torch.randn(shape, dtype=torch.float32, device="cuda", generator=g)
+            ms = timeit(lambda: _ops.encode(x))
+            d = _ops.encode(x)
+            ms2 = timeit(lambda: _ops.decode(d, shape))
+            nb = x.numel() * 8
+            print(f"permute {shape}: encode {ms:.3f} ms ({nb / ms / 1e6:.0f} GB/s), decode {ms2:.3f} ms ({nb / ms2 / 1e6:.0f} GB/s)", flush=True)
+    if "ssim" in which:
+        for shape in ((256, 256, 256), (64, 64, 32, 100)):
+            a = torch.rand(shape, dtype=torch.float32, device="cuda", generator=g)
+            b = a + 0.05 * torch.randn(shape, dtype=torch.float32, device="cuda", generator=g)
+            ms = timeit(lambda: _ops.ssim(a, b), reps=3, warm=1)
+            print(f"ssim {shape}: {ms:.3f} ms ({a.numel() * 16 / ms / 1e6:.0f} GB/s algorithmic)", flush=True)
+            ms = timeit(lambda: _ops.psnr_terms(a, b), reps=3, warm=1)
+            print(f"psnr {shape}: {ms:.3f} ms ({a.numel() * 8 / ms / 1e6:.0f} GB/s)", flush=True)
+    if "stages" in which:
+        from imgcompressionmps.core.ndmps import NDMPS
+        for n in (256,):
+            x = torch.rand((n, n, n), dtype=torch.float32, device="cuda", generator=g)
+            for _ in range(2):
+                NDMPS.from_tensor(x, max_bond=64).to_tensor_device()
+            ctx.profile(True)
+            ctx.stage_times(reset=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            NDMPS.from_tensor(x, max_bond=64).to_tensor_device()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            print(f"stages {n}^3 chi=64: wall {dt * 1e3:.2f} ms", {k: (round(v[0], 3), v[1]) for k, v in ctx.stage_times().items()}, flush=True)
+            ctx.profile(False)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["eigh", "gram", "proj", "permute", "ssim", "stages"])
