@@ -8,13 +8,23 @@
 // lambda_j = |w_j| and u_j = w_j / |w_j|.  Everything is float64 (B200's FP64 pipe),
 // because the sweep's rank decisions sit at lambda/lambda_max ~ 1e-10.
 //
-// Parallel scheme: the n columns are split into nb blocks of b columns.  A sweep
-// is a round-robin tournament over blocks (nb-1 rounds); in a round every CTA owns
-// one block pair in shared memory and one warp owns one column pair at a time.
-// Round 0 of a sweep runs the full tournament inside the 2b columns (this covers
-// the within-block pairs); later rounds only rotate cross pairs (i in P, j in Q).
-// Matrices that fit one CTA's shared memory are swept to convergence in a single
-// launch.
+// Parallel scheme: the n columns are split into nb blocks of b columns.  A sweep is a
+// round-robin tournament over blocks (nb-1 rounds); in a round every CTA owns one block
+// pair in shared memory and one warp owns one column pair at a time.  Round 0 of a
+// sweep runs the full tournament inside the 2b columns (this covers the within-block
+// pairs); later rounds only rotate cross pairs.  The whole solve is ONE persistent
+// cooperative launch: CTAs exchange column blocks through L2 (ld.cg / st.cg) and meet
+// at a counter barrier after every round; convergence is a per-sweep flag.  Matrices
+// that fit one CTA's shared memory are swept to convergence by a single CTA.
+//
+// Per rotation the latency chain is what matters (the FP64 work is tiny), so:
+//   * squared column norms are cached in shared memory and updated by the exact
+//     identities a' = a - t g, b' = b + t g (refreshed from the data every round);
+//     only ONE dot product (g) is reduced per rotation;
+//   * the rotation tangent is evaluated in float32 (MUFU), then c = rsqrt(1 + t^2)
+//     is refined to full float64, so every rotation is orthogonal to 1e-16 even though
+//     its angle is only float32-optimal (costs at most one extra sweep);
+//   * de Rijk ordering: after a rotation the larger column goes to the lower slot.
 #include "common.cuh"
 
 namespace ndmps {
@@ -22,57 +32,103 @@ namespace ndmps {
 // rotation threshold |x.y| <= tol |x||y| with tol = sqrt(n) * 2 eps (LAPACK dgesvj uses sqrt(n) eps)
 static inline double jacobi_tol(int n) { return sqrt((double)n) * 4.4408920985006262e-16; }
 
-// rotate columns x, y (length n, shared memory) so that they become orthogonal.
+__device__ __forceinline__ double rsqrt_refined(double x) {   // x in the normal range
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double rcp_approx(double x) {      // ~20 bits, full exponent range
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+// cos / sin / tan of the Jacobi rotation that orthogonalises two columns with squared
+// norms alpha, beta and inner product gamma (gamma != 0)
+__device__ __forceinline__ void rotation(double alpha, double beta, double gamma, double& c, double& s, double& t) {
+    double zeta = (beta - alpha) * rcp_approx(2.0 * gamma);
+    float zf = (float)zeta;
+    float az = fabsf(zf);
+    if (az > 1e8f) {
+        t = 0.5 * rcp_approx(zeta);                           // asymptotic branch, keeps the sign
+    } else {
+        float tf = __frcp_rn(az + __fsqrt_rn(fmaf(az, az, 1.0f)));
+        t = (double)copysignf(tf, zf);
+    }
+    c = rsqrt_refined(fma(t, t, 1.0));
+    s = c * t;
+}
+
+// Orthogonalise columns x, y (length n, shared memory).  nx, ny: cached squared norms.
 // NR > 0: n <= 32*NR, columns staged in registers.  NR == 0: generic n, two passes.
+// Returns true if a rotation was applied (warp-uniform).
 template <int NR>
-__device__ __forceinline__ bool rotate_pair(double* __restrict__ x, double* __restrict__ y, int n, int lane,
-                                            double tol, double floor2) {
+__device__ __forceinline__ bool rotate_pair(double* x, double* y, double* nx, double* ny, int n, int lane, double tol2,
+                                            double floor2) {
+    const double alpha = *nx, beta = *ny;
+    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
+    // round-off and would keep the sweep from ever reporting convergence
+    if (!(alpha > floor2) || !(beta > floor2)) return false;
     double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
-    double app = 0.0, aqq = 0.0, apq = 0.0;
+    double g0 = 0.0, g1 = 0.0;
     if (NR > 0) {
 #pragma unroll
         for (int t = 0; t < NR; t++) {
             int i = lane + 32 * t;
             xr[t] = i < n ? x[i] : 0.0;
             yr[t] = i < n ? y[i] : 0.0;
-            app = fma(xr[t], xr[t], app);
-            aqq = fma(yr[t], yr[t], aqq);
-            apq = fma(xr[t], yr[t], apq);
+            if (t & 1) g1 = fma(xr[t], yr[t], g1); else g0 = fma(xr[t], yr[t], g0);
         }
     } else {
-        for (int i = lane; i < n; i += 32) {
-            double a = x[i], b = y[i];
-            app = fma(a, a, app);
-            aqq = fma(b, b, aqq);
-            apq = fma(a, b, apq);
-        }
+        for (int i = lane; i < n; i += 32) g0 = fma(x[i], y[i], g0);
     }
-    app = warp_sum(app);
-    aqq = warp_sum(aqq);
-    apq = warp_sum(apq);
-    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
-    // round-off and would keep the sweep from ever reporting convergence
-    if (app <= floor2 || aqq <= floor2) return false;
-    if (apq == 0.0 || fabs(apq) <= tol * sqrt(app) * sqrt(aqq)) return false;
-    double zeta = (aqq - app) / (2.0 * apq);
-    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    double c = 1.0 / sqrt(1.0 + t * t);
-    double s = c * t;
+    const double gamma = warp_sum(g0 + g1);
+    if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    double c, s, t;
+    rotation(alpha, beta, gamma, c, s, t);
+    double na = alpha - t * gamma, nb = beta + t * gamma;
+    const bool swap = na < nb;                                // de Rijk: larger column to the lower slot
+    double* px = swap ? y : x;
+    double* py = swap ? x : y;
+    double ra = 0.0, rb = 0.0;
     if (NR > 0) {
 #pragma unroll
         for (int tt = 0; tt < NR; tt++) {
             int i = lane + 32 * tt;
+            double a = c * xr[tt] - s * yr[tt];
+            double b = s * xr[tt] + c * yr[tt];
+            ra = fma(a, a, ra);
+            rb = fma(b, b, rb);
             if (i < n) {
-                x[i] = c * xr[tt] - s * yr[tt];
-                y[i] = s * xr[tt] + c * yr[tt];
+                px[i] = a;
+                py[i] = b;
             }
         }
     } else {
+        // x, y may be swapped in place: read both before writing either
         for (int i = lane; i < n; i += 32) {
-            double a = x[i], b = y[i];
-            x[i] = c * a - s * b;
-            y[i] = s * a + c * b;
+            double xv = x[i], yv = y[i];
+            double a = c * xv - s * yv;
+            double b = s * xv + c * yv;
+            ra = fma(a, a, ra);
+            rb = fma(b, b, rb);
+            px[i] = a;
+            py[i] = b;
         }
+    }
+    // the update identities cancel catastrophically when a column collapses: recompute then
+    if (na < 0.01 * alpha || nb < 0.01 * beta) {
+        na = warp_sum(ra);
+        nb = warp_sum(rb);
+    }
+    if (lane == 0) {
+        *nx = swap ? nb : na;
+        *ny = swap ? na : nb;
     }
     return true;
 }
@@ -89,30 +145,44 @@ __device__ __forceinline__ void tournament_pair(int P, int lr, int w, int& s1, i
     }
 }
 
-// One round of the block tournament.  grid = nb/2 CTAs, block = 32*b threads,
-// dynamic smem = 2*b*n doubles.  A is n x n with "column" j stored at A + j*n
-// (the input is symmetric, so row-major == column-major).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned*)counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// One CTA, one block pair (p, q) of one tournament round: load both column blocks from
+// L2, refresh their norms, rotate, store back.  S: 2*b*n doubles, norm2: 2*b doubles.
 template <int NR>
-__global__ void __launch_bounds__(512)
-jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int* __restrict__ rotated, double tol,
-                    const double* __restrict__ floor2_ptr) {
-    extern __shared__ double S[];
-    const double floor2 = *floor2_ptr;
+__device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int nb, int round, int cta, double* S,
+                                                   double* norm2, double tol2, double floor2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int p, q;
-    tournament_pair(nb, round, blockIdx.x, p, q);
+    tournament_pair(nb, round, cta, p, q);
     const int colp0 = p * b, colq0 = q * b;
     int cntp = n - colp0; cntp = cntp < 0 ? 0 : (cntp > b ? b : cntp);
     int cntq = n - colq0; cntq = cntq < 0 ? 0 : (cntq > b ? b : cntq);
-    // load the two column blocks
     for (int lc = warp; lc < 2 * b; lc += b) {
-        bool isq = lc >= b;
-        int l = isq ? lc - b : lc;
+        const bool isq = lc >= b;
+        const int l = isq ? lc - b : lc;
+        double acc = 0.0;
         if (l < (isq ? cntq : cntp)) {
             const double* src = A + (size_t)((isq ? colq0 : colp0) + l) * n;
             double* dst = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+            for (int i = lane; i < n; i += 32) {
+                double v = __ldcg(src + i);
+                dst[i] = v;
+                acc = fma(v, v, acc);
+            }
         }
+        acc = warp_sum(acc);
+        if (lane == 0) norm2[lc] = acc;
     }
     __syncthreads();
     bool any = false;
@@ -121,37 +191,79 @@ jacobi_round_kernel(double* __restrict__ A, int n, int b, int nb, int round, int
         for (int lr = 0; lr < P - 1; lr++) {
             int s1, s2;
             tournament_pair(P, lr, warp, s1, s2);
-            bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
-            bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
-            if (v1 && v2) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol, floor2);
+            if (s1 > s2) { int tmp = s1; s1 = s2; s2 = tmp; }
+            const bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
+            const bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
+            if (v1 && v2)
+                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, norm2 + s1, norm2 + s2, n, lane, tol2, floor2);
             __syncthreads();
         }
     } else {
         for (int k = 0; k < b; k++) {
-            int j = warp + k; j = j >= b ? j - b : j;
-            if (warp < cntp && j < cntq) any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol, floor2);
+            int j = warp + k;
+            j = j >= b ? j - b : j;
+            if (warp < cntp && j < cntq)
+                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, norm2 + warp, norm2 + b + j, n, lane,
+                                       tol2, floor2);
             __syncthreads();
         }
     }
     for (int lc = warp; lc < 2 * b; lc += b) {
-        bool isq = lc >= b;
-        int l = isq ? lc - b : lc;
+        const bool isq = lc >= b;
+        const int l = isq ? lc - b : lc;
         if (l < (isq ? cntq : cntp)) {
             double* dst = A + (size_t)((isq ? colq0 : colp0) + l) * n;
             const double* src = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+            for (int i = lane; i < n; i += 32) __stcg(dst + i, src[i]);
         }
     }
-    if (any && lane == 0) *rotated = 1;
+    return any;
+}
+
+// Persistent solve: grid = nb/2 CTAs (cooperative launch), block = 32*b threads.
+// ctrl[0]: barrier counter, ctrl[1]: sweeps used (negative = not converged), ctrl[2+s]: sweep flags.
+template <int NR>
+__global__ void __launch_bounds__(512)
+jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
+                         const double* floor2_ptr) {
+    extern __shared__ double S[];
+    double* norm2 = S + (size_t)2 * b * n;
+    const double floor2 = *floor2_ptr;
+    unsigned epoch = 0;
+    int sweep = 0;
+    bool converged = false;
+    while (sweep < max_sweeps) {
+        for (int round = 0; round < nb - 1; round++) {
+            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, norm2, tol2, floor2);
+            if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
+            epoch++;
+            grid_barrier(ctrl, epoch * gridDim.x);
+        }
+        unsigned flag = __ldcg(ctrl + 2 + sweep);
+        sweep++;
+        if (flag == 0) { converged = true; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ((int*)ctrl)[1] = converged ? sweep : -sweep;
+}
+
+// Same work as one round of the persistent kernel, for matrices whose block count exceeds the
+// number of co-resident CTAs (n > ~4700): one launch per round.
+template <int NR>
+__global__ void __launch_bounds__(512)
+jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr) {
+    extern __shared__ double S[];
+    double* norm2 = S + (size_t)2 * b * n;
+    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, norm2, tol2, *floor2_ptr);
+    if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
 // Whole matrix in one CTA: sweep until no rotation happens.  block = 32*W threads,
-// dynamic smem = n*n doubles.  sweeps_out[0] = sweeps used (negative: not converged).
+// dynamic smem = (n*n + n) doubles.  ctrl[1] = sweeps used (negative: not converged).
 template <int NR>
 __global__ void __launch_bounds__(1024)
-jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restrict__ sweeps_out, double tol,
-                     const double* __restrict__ floor2_ptr) {
+jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double tol2, const double* floor2_ptr) {
     extern __shared__ double S[];
+    double* norm2 = S + (size_t)n * n;
     const double floor2 = *floor2_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[i] = A[i];
@@ -161,12 +273,21 @@ jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restr
     int sweep = 0;
     int done = n < 2 ? 1 : 0;
     while (!done && sweep < max_sweeps) {
+        for (int col = warp; col < n; col += W) {            // refresh the cached norms once per sweep
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) acc = fma(S[(size_t)col * n + i], S[(size_t)col * n + i], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) norm2[col] = acc;
+        }
+        __syncthreads();
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
             for (int w = warp; w < matches; w += W) {
                 int s1, s2;
                 tournament_pair(P, lr, w, s1, s2);
-                if (s1 < n && s2 < n) any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol, floor2);
+                if (s1 > s2) { int tmp = s1; s1 = s2; s2 = tmp; }
+                if (s2 < n)
+                    any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, norm2 + s1, norm2 + s2, n, lane, tol2, floor2);
             }
             __syncthreads();
         }
@@ -174,7 +295,7 @@ jacobi_single_kernel(double* __restrict__ A, int n, int max_sweeps, int* __restr
         done = !__syncthreads_or(any ? 1 : 0);
     }
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) A[i] = S[i];
-    if (threadIdx.x == 0) sweeps_out[0] = done ? sweep : -sweep;
+    if (threadIdx.x == 0) ((int*)ctrl)[1] = done ? sweep : -sweep;
 }
 
 // lambda_j = |column j|, one warp per column
@@ -222,30 +343,40 @@ sort_extract_kernel(const double* __restrict__ A, const double* __restrict__ nor
     for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + rank] = col[i] * inv;
 }
 
+template <class K>
+static int raise_smem(K kernel, const ndmps_ctx* ctx) {
+    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    return NDMPS_OK;
+}
+
 template <int NR>
-static int launch_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round, int* flag, size_t smem,
-                        const double* floor2) {
+static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
+                          const double* floor2, size_t smem) {
     static bool attr_set = false;
-    if (!attr_set) {
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(jacobi_round_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ctx->smem_optin));
-        attr_set = true;
-    }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, jacobi_tol(n), floor2);
+    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
+    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
+    NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
+                                               ctx->stream));
+    ctx->launches++;
+    return NDMPS_OK;
+}
+
+template <int NR>
+static int run_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round, unsigned* flag, double tol2,
+                     const double* floor2, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
 
 template <int NR>
-static int launch_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweeps, int* sweeps_dev, size_t smem,
-                         const double* floor2) {
+static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweeps, unsigned* ctrl, double tol2,
+                      const double* floor2, size_t smem) {
     static bool attr_set = false;
-    if (!attr_set) {
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(jacobi_single_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ctx->smem_optin));
-        attr_set = true;
-    }
-    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, sweeps_dev, jacobi_tol(n), floor2);
+    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_single_kernel<NR>, ctx)); attr_set = true; }
+    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -256,9 +387,9 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
     const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 1024 : 0;
     NDMPS_TRY(ensure_pinned(ctx, 64));
-    int* flags = nullptr;   // device ints: [0] single-kernel sweeps, [1..] per-sweep rotation flags
-    NDMPS_TRY(ctx->ws.get<int>((size_t)max_sweeps + 2, &flags));
-    NDMPS_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)max_sweeps + 2) * sizeof(int), ctx->stream));
+    unsigned* ctrl = nullptr;   // [0] barrier counter, [1] sweeps used, [2..] per-sweep rotation flags
+    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)max_sweeps + 4, &ctrl));
+    NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, ((size_t)max_sweeps + 4) * sizeof(unsigned), ctx->stream));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     int sweeps_used = 0;
     double* norms = nullptr;
@@ -270,17 +401,16 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
     NDMPS_LAUNCH_CHECK(ctx);
     null_floor_kernel<<<1, 256, 0, ctx->stream>>>(norms, n, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
+    const double tol = jacobi_tol(n), tol2 = tol * tol;
     const int nr = n <= 64 ? 2 : n <= 128 ? 4 : n <= 256 ? 8 : n <= 512 ? 16 : 0;
 
-    const size_t single_bytes = (size_t)n * n * sizeof(double);
+    const size_t single_bytes = ((size_t)n * n + n) * sizeof(double);
     if (n >= 2 && single_bytes <= smem_cap && n <= 128) {
         int matches = (n + 1) / 2;
         int warps = matches < 32 ? matches : 32;
-        switch (nr) {
-            case 2: NDMPS_TRY(launch_single<2>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes, floor2)); break;
-            default: NDMPS_TRY(launch_single<4>(ctx, a_dev, n, warps, max_sweeps, flags, single_bytes, floor2)); break;
-        }
-        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nr == 2) NDMPS_TRY(run_single<2>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        else NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (host_flag[0] <= 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d)", max_sweeps, n);
@@ -288,43 +418,51 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
         }
         sweeps_used = host_flag[0];
     } else if (n >= 2) {
-        // block size: as many columns as shared memory allows, at most 32 warps, tunable
-        int b = (int)(smem_cap / (16 * (size_t)n));
+        // block size: as many columns as shared memory allows, at most 16 warps, tunable
+        int b = (int)((smem_cap - 512) / (16 * (size_t)n));
         if (b > 16) b = 16;
         if (ctx->opt_jacobi_block > 0 && ctx->opt_jacobi_block < b) b = (int)ctx->opt_jacobi_block;
         NDMPS_REQUIRE(b >= 1, "eigh: n = %d does not fit a column pair in shared memory", n);
         int nb = (n + b - 1) / b;
         if (nb & 1) nb++;
         if (nb < 2) nb = 2;
-        size_t smem = (size_t)2 * b * n * sizeof(double);
-        bool converged = false;
-        for (int s = 0; s < max_sweeps && !converged; s++) {
-            int* flag = flags + 1 + s;
-            for (int round = 0; round < nb - 1; round++) {
-                switch (nr) {
-                    case 4: NDMPS_TRY(launch_round<4>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
-                    case 8: NDMPS_TRY(launch_round<8>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
-                    case 16: NDMPS_TRY(launch_round<16>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
-                    default: NDMPS_TRY(launch_round<0>(ctx, a_dev, n, b, nb, round, flag, smem, floor2)); break;
+        const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
+        if (nb / 2 <= ctx->sm_count) {
+            switch (nr) {
+                case 8: NDMPS_TRY(run_persistent<8>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+                case 16: NDMPS_TRY(run_persistent<16>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+                default: NDMPS_TRY(run_persistent<0>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+            }
+            NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (host_flag[0] <= 0) {
+                set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, b = %d)", max_sweeps, n, b);
+                return NDMPS_ERR_NOCONV;
+            }
+            sweeps_used = host_flag[0];
+        } else {
+            bool converged = false;
+            for (int s = 0; s < max_sweeps && !converged; s++) {
+                unsigned* flag = ctrl + 2 + s;
+                for (int round = 0; round < nb - 1; round++)
+                    NDMPS_TRY(run_round<0>(ctx, a_dev, n, b, nb, round, flag, tol2, floor2, smem));
+                sweeps_used = s + 1;
+                if (s >= 3) {
+                    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                    converged = host_flag[0] == 0;
                 }
             }
-            sweeps_used = s + 1;
-            if (s >= 3) {
-                NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                converged = host_flag[0] == 0;
+            if (!converged) {
+                set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, b = %d)", max_sweeps, n, b);
+                return NDMPS_ERR_NOCONV;
             }
-        }
-        if (!converged) {
-            set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, b = %d)", max_sweeps, n, b);
-            return NDMPS_ERR_NOCONV;
         }
     }
     ctx->last_eig_sweeps = sweeps_used;
-    int grid = ngrid;
-    column_norms_kernel<<<grid, 256, 0, ctx->stream>>>(a_dev, n, norms);
+    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, n, norms);
     NDMPS_LAUNCH_CHECK(ctx);
-    sort_extract_kernel<<<grid, 256, 0, ctx->stream>>>(a_dev, norms, n, evals_dev, evecs_dev);
+    sort_extract_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, norms, n, evals_dev, evecs_dev);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }

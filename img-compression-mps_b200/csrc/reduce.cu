@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(256) quantize_kernel(const T* __restrict__ x, 
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // filetools.py:24-26: (x - min) / max(x - min) * iinfo.max, cast truncates toward zero
-        double u = ((double)x[i] - lo) / span;
-        double v = u * qmax;
+        // every step rounded separately (no FMA contraction) so the bytes match numpy's
+        double u = __ddiv_rn(__dsub_rn((double)x[i], lo), span);
+        double v = __dmul_rn(u, qmax);
         q[i] = (Q)(long long)v;
     }
 }
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const Q* __restrict__ q
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // filetools.py:38-39: q / iinfo.max * (max - min) + min
-        double u = (double)q[i] / qmax;
-        x[i] = (T)(u * (hi - lo) + lo);
+        double u = __ddiv_rn((double)q[i], qmax);
+        x[i] = (T)__dadd_rn(__dmul_rn(u, __dsub_rn(hi, lo)), lo);
     }
 }
 

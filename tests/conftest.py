@@ -38,7 +38,7 @@ def golden_dct():
     return np.load(GOLDEN / "dct.npz")
 
 
-def phantom(shape, seed, noise=0.02):
+def phantom(shape, seed, noise=0.02, background=0.0):
     """Synthetic 'MRI': nested ellipsoids, smoothed edges, exact-zero background, small noise
     inside the object only."""
     rng = np.random.default_rng(seed)
@@ -48,8 +48,12 @@ def phantom(shape, seed, noise=0.02):
         centre = rng.uniform(-0.25, 0.25, size=len(shape))
         radii = rng.uniform(0.35, 0.8, size=len(shape)) * (1.0 - 0.18 * k)
         r2 = sum(((g - c) / r) ** 2 for g, c, r in zip(grids, centre, radii))
-        vol += (0.25 + 0.1 * k) / (1.0 + np.exp((r2 - 1.0) * 12.0))
+        vol += (0.25 + 0.1 * k) / (1.0 + np.exp(np.clip((r2 - 1.0) * 12.0, -60.0, 60.0)))
     vol += 0.05 * np.prod([np.cos(3.0 * g + k) for k, g in enumerate(grids)], axis=0) * (vol > 0.05)
     vol += noise * rng.random(shape) * (vol > 0.05)
     vol[vol < 0.02] = 0.0
+    if background:
+        # faint texture everywhere: no slice is constant, so no slice has data range 0 (where the
+        # reference's SSIM is 0/0)
+        vol += background * rng.random(shape)
     return vol
