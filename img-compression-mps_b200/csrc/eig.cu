@@ -21,9 +21,8 @@
 //   * squared column norms are cached in shared memory and updated by the exact
 //     identities a' = a - t g, b' = b + t g (refreshed from the data every round);
 //     only ONE dot product (g) is reduced per rotation;
-//   * the rotation tangent is evaluated in float32 (MUFU), then c = rsqrt(1 + t^2)
-//     is refined to full float64, so every rotation is orthogonal to 1e-16 even though
-//     its angle is only float32-optimal (costs at most one extra sweep);
+//   * tangent / cosine come from MUFU rcp / rsqrt seeds plus Newton steps (full float64
+//     accuracy) instead of the IEEE division / square-root instruction sequences;
 //   * de Rijk ordering: after a rotation the larger column goes to the lower slot.
 #include "common.cuh"
 
@@ -48,17 +47,26 @@ __device__ __forceinline__ double rcp_approx(double x) {      // ~20 bits, full 
     return r;
 }
 
+__device__ __forceinline__ double rcp_refined(double x) {     // full float64 accuracy
+    double r = rcp_approx(x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 // cos / sin / tan of the Jacobi rotation that orthogonalises two columns with squared
-// norms alpha, beta and inner product gamma (gamma != 0)
+// norms alpha, beta and inner product gamma (gamma != 0): t is the smaller root of
+// t^2 + 2 zeta t - 1 = 0.  MUFU seeds + Newton steps instead of the IEEE div / sqrt sequences;
+// all results are float64-accurate (the cached-norm identities below rely on an exact t).
 __device__ __forceinline__ void rotation(double alpha, double beta, double gamma, double& c, double& s, double& t) {
-    double zeta = (beta - alpha) * rcp_approx(2.0 * gamma);
-    float zf = (float)zeta;
-    float az = fabsf(zf);
-    if (az > 1e8f) {
-        t = 0.5 * rcp_approx(zeta);                           // asymptotic branch, keeps the sign
+    const double zeta = (beta - alpha) * rcp_refined(2.0 * gamma);
+    const double az = fabs(zeta);
+    if (az > 1e150) {
+        t = 0.5 * rcp_refined(zeta);
     } else {
-        float tf = __frcp_rn(az + __fsqrt_rn(fmaf(az, az, 1.0f)));
-        t = (double)copysignf(tf, zf);
+        const double w = fma(az, az, 1.0);
+        const double sq = w * rsqrt_refined(w);
+        t = copysign(rcp_refined(az + sq), zeta);
     }
     c = rsqrt_refined(fma(t, t, 1.0));
     s = c * t;
@@ -95,15 +103,12 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, double* nx, do
     const bool swap = na < nb;                                // de Rijk: larger column to the lower slot
     double* px = swap ? y : x;
     double* py = swap ? x : y;
-    double ra = 0.0, rb = 0.0;
     if (NR > 0) {
 #pragma unroll
         for (int tt = 0; tt < NR; tt++) {
             int i = lane + 32 * tt;
             double a = c * xr[tt] - s * yr[tt];
             double b = s * xr[tt] + c * yr[tt];
-            ra = fma(a, a, ra);
-            rb = fma(b, b, rb);
             if (i < n) {
                 px[i] = a;
                 py[i] = b;
@@ -113,16 +118,17 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, double* nx, do
         // x, y may be swapped in place: read both before writing either
         for (int i = lane; i < n; i += 32) {
             double xv = x[i], yv = y[i];
-            double a = c * xv - s * yv;
-            double b = s * xv + c * yv;
-            ra = fma(a, a, ra);
-            rb = fma(b, b, rb);
-            px[i] = a;
-            py[i] = b;
+            px[i] = c * xv - s * yv;
+            py[i] = s * xv + c * yv;
         }
     }
     // the update identities cancel catastrophically when a column collapses: recompute then
     if (na < 0.01 * alpha || nb < 0.01 * beta) {
+        double ra = 0.0, rb = 0.0;
+        for (int i = lane; i < n; i += 32) {                  // each lane re-reads what it wrote
+            ra = fma(px[i], px[i], ra);
+            rb = fma(py[i], py[i], rb);
+        }
         na = warp_sum(ra);
         nb = warp_sum(rb);
     }
