@@ -18,9 +18,7 @@
 // that fit one CTA's shared memory are swept to convergence by a single CTA.
 //
 // Per rotation the latency chain is what matters (the FP64 work is tiny), so:
-//   * squared column norms are cached in shared memory and updated by the exact
-//     identities a' = a - t g, b' = b + t g (refreshed from the data every round);
-//     only ONE dot product (g) is reduced per rotation;
+//   * the three reductions of a pair (|x|^2, |y|^2, x.y) run as interleaved butterflies;
 //   * tangent / cosine come from MUFU rcp / rsqrt seeds plus Newton steps (full float64
 //     accuracy) instead of the IEEE division / square-root instruction sequences;
 //   * de Rijk ordering: after a rotation the larger column goes to the lower slot.
@@ -72,35 +70,51 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
     s = c * t;
 }
 
-// Orthogonalise columns x, y (length n, shared memory).  nx, ny: cached squared norms.
+// Orthogonalise columns x, y (length n, shared memory).
 // NR > 0: n <= 32*NR, columns staged in registers.  NR == 0: generic n, two passes.
+// derijk: after a rotation the larger column goes to slot x (the lower slot).
 // Returns true if a rotation was applied (warp-uniform).
+//
+// The squared norms are recomputed with every visit (three reductions that pipeline with
+// each other): cached norms updated by a' = a - t g drift by a few eps per rotation, and for
+// nearly degenerate pairs that drift ends up in the angle and leaves residuals right at the
+// convergence threshold, so the sweep count grows instead of shrinking.
 template <int NR>
-__device__ __forceinline__ bool rotate_pair(double* x, double* y, double* nx, double* ny, int n, int lane, double tol2,
-                                            double floor2) {
-    const double alpha = *nx, beta = *ny;
-    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
-    // round-off and would keep the sweep from ever reporting convergence
-    if (!(alpha > floor2) || !(beta > floor2)) return false;
+__device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lane, double tol2, double floor2,
+                                            bool derijk) {
     double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
-    double g0 = 0.0, g1 = 0.0;
+    double alpha = 0.0, beta = 0.0, gamma = 0.0;
     if (NR > 0) {
 #pragma unroll
         for (int t = 0; t < NR; t++) {
             int i = lane + 32 * t;
             xr[t] = i < n ? x[i] : 0.0;
             yr[t] = i < n ? y[i] : 0.0;
-            if (t & 1) g1 = fma(xr[t], yr[t], g1); else g0 = fma(xr[t], yr[t], g0);
+            alpha = fma(xr[t], xr[t], alpha);
+            beta = fma(yr[t], yr[t], beta);
+            gamma = fma(xr[t], yr[t], gamma);
         }
     } else {
-        for (int i = lane; i < n; i += 32) g0 = fma(x[i], y[i], g0);
+        for (int i = lane; i < n; i += 32) {
+            double a = x[i], b = y[i];
+            alpha = fma(a, a, alpha);
+            beta = fma(b, b, beta);
+            gamma = fma(a, b, gamma);
+        }
     }
-    const double gamma = warp_sum(g0 + g1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                        // three interleaved butterflies
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+    }
+    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
+    // round-off and would keep the sweep from ever reporting convergence
+    if (!(alpha > floor2) || !(beta > floor2)) return false;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;
     double c, s, t;
     rotation(alpha, beta, gamma, c, s, t);
-    double na = alpha - t * gamma, nb = beta + t * gamma;
-    const bool swap = na < nb;                                // de Rijk: larger column to the lower slot
+    const bool swap = derijk && (alpha - t * gamma < beta + t * gamma);
     double* px = swap ? y : x;
     double* py = swap ? x : y;
     if (NR > 0) {
@@ -121,20 +135,6 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, double* nx, do
             px[i] = c * xv - s * yv;
             py[i] = s * xv + c * yv;
         }
-    }
-    // the update identities cancel catastrophically when a column collapses: recompute then
-    if (na < 0.01 * alpha || nb < 0.01 * beta) {
-        double ra = 0.0, rb = 0.0;
-        for (int i = lane; i < n; i += 32) {                  // each lane re-reads what it wrote
-            ra = fma(px[i], px[i], ra);
-            rb = fma(py[i], py[i], rb);
-        }
-        na = warp_sum(ra);
-        nb = warp_sum(rb);
-    }
-    if (lane == 0) {
-        *nx = swap ? nb : na;
-        *ny = swap ? na : nb;
     }
     return true;
 }
@@ -164,10 +164,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 }
 
 // One CTA, one block pair (p, q) of one tournament round: load both column blocks from
-// L2, refresh their norms, rotate, store back.  S: 2*b*n doubles, norm2: 2*b doubles.
+// L2, rotate, store back.  S: 2*b*n doubles.
 template <int NR>
 __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int nb, int round, int cta, double* S,
-                                                   double* norm2, double tol2, double floor2) {
+                                                   double tol2, double floor2, bool derijk) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int p, q;
     tournament_pair(nb, round, cta, p, q);
@@ -177,18 +177,11 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
     for (int lc = warp; lc < 2 * b; lc += b) {
         const bool isq = lc >= b;
         const int l = isq ? lc - b : lc;
-        double acc = 0.0;
         if (l < (isq ? cntq : cntp)) {
             const double* src = A + (size_t)((isq ? colq0 : colp0) + l) * n;
             double* dst = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) {
-                double v = __ldcg(src + i);
-                dst[i] = v;
-                acc = fma(v, v, acc);
-            }
+            for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + i);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) norm2[lc] = acc;
     }
     __syncthreads();
     bool any = false;
@@ -201,7 +194,7 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
             const bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
             const bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
             if (v1 && v2)
-                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, norm2 + s1, norm2 + s2, n, lane, tol2, floor2);
+                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk);
             __syncthreads();
         }
     } else {
@@ -209,8 +202,7 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
             int j = warp + k;
             j = j >= b ? j - b : j;
             if (warp < cntp && j < cntq)
-                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, norm2 + warp, norm2 + b + j, n, lane,
-                                       tol2, floor2);
+                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol2, floor2, derijk);
             __syncthreads();
         }
     }
@@ -231,16 +223,15 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                         const double* floor2_ptr) {
+                         const double* floor2_ptr, bool derijk) {
     extern __shared__ double S[];
-    double* norm2 = S + (size_t)2 * b * n;
     const double floor2 = *floor2_ptr;
     unsigned epoch = 0;
     int sweep = 0;
     bool converged = false;
     while (sweep < max_sweeps) {
         for (int round = 0; round < nb - 1; round++) {
-            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, norm2, tol2, floor2);
+            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2, derijk);
             if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
             epoch++;
             grid_barrier(ctrl, epoch * gridDim.x);
@@ -256,20 +247,20 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
 // number of co-resident CTAs (n > ~4700): one launch per round.
 template <int NR>
 __global__ void __launch_bounds__(512)
-jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr) {
+jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr,
+                    bool derijk) {
     extern __shared__ double S[];
-    double* norm2 = S + (size_t)2 * b * n;
-    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, norm2, tol2, *floor2_ptr);
+    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr, derijk);
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
 // Whole matrix in one CTA: sweep until no rotation happens.  block = 32*W threads,
-// dynamic smem = (n*n + n) doubles.  ctrl[1] = sweeps used (negative: not converged).
+// dynamic smem = n*n doubles.  ctrl[1] = sweeps used (negative: not converged).
 template <int NR>
 __global__ void __launch_bounds__(1024)
-jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double tol2, const double* floor2_ptr) {
+jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double tol2, const double* floor2_ptr,
+                     bool derijk) {
     extern __shared__ double S[];
-    double* norm2 = S + (size_t)n * n;
     const double floor2 = *floor2_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[i] = A[i];
@@ -279,13 +270,6 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
     int sweep = 0;
     int done = n < 2 ? 1 : 0;
     while (!done && sweep < max_sweeps) {
-        for (int col = warp; col < n; col += W) {            // refresh the cached norms once per sweep
-            double acc = 0.0;
-            for (int i = lane; i < n; i += 32) acc = fma(S[(size_t)col * n + i], S[(size_t)col * n + i], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) norm2[col] = acc;
-        }
-        __syncthreads();
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
             for (int w = warp; w < matches; w += W) {
@@ -293,7 +277,7 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
                 tournament_pair(P, lr, w, s1, s2);
                 if (s1 > s2) { int tmp = s1; s1 = s2; s2 = tmp; }
                 if (s2 < n)
-                    any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, norm2 + s1, norm2 + s2, n, lane, tol2, floor2);
+                    any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk);
             }
             __syncthreads();
         }
@@ -360,7 +344,8 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int m
                           const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
-    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
+    bool derijk = ctx->opt_jacobi_derijk != 0;
+    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &derijk};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -372,7 +357,7 @@ static int run_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round,
                      const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2);
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2, ctx->opt_jacobi_derijk != 0);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -382,7 +367,7 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
                       const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_single_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2);
+    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2, ctx->opt_jacobi_derijk != 0);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -410,7 +395,7 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
     const double tol = jacobi_tol(n), tol2 = tol * tol;
     const int nr = n <= 64 ? 2 : n <= 128 ? 4 : n <= 256 ? 8 : n <= 512 ? 16 : 0;
 
-    const size_t single_bytes = ((size_t)n * n + n) * sizeof(double);
+    const size_t single_bytes = (size_t)n * n * sizeof(double);
     if (n >= 2 && single_bytes <= smem_cap && n <= 128) {
         int matches = (n + 1) / 2;
         int warps = matches < 32 ? matches : 32;
@@ -432,7 +417,7 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
         int nb = (n + b - 1) / b;
         if (nb & 1) nb++;
         if (nb < 2) nb = 2;
-        const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
+        const size_t smem = (size_t)2 * b * n * sizeof(double);
         if (nb / 2 <= ctx->sm_count) {
             switch (nr) {
                 case 8: NDMPS_TRY(run_persistent<8>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
