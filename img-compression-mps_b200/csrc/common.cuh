@@ -109,7 +109,9 @@ struct ndmps_ctx {
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
-    int64_t opt_jacobi_derijk = 1;
+    int64_t opt_jacobi_derijk = 0;        // dynamic swaps break the pair coverage of the parallel tournament
+    int64_t opt_jacobi_cached_norms = 0;
+    int64_t opt_jacobi_presort = 1;
     int64_t opt_verbose = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;
@@ -154,7 +156,8 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
          const void* b, int dtype_b, int64_t b_rs, int64_t b_cs,
          void* c, int dtype_c, int64_t ldc);
 int gram(ndmps_ctx* ctx, const void* m, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev);
-int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev);
+// tol_override > 0 loosens the relative off-diagonal threshold (float32 payloads do not need 1e-15)
+int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, double tol_override = 0.0);
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);
 
 #ifdef __CUDACC__

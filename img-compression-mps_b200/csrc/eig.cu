@@ -81,18 +81,24 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
 // convergence threshold, so the sweep count grows instead of shrinking.
 template <int NR>
 __device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lane, double tol2, double floor2,
-                                            bool derijk) {
+                                            bool derijk, double* nx = nullptr, double* ny = nullptr) {
     double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
+    const bool cached = nx != nullptr;                        // warp-uniform
     if (NR > 0) {
 #pragma unroll
         for (int t = 0; t < NR; t++) {
             int i = lane + 32 * t;
             xr[t] = i < n ? x[i] : 0.0;
             yr[t] = i < n ? y[i] : 0.0;
-            alpha = fma(xr[t], xr[t], alpha);
-            beta = fma(yr[t], yr[t], beta);
             gamma = fma(xr[t], yr[t], gamma);
+        }
+        if (!cached) {
+#pragma unroll
+            for (int t = 0; t < NR; t++) {
+                alpha = fma(xr[t], xr[t], alpha);
+                beta = fma(yr[t], yr[t], beta);
+            }
         }
     } else {
         for (int i = lane; i < n; i += 32) {
@@ -102,11 +108,17 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lan
             gamma = fma(a, b, gamma);
         }
     }
+    if (cached) {
+        gamma = warp_sum(gamma);
+        alpha = *nx;
+        beta = *ny;
+    } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {                        // three interleaved butterflies
-        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-        beta += __shfl_xor_sync(0xffffffffu, beta, o);
-        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+        for (int o = 16; o > 0; o >>= 1) {                    // three interleaved butterflies
+            alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+            beta += __shfl_xor_sync(0xffffffffu, beta, o);
+            gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+        }
     }
     // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
     // round-off and would keep the sweep from ever reporting convergence
@@ -134,6 +146,23 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lan
             double xv = x[i], yv = y[i];
             px[i] = c * xv - s * yv;
             py[i] = s * xv + c * yv;
+        }
+    }
+    if (cached) {
+        // exact update identities; when a column collapses they cancel, so recompute from the data
+        double na = alpha - t * gamma, nb = beta + t * gamma;
+        if (na < 0.01 * alpha || nb < 0.01 * beta) {
+            double ra = 0.0, rb = 0.0;
+            for (int i = lane; i < n; i += 32) {              // each lane re-reads what it wrote
+                ra = fma(px[i], px[i], ra);
+                rb = fma(py[i], py[i], rb);
+            }
+            na = warp_sum(ra);
+            nb = warp_sum(rb);
+        }
+        if (lane == 0) {
+            *nx = swap ? nb : na;
+            *ny = swap ? na : nb;
         }
     }
     return true;
@@ -167,8 +196,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 // L2, rotate, store back.  S: 2*b*n doubles.
 template <int NR>
 __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int nb, int round, int cta, double* S,
-                                                   double tol2, double floor2, bool derijk) {
+                                                   double tol2, double floor2, bool derijk, bool cache_norms) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* norm2 = S + (size_t)2 * b * n;
     int p, q;
     tournament_pair(nb, round, cta, p, q);
     const int colp0 = p * b, colq0 = q * b;
@@ -177,10 +207,19 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
     for (int lc = warp; lc < 2 * b; lc += b) {
         const bool isq = lc >= b;
         const int l = isq ? lc - b : lc;
+        double acc = 0.0;
         if (l < (isq ? cntq : cntp)) {
             const double* src = A + (size_t)((isq ? colq0 : colp0) + l) * n;
             double* dst = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+            for (int i = lane; i < n; i += 32) {
+                double v = __ldcg(src + i);
+                dst[i] = v;
+                acc = fma(v, v, acc);
+            }
+        }
+        if (cache_norms) {
+            acc = warp_sum(acc);
+            if (lane == 0) norm2[lc] = acc;
         }
     }
     __syncthreads();
@@ -194,7 +233,8 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
             const bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
             const bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
             if (v1 && v2)
-                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk);
+                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk,
+                                       cache_norms ? norm2 + s1 : nullptr, cache_norms ? norm2 + s2 : nullptr);
             __syncthreads();
         }
     } else {
@@ -202,7 +242,8 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
             int j = warp + k;
             j = j >= b ? j - b : j;
             if (warp < cntp && j < cntq)
-                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol2, floor2, derijk);
+                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol2, floor2, derijk,
+                                       cache_norms ? norm2 + warp : nullptr, cache_norms ? norm2 + b + j : nullptr);
             __syncthreads();
         }
     }
@@ -223,7 +264,7 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                         const double* floor2_ptr, bool derijk) {
+                         const double* floor2_ptr, bool derijk, bool cache_norms) {
     extern __shared__ double S[];
     const double floor2 = *floor2_ptr;
     unsigned epoch = 0;
@@ -231,7 +272,7 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
     bool converged = false;
     while (sweep < max_sweeps) {
         for (int round = 0; round < nb - 1; round++) {
-            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2, derijk);
+            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2, derijk, cache_norms);
             if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
             epoch++;
             grid_barrier(ctrl, epoch * gridDim.x);
@@ -248,9 +289,9 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr,
-                    bool derijk) {
+                    bool derijk, bool cache_norms) {
     extern __shared__ double S[];
-    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr, derijk);
+    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr, derijk, cache_norms);
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
@@ -311,6 +352,24 @@ __global__ void __launch_bounds__(256) null_floor_kernel(const double* __restric
     }
 }
 
+// copy column j of A to column rank(j) of B, rank = descending order of the column norms
+__global__ void __launch_bounds__(256)
+sort_columns_kernel(const double* __restrict__ A, const double* __restrict__ norms, int n, double* __restrict__ B) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    double mine = norms[warp];
+    int cnt = 0;
+    for (int k = lane; k < n; k += 32) {
+        double o = norms[k];
+        cnt += (o > mine || (o == mine && k < warp)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const double* src = A + (size_t)warp * n;
+    double* dst = B + (size_t)cnt * n;
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
 // descending rank of every column by counting (ties broken by index), then write
 // evals[rank] and the normalised column into evecs[:, rank] (row-major n x n)
 __global__ void __launch_bounds__(256)
@@ -344,8 +403,8 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int m
                           const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
-    bool derijk = ctx->opt_jacobi_derijk != 0;
-    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &derijk};
+    bool derijk = ctx->opt_jacobi_derijk != 0, cache = ctx->opt_jacobi_cached_norms != 0;
+    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &derijk, &cache};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -357,7 +416,8 @@ static int run_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round,
                      const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2, ctx->opt_jacobi_derijk != 0);
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2, ctx->opt_jacobi_derijk != 0,
+                                                                   ctx->opt_jacobi_cached_norms != 0);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -372,7 +432,7 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
     return NDMPS_OK;
 }
 
-int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* evecs_dev) {
+int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* evecs_dev, double tol_override) {
     NDMPS_REQUIRE(n64 >= 1 && n64 <= 16384, "eigh: n = %lld outside 1..16384", (long long)n64);
     const int n = (int)n64;
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
@@ -388,11 +448,21 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
     NDMPS_TRY(ctx->ws.get<double>((size_t)n, &norms));
     NDMPS_TRY(ctx->ws.get<double>(1, &floor2));
     const int ngrid = (n * 32 + 255) / 256;
-    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, n, norms);
+    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_in, n, norms);
     NDMPS_LAUNCH_CHECK(ctx);
     null_floor_kernel<<<1, 256, 0, ctx->stream>>>(norms, n, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
-    const double tol = jacobi_tol(n), tol2 = tol * tol;
+    // start from columns sorted by norm (a static permutation: the left singular vectors of
+    // G Pi are those of G); sorted starts converge in fewer sweeps
+    double* a_dev = a_in;
+    if (ctx->opt_jacobi_presort && n > 2) {
+        NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &a_dev));
+        sort_columns_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_in, norms, n, a_dev);
+        NDMPS_LAUNCH_CHECK(ctx);
+    }
+    double tol = jacobi_tol(n);
+    if (tol_override > tol) tol = tol_override;
+    const double tol2 = tol * tol;
     const int nr = n <= 64 ? 2 : n <= 128 ? 4 : n <= 256 ? 8 : n <= 512 ? 16 : 0;
 
     const size_t single_bytes = (size_t)n * n * sizeof(double);
@@ -417,7 +487,7 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n64, double* evals_dev, double* 
         int nb = (n + b - 1) / b;
         if (nb & 1) nb++;
         if (nb < 2) nb = 2;
-        const size_t smem = (size_t)2 * b * n * sizeof(double);
+        const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
         if (nb / 2 <= ctx->sm_count) {
             switch (nr) {
                 case 8: NDMPS_TRY(run_persistent<8>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
@@ -467,7 +537,7 @@ extern "C" {
 int ndmps_eigh(ndmps_ctx_t* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, int* sweeps_out_host) {
     NDMPS_REQUIRE(ctx && a_dev && evals_dev && evecs_dev, "ndmps_eigh: NULL argument");
     NDMPS_TRY(ctx->ws.reset(ctx->stream));
-    NDMPS_TRY(eigh(ctx, a_dev, n, evals_dev, evecs_dev));
+    NDMPS_TRY(eigh(ctx, a_dev, n, evals_dev, evecs_dev, 0.0));
     if (sweeps_out_host) *sweeps_out_host = ctx->last_eig_sweeps;
     return NDMPS_OK;
 }
