@@ -109,9 +109,7 @@ struct ndmps_ctx {
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
-    int64_t opt_jacobi_derijk = 0;        // dynamic swaps break the pair coverage of the parallel tournament
-    int64_t opt_jacobi_cached_norms = 0;
-    int64_t opt_jacobi_presort = 1;
+    int64_t opt_jacobi_presort = 0;
     int64_t opt_verbose = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;

@@ -19,9 +19,13 @@
 //
 // Per rotation the latency chain is what matters (the FP64 work is tiny), so:
 //   * the three reductions of a pair (|x|^2, |y|^2, x.y) run as interleaved butterflies;
+//   * short columns (n <= 128) use 8 lanes per pair, four pairs per warp;
+//   * in the cross rounds of a block pair the P column stays in registers and only the Q
+//     columns stream through shared memory (the long-column case is smem-bandwidth bound);
 //   * tangent / cosine come from MUFU rcp / rsqrt seeds plus Newton steps (full float64
 //     accuracy) instead of the IEEE division / square-root instruction sequences;
-//   * de Rijk ordering: after a rotation the larger column goes to the lower slot.
+// (de Rijk's dynamic column swaps were tried and dropped: in a parallel tournament they break
+// the once-per-sweep pair coverage and the sweep count explodes.)
 #include "common.cuh"
 
 namespace ndmps {
@@ -70,37 +74,53 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
     s = c * t;
 }
 
-// Orthogonalise columns x, y (length n, shared memory).
-// NR > 0: n <= 32*NR, columns staged in registers.  NR == 0: generic n, two passes.
-// derijk: after a rotation the larger column goes to slot x (the lower slot).
-// Returns true if a rotation was applied (warp-uniform).
-//
-// The squared norms are recomputed with every visit (three reductions that pipeline with
-// each other): cached norms updated by a' = a - t g drift by a few eps per rotation, and for
-// nearly degenerate pairs that drift ends up in the angle and leaves residuals right at the
-// convergence threshold, so the sweep count grows instead of shrinking.
-template <int NR>
-__device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lane, double tol2, double floor2,
-                                            bool derijk, double* nx = nullptr, double* ny = nullptr) {
-    double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
+// Orthogonalise columns x, y (length n, shared memory) with a group of LP lanes (LP = 32: one
+// pair per warp; LP = 8: four pairs per warp, for short columns where the butterfly
+// reductions and the redundant per-lane rotation math would otherwise dominate).
+// li: lane index inside the group.  Every lane of the warp must call this (the shuffles
+// use the full mask); `valid` masks out groups without a pair.  Squared norms are
+// recomputed at every visit: three interleaved butterflies.
+template <int NR, int LP>
+__device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li, bool valid, double tol2, double floor2) {
+    double xr[NR], yr[NR];
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
-    const bool cached = nx != nullptr;                        // warp-uniform
-    if (NR > 0) {
 #pragma unroll
-        for (int t = 0; t < NR; t++) {
-            int i = lane + 32 * t;
-            xr[t] = i < n ? x[i] : 0.0;
-            yr[t] = i < n ? y[i] : 0.0;
-            gamma = fma(xr[t], yr[t], gamma);
-        }
-        if (!cached) {
+    for (int t = 0; t < NR; t++) {
+        const int i = li + LP * t;
+        const bool in = valid && i < n;
+        xr[t] = in ? x[i] : 0.0;
+        yr[t] = in ? y[i] : 0.0;
+        alpha = fma(xr[t], xr[t], alpha);
+        beta = fma(yr[t], yr[t], beta);
+        gamma = fma(xr[t], yr[t], gamma);
+    }
 #pragma unroll
-            for (int t = 0; t < NR; t++) {
-                alpha = fma(xr[t], xr[t], alpha);
-                beta = fma(yr[t], yr[t], beta);
-            }
+    for (int o = LP / 2; o > 0; o >>= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+    }
+    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
+    // round-off and would keep the sweep from ever reporting convergence
+    if (!valid || !(alpha > floor2) || !(beta > floor2)) return false;
+    if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    double c, s, t;
+    rotation(alpha, beta, gamma, c, s, t);
+#pragma unroll
+    for (int tt = 0; tt < NR; tt++) {
+        const int i = li + LP * tt;
+        if (i < n) {
+            x[i] = c * xr[tt] - s * yr[tt];
+            y[i] = s * xr[tt] + c * yr[tt];
         }
-    } else {
+    }
+    return true;
+}
+
+// same for columns of any length (n > 512): one pair per warp, two passes over shared memory
+__device__ __forceinline__ bool rotate_generic(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2) {
+    double alpha = 0.0, beta = 0.0, gamma = 0.0;
+    if (valid) {
         for (int i = lane; i < n; i += 32) {
             double a = x[i], b = y[i];
             alpha = fma(a, a, alpha);
@@ -108,64 +128,101 @@ __device__ __forceinline__ bool rotate_pair(double* x, double* y, int n, int lan
             gamma = fma(a, b, gamma);
         }
     }
-    if (cached) {
-        gamma = warp_sum(gamma);
-        alpha = *nx;
-        beta = *ny;
-    } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {                    // three interleaved butterflies
-            alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-            beta += __shfl_xor_sync(0xffffffffu, beta, o);
-            gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
     }
-    // columns whose norm is below n*eps*|G| are numerically null: rotating them only churns
-    // round-off and would keep the sweep from ever reporting convergence
-    if (!(alpha > floor2) || !(beta > floor2)) return false;
+    if (!valid || !(alpha > floor2) || !(beta > floor2)) return false;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;
     double c, s, t;
     rotation(alpha, beta, gamma, c, s, t);
-    const bool swap = derijk && (alpha - t * gamma < beta + t * gamma);
-    double* px = swap ? y : x;
-    double* py = swap ? x : y;
-    if (NR > 0) {
-#pragma unroll
-        for (int tt = 0; tt < NR; tt++) {
-            int i = lane + 32 * tt;
-            double a = c * xr[tt] - s * yr[tt];
-            double b = s * xr[tt] + c * yr[tt];
-            if (i < n) {
-                px[i] = a;
-                py[i] = b;
-            }
-        }
-    } else {
-        // x, y may be swapped in place: read both before writing either
-        for (int i = lane; i < n; i += 32) {
-            double xv = x[i], yv = y[i];
-            px[i] = c * xv - s * yv;
-            py[i] = s * xv + c * yv;
-        }
-    }
-    if (cached) {
-        // exact update identities; when a column collapses they cancel, so recompute from the data
-        double na = alpha - t * gamma, nb = beta + t * gamma;
-        if (na < 0.01 * alpha || nb < 0.01 * beta) {
-            double ra = 0.0, rb = 0.0;
-            for (int i = lane; i < n; i += 32) {              // each lane re-reads what it wrote
-                ra = fma(px[i], px[i], ra);
-                rb = fma(py[i], py[i], rb);
-            }
-            na = warp_sum(ra);
-            nb = warp_sum(rb);
-        }
-        if (lane == 0) {
-            *nx = swap ? nb : na;
-            *ny = swap ? na : nb;
-        }
+    for (int i = lane; i < n; i += 32) {
+        double xv = x[i], yv = y[i];
+        x[i] = c * xv - s * yv;
+        y[i] = s * xv + c * yv;
     }
     return true;
+}
+
+template <int NR>
+__device__ __forceinline__ bool rotate_warp(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2) {
+    if constexpr (NR > 0) return rotate_group<NR, 32>(x, y, n, lane, valid, tol2, floor2);
+    else return rotate_generic(x, y, n, lane, valid, tol2, floor2);
+}
+
+// The b cross rounds of one block pair with the P column held in REGISTERS: warp w keeps
+// column P_w for all b rounds and only the Q columns stream through shared memory, which
+// halves the shared-memory traffic that bounds the long-column case.  Squared norms are
+// cached for the duration of the block pair (<= b rotations per column) and updated by the
+// exact identities a' = a - t g, b' = b + t g; they are recomputed from the data whenever a
+// column collapses (catastrophic cancellation) and at every block load.
+template <int NR>
+__device__ __forceinline__ bool cross_rounds_stationary(double* S, double* norm2, int n, int b, int cntp, int cntq,
+                                                        int warp, int lane, double tol2, double floor2) {
+    double xr[NR];
+    double* x = S + (size_t)warp * n;
+    const bool have_x = warp < cntp;
+#pragma unroll
+    for (int t = 0; t < NR; t++) {
+        const int i = lane + 32 * t;
+        xr[t] = (have_x && i < n) ? x[i] : 0.0;
+    }
+    double alpha = have_x ? norm2[warp] : 0.0;
+    bool any = false;
+    for (int k = 0; k < b; k++) {
+        int j = warp + k;
+        j = j >= b ? j - b : j;
+        const bool valid = have_x && j < cntq;
+        double* y = S + (size_t)(b + j) * n;
+        double yr[NR];
+        double gamma = 0.0;
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            yr[t] = (valid && i < n) ? y[i] : 0.0;
+            gamma = fma(xr[t], yr[t], gamma);
+        }
+        gamma = warp_sum(gamma);
+        const double beta = valid ? norm2[b + j] : 0.0;
+        if (valid && alpha > floor2 && beta > floor2 && gamma * gamma > tol2 * alpha * beta) {
+            double c, s, t;
+            rotation(alpha, beta, gamma, c, s, t);
+            double ra = 0.0, rb = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < NR; tt++) {
+                const int i = lane + 32 * tt;
+                const double xn = c * xr[tt] - s * yr[tt];
+                const double yn = s * xr[tt] + c * yr[tt];
+                xr[tt] = xn;
+                if (i < n) y[i] = yn;
+                yr[tt] = yn;
+            }
+            double na = alpha - t * gamma, nb = beta + t * gamma;
+            if (na < 0.01 * alpha || nb < 0.01 * beta) {      // warp-uniform
+#pragma unroll
+                for (int tt = 0; tt < NR; tt++) {
+                    ra = fma(xr[tt], xr[tt], ra);
+                    rb = fma(yr[tt], yr[tt], rb);
+                }
+                na = warp_sum(ra);
+                nb = warp_sum(rb);
+            }
+            alpha = na;
+            if (lane == 0) norm2[b + j] = nb;
+            any = true;
+        }
+        __syncthreads();
+    }
+    if (any) {
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            if (i < n) x[i] = xr[t];
+        }
+    }
+    return any;
 }
 
 // slot pair of a round-robin tournament over P (even) players, match `w` of round `lr`
@@ -193,10 +250,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 }
 
 // One CTA, one block pair (p, q) of one tournament round: load both column blocks from
-// L2, rotate, store back.  S: 2*b*n doubles.
+// L2, rotate, store back.  S: 2*b*n doubles followed by 2*b cached squared norms.
 template <int NR>
 __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int nb, int round, int cta, double* S,
-                                                   double tol2, double floor2, bool derijk, bool cache_norms) {
+                                                   double tol2, double floor2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* norm2 = S + (size_t)2 * b * n;
     int p, q;
@@ -217,10 +274,8 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
                 acc = fma(v, v, acc);
             }
         }
-        if (cache_norms) {
-            acc = warp_sum(acc);
-            if (lane == 0) norm2[lc] = acc;
-        }
+        acc = warp_sum(acc);
+        if (lane == 0) norm2[lc] = acc;
     }
     __syncthreads();
     bool any = false;
@@ -229,21 +284,19 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
         for (int lr = 0; lr < P - 1; lr++) {
             int s1, s2;
             tournament_pair(P, lr, warp, s1, s2);
-            if (s1 > s2) { int tmp = s1; s1 = s2; s2 = tmp; }
             const bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
             const bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
-            if (v1 && v2)
-                any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk,
-                                       cache_norms ? norm2 + s1 : nullptr, cache_norms ? norm2 + s2 : nullptr);
+            any |= rotate_warp<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, v1 && v2, tol2, floor2);
             __syncthreads();
         }
+    } else if constexpr (NR > 0) {
+        any = cross_rounds_stationary<NR>(S, norm2, n, b, cntp, cntq, warp, lane, tol2, floor2);
+        __syncthreads();
     } else {
         for (int k = 0; k < b; k++) {
             int j = warp + k;
             j = j >= b ? j - b : j;
-            if (warp < cntp && j < cntq)
-                any |= rotate_pair<NR>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, tol2, floor2, derijk,
-                                       cache_norms ? norm2 + warp : nullptr, cache_norms ? norm2 + b + j : nullptr);
+            any |= rotate_warp<0>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, warp < cntp && j < cntq, tol2, floor2);
             __syncthreads();
         }
     }
@@ -264,7 +317,7 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                         const double* floor2_ptr, bool derijk, bool cache_norms) {
+                         const double* floor2_ptr) {
     extern __shared__ double S[];
     const double floor2 = *floor2_ptr;
     unsigned epoch = 0;
@@ -272,7 +325,7 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
     bool converged = false;
     while (sweep < max_sweeps) {
         for (int round = 0; round < nb - 1; round++) {
-            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2, derijk, cache_norms);
+            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2);
             if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
             epoch++;
             grid_barrier(ctrl, epoch * gridDim.x);
@@ -288,22 +341,22 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
 // number of co-resident CTAs (n > ~4700): one launch per round.
 template <int NR>
 __global__ void __launch_bounds__(512)
-jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr,
-                    bool derijk, bool cache_norms) {
+jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr) {
     extern __shared__ double S[];
-    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr, derijk, cache_norms);
+    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr);
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
-// Whole matrix in one CTA: sweep until no rotation happens.  block = 32*W threads,
-// dynamic smem = n*n doubles.  ctrl[1] = sweeps used (negative: not converged).
+// Whole matrix in one CTA (n <= 128): sweep until no rotation happens.  Eight lanes per column
+// pair, four pairs per warp; block = 32*W threads, dynamic smem = n*n doubles.
+// ctrl[1] = sweeps used (negative: not converged).
 template <int NR>
-__global__ void __launch_bounds__(1024)
-jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double tol2, const double* floor2_ptr,
-                     bool derijk) {
+__global__ void __launch_bounds__(512)
+jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double tol2, const double* floor2_ptr) {
     extern __shared__ double S[];
     const double floor2 = *floor2_ptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const int grp = lane >> 3, li = lane & 7;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[i] = A[i];
     __syncthreads();
     const int P = (n + 1) & ~1;          // pad to an even number of players; player n (if any) is a bye
@@ -313,12 +366,12 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
     while (!done && sweep < max_sweeps) {
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
-            for (int w = warp; w < matches; w += W) {
-                int s1, s2;
-                tournament_pair(P, lr, w, s1, s2);
-                if (s1 > s2) { int tmp = s1; s1 = s2; s2 = tmp; }
-                if (s2 < n)
-                    any |= rotate_pair<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, tol2, floor2, derijk);
+            for (int m0 = warp * 4; m0 < matches; m0 += W * 4) {     // warp-uniform trip count
+                const int m = m0 + grp;
+                int s1 = 0, s2 = 0;
+                if (m < matches) tournament_pair(P, lr, m, s1, s2);
+                const bool valid = m < matches && s1 < n && s2 < n;
+                any |= rotate_group<NR, 8>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, li, valid, tol2, floor2);
             }
             __syncthreads();
         }
@@ -403,8 +456,7 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int m
                           const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
-    bool derijk = ctx->opt_jacobi_derijk != 0, cache = ctx->opt_jacobi_cached_norms != 0;
-    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &derijk, &cache};
+    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -416,8 +468,7 @@ static int run_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round,
                      const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2, ctx->opt_jacobi_derijk != 0,
-                                                                   ctx->opt_jacobi_cached_norms != 0);
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -427,7 +478,7 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
                       const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_single_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2, ctx->opt_jacobi_derijk != 0);
+    jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -463,14 +514,16 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     double tol = jacobi_tol(n);
     if (tol_override > tol) tol = tol_override;
     const double tol2 = tol * tol;
-    const int nr = n <= 64 ? 2 : n <= 128 ? 4 : n <= 256 ? 8 : n <= 512 ? 16 : 0;
+    const int nr = n <= 256 ? 8 : n <= 512 ? 16 : 0;      // rows per lane of the block kernels
 
     const size_t single_bytes = (size_t)n * n * sizeof(double);
     if (n >= 2 && single_bytes <= smem_cap && n <= 128) {
         int matches = (n + 1) / 2;
-        int warps = matches < 32 ? matches : 32;
-        if (nr == 2) NDMPS_TRY(run_single<2>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
-        else NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        int warps = (matches + 3) / 4;                        // four pairs per warp
+        if (warps > 16) warps = 16;
+        if (n <= 32) NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        else if (n <= 64) NDMPS_TRY(run_single<8>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        else NDMPS_TRY(run_single<16>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (host_flag[0] <= 0) {
