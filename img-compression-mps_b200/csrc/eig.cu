@@ -347,7 +347,7 @@ jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, 
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
-// Whole matrix in one CTA (n <= 128): sweep until no rotation happens.  Eight lanes per column
+// Whole matrix in one CTA (n <= 32; larger ones are faster on the block path): sweep until no rotation happens.  Eight lanes per column
 // pair, four pairs per warp; block = 32*W threads, dynamic smem = n*n doubles.
 // ctrl[1] = sweeps used (negative: not converged).
 template <int NR>
@@ -517,13 +517,11 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     const int nr = n <= 256 ? 8 : n <= 512 ? 16 : 0;      // rows per lane of the block kernels
 
     const size_t single_bytes = (size_t)n * n * sizeof(double);
-    if (n >= 2 && single_bytes <= smem_cap && n <= 128) {
+    if (n >= 2 && single_bytes <= smem_cap && n <= 32) {
         int matches = (n + 1) / 2;
         int warps = (matches + 3) / 4;                        // four pairs per warp
         if (warps > 16) warps = 16;
-        if (n <= 32) NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
-        else if (n <= 64) NDMPS_TRY(run_single<8>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
-        else NDMPS_TRY(run_single<16>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (host_flag[0] <= 0) {
