@@ -572,6 +572,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         }
     }
     ctx->last_eig_sweeps = sweeps_used;
+    if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh n = %d: %d sweeps (presort %d)\n", n, sweeps_used, (int)ctx->opt_jacobi_presort);
     column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, n, norms);
     NDMPS_LAUNCH_CHECK(ctx);
     sort_extract_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, norms, n, evals_dev, evecs_dev);

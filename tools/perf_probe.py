@@ -75,8 +75,9 @@ def main(which):
             print(f"psnr {shape}: {ms:.3f} ms ({a.numel() * 8 / ms / 1e6:.0f} GB/s)", flush=True)
     if "stages" in which:
         from imgcompressionmps.core.ndmps import NDMPS
+        from bench import synthetic_volume
         for n in (256,):
-            x = torch.rand((n, n, n), dtype=torch.float32, device="cuda", generator=g)
+            x = torch.from_numpy(synthetic_volume((n, n, n), 2026)).cuda()
             for _ in range(2):
                 NDMPS.from_tensor(x, max_bond=64).to_tensor_device()
             ctx.profile(True)
