@@ -252,15 +252,15 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 // One CTA, one block pair (p, q) of one tournament round: load both column blocks from
 // L2, rotate, store back.  S: 2*b*n doubles followed by 2*b cached squared norms.
 template <int NR>
-__device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int nb, int round, int cta, double* S,
-                                                   double tol2, double floor2) {
+__device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, int b, int nb, int round, int cta,
+                                                   double* S, double tol2, double floor2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* norm2 = S + (size_t)2 * b * n;
     int p, q;
     tournament_pair(nb, round, cta, p, q);
     const int colp0 = p * b, colq0 = q * b;
-    int cntp = n - colp0; cntp = cntp < 0 ? 0 : (cntp > b ? b : cntp);
-    int cntq = n - colq0; cntq = cntq < 0 ? 0 : (cntq > b ? b : cntq);
+    int cntp = ncols - colp0; cntp = cntp < 0 ? 0 : (cntp > b ? b : cntp);
+    int cntq = ncols - colq0; cntq = cntq < 0 ? 0 : (cntq > b ? b : cntq);
     for (int lc = warp; lc < 2 * b; lc += b) {
         const bool isq = lc >= b;
         const int l = isq ? lc - b : lc;
@@ -312,11 +312,12 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int b, int 
     return any;
 }
 
-// Persistent solve: grid = nb/2 CTAs (cooperative launch), block = 32*b threads.
+// Persistent solve of an n x ncols column set (column j at A + j*n): grid = nb/2 CTAs
+// (cooperative launch), block = 32*b threads.
 // ctrl[0]: barrier counter, ctrl[1]: sweeps used (negative = not converged), ctrl[2+s]: sweep flags.
 template <int NR>
 __global__ void __launch_bounds__(512)
-jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
+jacobi_persistent_kernel(double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
                          const double* floor2_ptr) {
     extern __shared__ double S[];
     const double floor2 = *floor2_ptr;
@@ -325,7 +326,7 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
     bool converged = false;
     while (sweep < max_sweeps) {
         for (int round = 0; round < nb - 1; round++) {
-            bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, floor2);
+            bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, floor2);
             if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
             epoch++;
             grid_barrier(ctrl, epoch * gridDim.x);
@@ -341,9 +342,10 @@ jacobi_persistent_kernel(double* A, int n, int b, int nb, int max_sweeps, unsign
 // number of co-resident CTAs (n > ~4700): one launch per round.
 template <int NR>
 __global__ void __launch_bounds__(512)
-jacobi_round_kernel(double* A, int n, int b, int nb, int round, unsigned* flag, double tol2, const double* floor2_ptr) {
+jacobi_round_kernel(double* A, int n, int ncols, int b, int nb, int round, unsigned* flag, double tol2,
+                    const double* floor2_ptr) {
     extern __shared__ double S[];
-    bool any = process_block_pair<NR>(A, n, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr);
+    bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr);
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
@@ -382,10 +384,11 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
     if (threadIdx.x == 0) ((int*)ctrl)[1] = done ? sweep : -sweep;
 }
 
-// lambda_j = |column j|, one warp per column
-__global__ void __launch_bounds__(256) column_norms_kernel(const double* __restrict__ A, int n, double* __restrict__ norms) {
+// |column j| for j < ncols (columns of length n), one warp per column
+__global__ void __launch_bounds__(256)
+column_norms_kernel(const double* __restrict__ A, int n, int ncols, double* __restrict__ norms) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
+    if (warp >= ncols) return;
     const double* col = A + (size_t)warp * n;
     double s = 0.0;
     for (int i = lane; i < n; i += 32) s = fma(col[i], col[i], s);
@@ -394,10 +397,11 @@ __global__ void __launch_bounds__(256) column_norms_kernel(const double* __restr
 }
 
 // floor2 = (n * eps * max_j |column j|)^2 : squared norm below which a column counts as null
-__global__ void __launch_bounds__(256) null_floor_kernel(const double* __restrict__ norms, int n, double* __restrict__ floor2) {
+__global__ void __launch_bounds__(256)
+null_floor_kernel(const double* __restrict__ norms, int n, int ncols, double* __restrict__ floor2) {
     __shared__ double scratch[32];
     double m = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, norms[i]);
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) m = fmax(m, norms[i]);
     m = block_max(m, scratch);
     if (threadIdx.x == 0) {
         double f = (double)n * 2.220446049250313e-16 * m;
@@ -424,25 +428,133 @@ sort_columns_kernel(const double* __restrict__ A, const double* __restrict__ nor
 }
 
 // descending rank of every column by counting (ties broken by index), then write
-// evals[rank] and the normalised column into evecs[:, rank] (row-major n x n)
+// evals[rank] (the norm, or its square when the columns are those of a Cholesky factor) and
+// the normalised column into evecs[:, rank] (row-major n x n).  Ranks >= ncols are zero-filled.
 __global__ void __launch_bounds__(256)
-sort_extract_kernel(const double* __restrict__ A, const double* __restrict__ norms, int n, double* __restrict__ evals,
-                    double* __restrict__ evecs) {
+sort_extract_kernel(const double* __restrict__ A, const double* __restrict__ norms, int n, int ncols, int square,
+                    double* __restrict__ evals, double* __restrict__ evecs) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
+    if (warp >= ncols) {                                     // rank-deficient tail
+        if (lane == 0) evals[warp] = 0.0;
+        for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + warp] = 0.0;
+        return;
+    }
     double mine = norms[warp];
     int cnt = 0;
-    for (int k = lane; k < n; k += 32) {
+    for (int k = lane; k < ncols; k += 32) {
         double o = norms[k];
         cnt += (o > mine || (o == mine && k < warp)) ? 1 : 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     int rank = cnt;
-    if (lane == 0) evals[rank] = mine;
+    if (lane == 0) evals[rank] = square ? mine * mine : mine;
     double inv = mine > 0.0 ? 1.0 / mine : 0.0;
     const double* col = A + (size_t)warp * n;
     for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + rank] = col[i] * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pivoted Cholesky G = L L^T (diagonal pivoting, rank revealing), the preconditioner of the
+// Jacobi solve: one-sided Jacobi on the columns of L works on sqrt(lambda) instead of lambda,
+// on rank(G) columns instead of n, and L's columns are graded and nearly orthogonal - on the
+// bond Gram matrices of real volumes this halves the sweep count (profiles/r01_jacobi_sweeps.md).
+//
+// Persistent cooperative kernel, rows distributed over CTAs (each keeps its rows of the running
+// Schur complement in shared memory).  Per step: every CTA publishes its best remaining diagonal
+// entry TOGETHER with that row (so one grid barrier per step is enough), all CTAs pick the same
+// winner, scale it into column k of L and update their own rows.  L is produced column-major in
+// the ORIGINAL row order (no permutation to undo: G = sum_k l_k l_k^T).
+// ---------------------------------------------------------------------------------------------
+struct CholCand { double val; int row; int pad; };
+
+__global__ void __launch_bounds__(256)
+pivoted_cholesky_kernel(const double* __restrict__ G, int n, int rows_per, double* __restrict__ Lcol,
+                        double* cand_rows, CholCand* cand, unsigned* ctrl, double stop_rel) {
+    extern __shared__ double sm[];
+    double* slab = sm;                                   // rows_per x n
+    double* piv = slab + (size_t)rows_per * n;           // n
+    double* lrow = piv + n;                              // rows_per
+    int* chosen = reinterpret_cast<int*>(lrow + rows_per);   // rows_per
+    __shared__ double s_val[160];
+    __shared__ int s_row[160];
+    __shared__ int s_cta[160];
+    __shared__ int s_best;
+    const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
+    const int row0 = cta * rows_per;
+    int nrows = n - row0;
+    nrows = nrows < 0 ? 0 : (nrows > rows_per ? rows_per : nrows);
+    for (int idx = tid; idx < nrows * n; idx += blockDim.x) slab[idx] = G[(size_t)row0 * n + idx];
+    if (tid < rows_per) chosen[tid] = tid < nrows ? 0 : 1;
+    __syncthreads();
+    double p0 = 0.0;
+    int rank = n;
+    for (int k = 0; k < n; k++) {
+        // ---- publish the local candidate (value, row index, the row itself) ----
+        if (tid == 0) {
+            double best = -1.0;
+            int bi = -1;
+            for (int r = 0; r < nrows; r++) {
+                double d = slab[(size_t)r * n + row0 + r];
+                if (!chosen[r] && d > best) { best = d; bi = r; }
+            }
+            s_best = bi;
+            CholCand c;
+            c.val = best;
+            c.row = bi >= 0 ? row0 + bi : -1;
+            c.pad = 0;
+            cand[(size_t)(k & 1) * ncta + cta] = c;
+        }
+        __syncthreads();
+        const int bi = s_best;
+        if (bi >= 0) {
+            double* dst = cand_rows + ((size_t)(k & 1) * ncta + cta) * n;
+            for (int c = tid; c < n; c += blockDim.x) __stcg(dst + c, slab[(size_t)bi * n + c]);
+        }
+        grid_barrier(ctrl, (unsigned)(k + 1) * ncta);
+        // ---- every CTA picks the same winner ----
+        if (tid < ncta) {
+            const CholCand* cp = cand + (size_t)(k & 1) * ncta + tid;
+            s_val[tid] = __ldcg(&cp->val);
+            s_row[tid] = __ldcg(&cp->row);
+            s_cta[tid] = tid;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int w = -1;
+            for (int t = 0; t < ncta; t++) {
+                if (s_row[t] < 0) continue;
+                if (w < 0 || s_val[t] > s_val[w] || (s_val[t] == s_val[w] && s_row[t] < s_row[w])) w = t;
+            }
+            s_best = w;
+        }
+        __syncthreads();
+        const int w = s_best;
+        const double pval = w >= 0 ? s_val[w] : -1.0;
+        const int prow = w >= 0 ? s_row[w] : -1;
+        if (k == 0) p0 = pval;
+        if (w < 0 || !(pval > stop_rel * p0) || !(pval > 0.0)) { rank = k; break; }   // uniform across the grid
+        const double* src = cand_rows + ((size_t)(k & 1) * ncta + w) * n;
+        for (int c = tid; c < n; c += blockDim.x) piv[c] = __ldcg(src + c);
+        const double root = sqrt(pval), inv = 1.0 / root;
+        __syncthreads();
+        if (tid < nrows) {
+            double l;
+            if (row0 + tid == prow) { l = root; chosen[tid] = 1; }
+            else if (!chosen[tid]) l = slab[(size_t)tid * n + prow] * inv;
+            else l = 0.0;
+            lrow[tid] = l;
+            __stcg(Lcol + (size_t)k * n + row0 + tid, l);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nrows * n; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            if (!chosen[r]) slab[idx] = fma(-lrow[r], piv[c] * inv, slab[idx]);
+        }
+        __syncthreads();
+    }
+    if (cta == 0 && tid == 0) ((int*)ctrl)[1] = rank;
 }
 
 template <class K>
@@ -452,11 +564,11 @@ static int raise_smem(K kernel, const ndmps_ctx* ctx) {
 }
 
 template <int NR>
-static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                          const double* floor2, size_t smem) {
+static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl,
+                          double tol2, const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
-    void* args[] = {&A, &n, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
+    void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -464,11 +576,11 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int b, int nb, int m
 }
 
 template <int NR>
-static int run_round(ndmps_ctx* ctx, double* A, int n, int b, int nb, int round, unsigned* flag, double tol2,
+static int run_round(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb, int round, unsigned* flag, double tol2,
                      const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
-    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, b, nb, round, flag, tol2, floor2);
+    jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, ncols, b, nb, round, flag, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -483,45 +595,133 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
     return NDMPS_OK;
 }
 
+// Jacobi sweeps over the ncols columns (length n) stored at A + j*n, block path.
+static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double tol2, const double* floor2, int* sweeps_used) {
+    const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
+    const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 1024 : 0;
+    unsigned* ctrl = nullptr;   // [0] barrier counter, [1] sweeps used, [2..] per-sweep rotation flags
+    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)max_sweeps + 4, &ctrl));
+    NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, ((size_t)max_sweeps + 4) * sizeof(unsigned), ctx->stream));
+    int* host_flag = reinterpret_cast<int*>(ctx->pinned);
+    const int nr = n <= 256 ? 8 : n <= 512 ? 16 : 0;      // rows per lane of the block kernels
+    // block size: as many columns as shared memory allows, at most 16 warps, tunable
+    int b = (int)((smem_cap - 512) / (16 * (size_t)n));
+    if (b > 16) b = 16;
+    if (ctx->opt_jacobi_block > 0 && ctx->opt_jacobi_block < b) b = (int)ctx->opt_jacobi_block;
+    NDMPS_REQUIRE(b >= 1, "eigh: n = %d does not fit a column pair in shared memory", n);
+    while (b > 1 && (ncols + b - 1) / b < 2) b /= 2;      // at least two blocks
+    int nb = (ncols + b - 1) / b;
+    if (nb & 1) nb++;
+    if (nb < 2) nb = 2;
+    const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
+    if (nb / 2 <= ctx->sm_count) {
+        switch (nr) {
+            case 8: NDMPS_TRY(run_persistent<8>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+            case 16: NDMPS_TRY(run_persistent<16>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+            default: NDMPS_TRY(run_persistent<0>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+        }
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (host_flag[0] <= 0) {
+            set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, cols = %d, b = %d)", max_sweeps, n, ncols, b);
+            return NDMPS_ERR_NOCONV;
+        }
+        *sweeps_used = host_flag[0];
+        return NDMPS_OK;
+    }
+    bool converged = false;
+    for (int s = 0; s < max_sweeps && !converged; s++) {
+        unsigned* flag = ctrl + 2 + s;
+        for (int round = 0; round < nb - 1; round++)
+            NDMPS_TRY(run_round<0>(ctx, A, n, ncols, b, nb, round, flag, tol2, floor2, smem));
+        *sweeps_used = s + 1;
+        if (s >= 3) {
+            NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            converged = host_flag[0] == 0;
+        }
+    }
+    if (!converged) {
+        set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, cols = %d, b = %d)", max_sweeps, n, ncols, b);
+        return NDMPS_ERR_NOCONV;
+    }
+    return NDMPS_OK;
+}
+
+// G = L L^T with diagonal pivoting; returns the numerical rank (host) and L column-major.
+static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol, int* rank_out) {
+    int rows_per = (n + 63) / 64;
+    int ncta = (n + rows_per - 1) / rows_per;
+    while (ncta > ctx->sm_count || ncta > 160) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }
+    const size_t smem = ((size_t)rows_per * n + n + rows_per) * sizeof(double) + (size_t)rows_per * sizeof(int) + 16;
+    NDMPS_REQUIRE(smem <= ctx->smem_optin - 4096, "pivoted_cholesky: n = %d does not fit shared memory", n);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NDMPS_CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ctx->smem_optin));
+        attr_set = true;
+    }
+    double* cand_rows = nullptr;
+    CholCand* cand = nullptr;
+    unsigned* ctrl = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)2 * ncta * n, &cand_rows));
+    NDMPS_TRY(ctx->ws.get<CholCand>((size_t)2 * ncta, &cand));
+    NDMPS_TRY(ctx->ws.get<unsigned>(4, &ctrl));
+    NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 4 * sizeof(unsigned), ctx->stream));
+    double stop_rel = 2.220446049250313e-16;
+    void* args[] = {&G, &n, &rows_per, &Lcol, &cand_rows, &cand, &ctrl, &stop_rel};
+    NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)pivoted_cholesky_kernel, dim3(ncta), dim3(256), args, smem, ctx->stream));
+    ctx->launches++;
+    int* host_flag = reinterpret_cast<int*>(ctx->pinned);
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *rank_out = host_flag[0];
+    return NDMPS_OK;
+}
+
 int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* evecs_dev, double tol_override) {
     NDMPS_REQUIRE(n64 >= 1 && n64 <= 16384, "eigh: n = %lld outside 1..16384", (long long)n64);
     const int n = (int)n64;
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
     const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 1024 : 0;
     NDMPS_TRY(ensure_pinned(ctx, 64));
-    unsigned* ctrl = nullptr;   // [0] barrier counter, [1] sweeps used, [2..] per-sweep rotation flags
-    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)max_sweeps + 4, &ctrl));
-    NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, ((size_t)max_sweeps + 4) * sizeof(unsigned), ctx->stream));
-    int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     int sweeps_used = 0;
     double* norms = nullptr;
     double* floor2 = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)n, &norms));
     NDMPS_TRY(ctx->ws.get<double>(1, &floor2));
     const int ngrid = (n * 32 + 255) / 256;
-    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_in, n, norms);
-    NDMPS_LAUNCH_CHECK(ctx);
-    null_floor_kernel<<<1, 256, 0, ctx->stream>>>(norms, n, floor2);
-    NDMPS_LAUNCH_CHECK(ctx);
-    // start from columns sorted by norm (a static permutation: the left singular vectors of
-    // G Pi are those of G); sorted starts converge in fewer sweeps
-    double* a_dev = a_in;
-    if (ctx->opt_jacobi_presort && n > 2) {
-        NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &a_dev));
-        sort_columns_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_in, norms, n, a_dev);
-        NDMPS_LAUNCH_CHECK(ctx);
-    }
     double tol = jacobi_tol(n);
     if (tol_override > tol) tol = tol_override;
     const double tol2 = tol * tol;
-    const int nr = n <= 256 ? 8 : n <= 512 ? 16 : 0;      // rows per lane of the block kernels
 
-    const size_t single_bytes = (size_t)n * n * sizeof(double);
-    if (n >= 2 && single_bytes <= smem_cap && n <= 32) {
+    double* cols = a_in;      // the column set Jacobi works on
+    int ncols = n;
+    int square = 0;           // eigenvalue = column norm (Jacobi on G) or its square (Jacobi on L)
+    const bool use_chol = ctx->opt_eig_cholesky && n > 32 && n <= 1024;
+    if (use_chol) {
+        double* Lcol = nullptr;
+        NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &Lcol));
+        int rank = 0;
+        NDMPS_TRY(pivoted_cholesky(ctx, a_in, n, Lcol, &rank));
+        cols = Lcol;
+        ncols = rank;
+        square = 1;
+    }
+    if (ncols >= 1) {
+        column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(cols, n, ncols, norms);
+        NDMPS_LAUNCH_CHECK(ctx);
+        null_floor_kernel<<<1, 256, 0, ctx->stream>>>(norms, n, ncols, floor2);
+        NDMPS_LAUNCH_CHECK(ctx);
+    }
+    if (!use_chol && n >= 2 && n <= 32 && (size_t)n * n * sizeof(double) <= smem_cap) {
+        unsigned* ctrl = nullptr;
+        NDMPS_TRY(ctx->ws.get<unsigned>(4, &ctrl));
+        NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 4 * sizeof(unsigned), ctx->stream));
         int matches = (n + 1) / 2;
         int warps = (matches + 3) / 4;                        // four pairs per warp
-        if (warps > 16) warps = 16;
-        NDMPS_TRY(run_single<4>(ctx, a_dev, n, warps, max_sweeps, ctrl, tol2, floor2, single_bytes));
+        NDMPS_TRY(run_single<4>(ctx, cols, n, warps, max_sweeps, ctrl, tol2, floor2, (size_t)n * n * sizeof(double)));
+        int* host_flag = reinterpret_cast<int*>(ctx->pinned);
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (host_flag[0] <= 0) {
@@ -529,53 +729,17 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
             return NDMPS_ERR_NOCONV;
         }
         sweeps_used = host_flag[0];
-    } else if (n >= 2) {
-        // block size: as many columns as shared memory allows, at most 16 warps, tunable
-        int b = (int)((smem_cap - 512) / (16 * (size_t)n));
-        if (b > 16) b = 16;
-        if (ctx->opt_jacobi_block > 0 && ctx->opt_jacobi_block < b) b = (int)ctx->opt_jacobi_block;
-        NDMPS_REQUIRE(b >= 1, "eigh: n = %d does not fit a column pair in shared memory", n);
-        int nb = (n + b - 1) / b;
-        if (nb & 1) nb++;
-        if (nb < 2) nb = 2;
-        const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
-        if (nb / 2 <= ctx->sm_count) {
-            switch (nr) {
-                case 8: NDMPS_TRY(run_persistent<8>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
-                case 16: NDMPS_TRY(run_persistent<16>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
-                default: NDMPS_TRY(run_persistent<0>(ctx, a_dev, n, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
-            }
-            NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            if (host_flag[0] <= 0) {
-                set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, b = %d)", max_sweeps, n, b);
-                return NDMPS_ERR_NOCONV;
-            }
-            sweeps_used = host_flag[0];
-        } else {
-            bool converged = false;
-            for (int s = 0; s < max_sweeps && !converged; s++) {
-                unsigned* flag = ctrl + 2 + s;
-                for (int round = 0; round < nb - 1; round++)
-                    NDMPS_TRY(run_round<0>(ctx, a_dev, n, b, nb, round, flag, tol2, floor2, smem));
-                sweeps_used = s + 1;
-                if (s >= 3) {
-                    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                    converged = host_flag[0] == 0;
-                }
-            }
-            if (!converged) {
-                set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, b = %d)", max_sweeps, n, b);
-                return NDMPS_ERR_NOCONV;
-            }
-        }
+    } else if (ncols >= 2) {
+        NDMPS_TRY(jacobi_columns(ctx, cols, n, ncols, tol2, floor2, &sweeps_used));
     }
     ctx->last_eig_sweeps = sweeps_used;
-    if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh n = %d: %d sweeps (presort %d)\n", n, sweeps_used, (int)ctx->opt_jacobi_presort);
-    column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, n, norms);
-    NDMPS_LAUNCH_CHECK(ctx);
-    sort_extract_kernel<<<ngrid, 256, 0, ctx->stream>>>(a_dev, norms, n, evals_dev, evecs_dev);
+    if (ctx->opt_verbose)
+        fprintf(stderr, "[ndmps] eigh n = %d: %d columns, %d sweeps%s\n", n, ncols, sweeps_used, use_chol ? " (pivoted Cholesky)" : "");
+    if (ncols >= 1) {
+        column_norms_kernel<<<ngrid, 256, 0, ctx->stream>>>(cols, n, ncols, norms);
+        NDMPS_LAUNCH_CHECK(ctx);
+    }
+    sort_extract_kernel<<<ngrid, 256, 0, ctx->stream>>>(cols, norms, n, ncols, square, evals_dev, evecs_dev);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }

@@ -32,18 +32,18 @@ def main(which):
     ctx = _native.context()
     g = torch.Generator(device="cuda").manual_seed(0)
     if "eigh" in which:
-        for presort in (0, 1):
-            ctx.set_option("jacobi_presort", presort)
+        for chol in (1, 0):
+            ctx.set_option("eig_cholesky", chol)
             for n in (8, 64, 128, 256, 512, 1024):
                 a = torch.randn(n, 4 * n, dtype=torch.float64, device="cuda", generator=g)
                 gm = a @ a.T
                 try:
                     ms = timeit(lambda: _ops.eigh(gm), reps=3, warm=1)
                     _, _, sw = _ops.eigh(gm)
-                    print(f"eigh n={n} presort={presort}: {ms:.3f} ms, {sw} sweeps", flush=True)
+                    print(f"eigh n={n} cholesky={chol}: {ms:.3f} ms, {sw} sweeps", flush=True)
                 except Exception as exc:
-                    print(f"eigh n={n} presort={presort}: FAILED {exc}", flush=True)
-        ctx.set_option("jacobi_presort", 0)
+                    print(f"eigh n={n} cholesky={chol}: FAILED {exc}", flush=True)
+        ctx.set_option("eig_cholesky", 1)
     if "gram" in which:
         for rows, cols in ((8, 1 << 21), (64, 1 << 18), (512, 1 << 15), (512, 1 << 12), (512, 512), (512, 1 << 18)):
             m = torch.randn(rows, cols, dtype=torch.float32, device="cuda", generator=g)
