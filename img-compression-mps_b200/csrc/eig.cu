@@ -657,8 +657,9 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     NDMPS_REQUIRE(smem <= ctx->smem_optin - 4096, "pivoted_cholesky: n = %d does not fit shared memory", n);
     static bool attr_set = false;
     if (!attr_set) {
+        // the kernel also has ~3 KB of static shared memory: static + dynamic must stay within the opt-in limit
         NDMPS_CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ctx->smem_optin));
+                                            (int)ctx->smem_optin - 4096));
         attr_set = true;
     }
     double* cand_rows = nullptr;
