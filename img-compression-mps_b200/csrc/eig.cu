@@ -473,15 +473,15 @@ __global__ void __launch_bounds__(256)
 pivoted_cholesky_kernel(const double* __restrict__ G, int n, int rows_per, double* __restrict__ Lcol,
                         double* cand_rows, CholCand* cand, unsigned* ctrl, double stop_rel) {
     extern __shared__ double sm[];
-    double* slab = sm;                                   // rows_per x n
-    double* piv = slab + (size_t)rows_per * n;           // n
-    double* lrow = piv + n;                              // rows_per
+    double* slab = sm;                                   // rows_per x n : this CTA's rows of the Schur complement
+    double* piv = slab + (size_t)rows_per * n;           // n : winner row, already divided by sqrt(pivot)
+    double* lrow = piv + n;                              // rows_per : this step's column of L for our rows
     int* chosen = reinterpret_cast<int*>(lrow + rows_per);   // rows_per
-    __shared__ double s_val[160];
-    __shared__ int s_row[160];
-    __shared__ int s_cta[160];
-    __shared__ int s_best;
-    const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
+    __shared__ int s_bi;          // local candidate row (slab index) or -1
+    __shared__ int s_w;           // winning CTA or -1
+    __shared__ int s_prow;        // winning row (global index)
+    __shared__ double s_pval;     // winning pivot
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, ncta = gridDim.x;
     const int row0 = cta * rows_per;
     int nrows = n - row0;
     nrows = nrows < 0 ? 0 : (nrows > rows_per ? rows_per : nrows);
@@ -491,66 +491,79 @@ pivoted_cholesky_kernel(const double* __restrict__ G, int n, int rows_per, doubl
     double p0 = 0.0;
     int rank = n;
     for (int k = 0; k < n; k++) {
-        // ---- publish the local candidate (value, row index, the row itself) ----
-        if (tid == 0) {
+        // ---- [A] local candidate: largest remaining diagonal entry of our rows (warp 0) ----
+        if (warp == 0) {
             double best = -1.0;
             int bi = -1;
-            for (int r = 0; r < nrows; r++) {
+            for (int r = lane; r < nrows; r += 32) {
                 double d = slab[(size_t)r * n + row0 + r];
                 if (!chosen[r] && d > best) { best = d; bi = r; }
             }
-            s_best = bi;
-            CholCand c;
-            c.val = best;
-            c.row = bi >= 0 ? row0 + bi : -1;
-            c.pad = 0;
-            cand[(size_t)(k & 1) * ncta + cta] = c;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                s_bi = bi;
+                CholCand c;
+                c.val = best;
+                c.row = bi >= 0 ? row0 + bi : -1;
+                c.pad = 0;
+                cand[(size_t)(k & 1) * ncta + cta] = c;
+            }
         }
         __syncthreads();
-        const int bi = s_best;
+        // ---- [B] publish the candidate row itself, then meet ----
+        const int bi = s_bi;
         if (bi >= 0) {
             double* dst = cand_rows + ((size_t)(k & 1) * ncta + cta) * n;
             for (int c = tid; c < n; c += blockDim.x) __stcg(dst + c, slab[(size_t)bi * n + c]);
         }
         grid_barrier(ctrl, (unsigned)(k + 1) * ncta);
-        // ---- every CTA picks the same winner ----
-        if (tid < ncta) {
-            const CholCand* cp = cand + (size_t)(k & 1) * ncta + tid;
-            s_val[tid] = __ldcg(&cp->val);
-            s_row[tid] = __ldcg(&cp->row);
-            s_cta[tid] = tid;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int w = -1;
-            for (int t = 0; t < ncta; t++) {
-                if (s_row[t] < 0) continue;
-                if (w < 0 || s_val[t] > s_val[w] || (s_val[t] == s_val[w] && s_row[t] < s_row[w])) w = t;
+        // ---- [C] every CTA picks the same winner (warp 0) ----
+        if (warp == 0) {
+            double best = -1.0;
+            int brow = -1, bw = -1;
+            for (int t = lane; t < ncta; t += 32) {
+                const CholCand* cp = cand + (size_t)(k & 1) * ncta + t;
+                double v = __ldcg(&cp->val);
+                int r = __ldcg(&cp->row);
+                if (r >= 0 && (v > best || (v == best && (brow < 0 || r < brow)))) { best = v; brow = r; bw = t; }
             }
-            s_best = w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+                int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                if (orow >= 0 && (ob > best || (ob == best && (brow < 0 || orow < brow)))) { best = ob; brow = orow; bw = ow; }
+            }
+            if (lane == 0) { s_w = bw; s_prow = brow; s_pval = best; }
         }
         __syncthreads();
-        const int w = s_best;
-        const double pval = w >= 0 ? s_val[w] : -1.0;
-        const int prow = w >= 0 ? s_row[w] : -1;
+        const int w = s_w, prow = s_prow;
+        const double pval = s_pval;
         if (k == 0) p0 = pval;
         if (w < 0 || !(pval > stop_rel * p0) || !(pval > 0.0)) { rank = k; break; }   // uniform across the grid
-        const double* src = cand_rows + ((size_t)(k & 1) * ncta + w) * n;
-        for (int c = tid; c < n; c += blockDim.x) piv[c] = __ldcg(src + c);
+        // ---- [D] winner row (scaled), our entries of column k of L ----
         const double root = sqrt(pval), inv = 1.0 / root;
-        __syncthreads();
+        const double* src = cand_rows + ((size_t)(k & 1) * ncta + w) * n;
+        for (int c = tid; c < n; c += blockDim.x) piv[c] = __ldcg(src + c) * inv;
         if (tid < nrows) {
             double l;
             if (row0 + tid == prow) { l = root; chosen[tid] = 1; }
             else if (!chosen[tid]) l = slab[(size_t)tid * n + prow] * inv;
             else l = 0.0;
-            lrow[tid] = l;
+            lrow[tid] = chosen[tid] ? 0.0 : l;            // rows already eliminated take no update
             __stcg(Lcol + (size_t)k * n + row0 + tid, l);
         }
         __syncthreads();
+        // ---- [E] Schur complement update of our remaining rows ----
         for (int idx = tid; idx < nrows * n; idx += blockDim.x) {
             const int r = idx / n, c = idx - r * n;
-            if (!chosen[r]) slab[idx] = fma(-lrow[r], piv[c] * inv, slab[idx]);
+            const double l = lrow[r];
+            if (l != 0.0) slab[idx] = fma(-l, piv[c], slab[idx]);
         }
         __syncthreads();
     }
@@ -650,9 +663,10 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
 
 // G = L L^T with diagonal pivoting; returns the numerical rank (host) and L column-major.
 static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol, int* rank_out) {
-    int rows_per = (n + 63) / 64;
+    int rows_per = (n + 31) / 32;                            // <= 32 CTAs: the per-step grid barrier dominates
+    if (ctx->opt_chol_rows > 0) rows_per = (int)ctx->opt_chol_rows;
     int ncta = (n + rows_per - 1) / rows_per;
-    while (ncta > ctx->sm_count || ncta > 160) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }
+    while (ncta > ctx->sm_count) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }
     const size_t smem = ((size_t)rows_per * n + n + rows_per) * sizeof(double) + (size_t)rows_per * sizeof(int) + 16;
     NDMPS_REQUIRE(smem <= ctx->smem_optin - 4096, "pivoted_cholesky: n = %d does not fit shared memory", n);
     static bool attr_set = false;
