@@ -105,7 +105,7 @@ struct ndmps_ctx {
     double* pinned = nullptr;
     size_t pinned_doubles = 0;
     // options
-    int64_t opt_gram_path = 0;      // 0: SIMT f64-accumulate, 1: tcgen05 split-TF32 (when available)
+    int64_t opt_gram_path = 0;      // 0: auto (FP64 tensor pipe when the shape allows), 2: force the SIMT kernel
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;

@@ -663,7 +663,7 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
 
 // G = L L^T with diagonal pivoting; returns the numerical rank (host) and L column-major.
 static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol, int* rank_out) {
-    int rows_per = (n + 31) / 32;                            // <= 32 CTAs: the per-step grid barrier dominates
+    int rows_per = (n + 127) / 128;                          // many small slabs: the per-step update is the critical path
     if (ctx->opt_chol_rows > 0) rows_per = (int)ctx->opt_chol_rows;
     int ncta = (n + rows_per - 1) / rows_per;
     while (ncta > ctx->sm_count) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }

@@ -184,7 +184,14 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     return NDMPS_OK;
 }
 
+int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
+
 int gram(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev) {
+    if (side == 0 && ctx->opt_gram_path != 2) {   // FP64 tensor-pipe path when the shape allows (gram_dmma.cu)
+        bool done = false;
+        NDMPS_TRY(gram_dmma(ctx, mat, rows, cols, ld, dtype, g_dev, &done));
+        if (done) return NDMPS_OK;
+    }
     if (side == 0)  // G = M M^T : A = M (rows x cols), B = M^T
         return gemm(ctx, rows, rows, cols, 1.0, mat, dtype, ld, 1, mat, dtype, 1, ld, g_dev, NDMPS_F64, rows);
     // G = M^T M : A = M^T (cols x rows), B = M

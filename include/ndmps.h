@@ -69,7 +69,7 @@ int ndmps_ctx_profile(ndmps_ctx_t* ctx, int enable);
 int ndmps_stage_count(void);
 const char* ndmps_stage_name(int stage);
 int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, int reset);
-/* tuning knobs, e.g. "gram_path" 0=SIMT f64 1=tcgen05 split-TF32, "jacobi_block" */
+/* tuning knobs, e.g. "gram_path" 0=auto 2=force SIMT, "jacobi_block" */
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value);
 
 /* ---- K1: N-D volume <-> interleaved MPS site order ----------------------
