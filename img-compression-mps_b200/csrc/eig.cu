@@ -177,14 +177,14 @@ __device__ __forceinline__ bool cross_rounds_stationary(double* S, double* norm2
         const bool valid = have_x && j < cntq;
         double* y = S + (size_t)(b + j) * n;
         double yr[NR];
-        double gamma = 0.0;
+        double g4[4] = {0.0, 0.0, 0.0, 0.0};                 // four chains: the dot is latency-, not throughput-bound
 #pragma unroll
         for (int t = 0; t < NR; t++) {
             const int i = lane + 32 * t;
             yr[t] = (valid && i < n) ? y[i] : 0.0;
-            gamma = fma(xr[t], yr[t], gamma);
+            g4[t & 3] = fma(xr[t], yr[t], g4[t & 3]);
         }
-        gamma = warp_sum(gamma);
+        double gamma = warp_sum((g4[0] + g4[1]) + (g4[2] + g4[3]));
         const double beta = valid ? norm2[b + j] : 0.0;
         if (valid && alpha > floor2 && beta > floor2 && gamma * gamma > tol2 * alpha * beta) {
             double c, s, t;
