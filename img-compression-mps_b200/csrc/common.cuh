@@ -20,15 +20,39 @@ struct DigitList {
     int32_t shift[NDMPS_MAX_DIGITS];    // log2(extent) if power of two else -1
 };
 
+// Tiled form of one permutation direction (permute.cu): a tile is the set of digits A (the
+// innermost destination digits: a contiguous destination run of `pa` elements) united with B
+// (the smallest-stride source digits: a contiguous source run of `pb` elements).
+struct TilePlan {
+    bool ok = false;
+    int tile = 0;                        // elements per tile
+    int pa = 0, pb = 0;                  // contiguous run lengths on the destination / source side
+    int n_outer = 0;                     // digits outside the tile
+    uint32_t outer_extent[NDMPS_MAX_DIGITS];
+    int64_t outer_dst[NDMPS_MAX_DIGITS];
+    int64_t outer_src[NDMPS_MAX_DIGITS];
+    int64_t n_tiles = 0;
+    int conflict = 0;                    // worst shared-memory bank conflict degree of the scatter
+    std::vector<int64_t> hi_src;         // tile/pb source offsets of the source runs (read order)
+    std::vector<int64_t> hi_dst;         // tile/pa destination offsets of the destination runs (write order)
+    std::vector<uint16_t> pos;           // read index -> (skewed) shared-memory slot
+    // device copies, uploaded on first use
+    int64_t* d_hi_src = nullptr;
+    int64_t* d_hi_dst = nullptr;
+    uint16_t* d_pos = nullptr;
+    int device = -1;
+};
+
 struct ndmps_plan {
-    int ndim, levels;
-    int64_t shape[8];
-    int64_t factors[NDMPS_MAX_DIGITS];  // (levels, ndim)
-    int64_t site_dims[NDMPS_MAX_DIGITS];
-    int64_t total;
-    DigitList enc;                      // destination = site order, source = volume
-    DigitList dec;                      // destination = volume, source = site order
-    bool identity;
+    int ndim = 0, levels = 0;
+    int64_t shape[8] = {0};
+    int64_t factors[NDMPS_MAX_DIGITS] = {0};  // (levels, ndim)
+    int64_t site_dims[NDMPS_MAX_DIGITS] = {0};
+    int64_t total = 0;
+    DigitList enc = {};                 // destination = site order, source = volume
+    DigitList dec = {};                 // destination = volume, source = site order
+    bool identity = false;
+    TilePlan enc_tile, dec_tile;
 };
 
 namespace ndmps {
@@ -107,6 +131,7 @@ struct ndmps_ctx {
     // options
     int64_t opt_gram_path = 0;      // 0: auto (FP64 tensor pipe when the shape allows), 2: force the SIMT kernel
     int64_t opt_jacobi_block = 0;   // 0: auto
+    int64_t opt_permute_path = 0;   // 0: tiled through shared memory when the shape tiles, 2: force the gather kernel
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
     int64_t opt_chol_rows = 0;            // rows per CTA of the pivoted Cholesky (0: auto)

@@ -9,6 +9,7 @@
 // Here the plan stores, for each direction, the destination's digit extents (in
 // C order) and the source stride of every digit; kernels walk destination
 // offsets (coalesced writes) and gather the source.
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -83,6 +84,223 @@ __global__ void __launch_bounds__(256) copy_scale_kernel(const T* __restrict__ s
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled permutation.  Each CTA moves tiles through shared memory: it reads contiguous SOURCE runs
+// (pb elements, coalesced), scatters them into the tile's destination order in shared memory
+// (slot table from the plan, skewed against bank conflicts), then writes contiguous
+// DESTINATION runs (pa elements, coalesced).  Index arithmetic per element is one table
+// lookup; per tile a handful of divisions for the outer digits.
+// ---------------------------------------------------------------------------------------------
+constexpr int PERM_THREADS = 256;
+
+__host__ __device__ __forceinline__ int skew_slot(int w) { return w + (w >> 5); }
+
+struct TileArgs {
+    int tile, pa, pb, n_outer;
+    int64_t n_tiles;
+    uint32_t outer_extent[NDMPS_MAX_DIGITS];
+    int64_t outer_dst[NDMPS_MAX_DIGITS];
+    int64_t outer_src[NDMPS_MAX_DIGITS];
+    const int64_t* hi_src;
+    const int64_t* hi_dst;
+    const uint16_t* pos;
+};
+
+template <class T, int VEC>
+__global__ void __launch_bounds__(PERM_THREADS)
+permute_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, const TileArgs ta, double scale, bool do_scale) {
+    extern __shared__ unsigned char perm_smem[];
+    T* buf = reinterpret_cast<T*>(perm_smem);
+    const int tid = threadIdx.x;
+    for (int64_t tile = blockIdx.x; tile < ta.n_tiles; tile += gridDim.x) {
+        int64_t rem = tile, base_dst = 0, base_src = 0;
+        for (int j = ta.n_outer - 1; j >= 0; j--) {
+            int64_t q = rem / ta.outer_extent[j];
+            int64_t d = rem - q * ta.outer_extent[j];
+            base_dst += d * ta.outer_dst[j];
+            base_src += d * ta.outer_src[j];
+            rem = q;
+        }
+        // ---- source runs -> shared memory (destination order) ----
+        if (VEC == 4) {
+            const int nvec = ta.tile >> 2, pbv = ta.pb >> 2;
+            for (int v = tid; v < nvec; v += PERM_THREADS) {
+                const int hi = v / pbv, lo = (v - hi * pbv) << 2;
+                const float4 val = *reinterpret_cast<const float4*>(src + base_src + ta.hi_src[hi] + lo);
+                const int r = hi * ta.pb + lo;
+                const ushort4 p4 = *reinterpret_cast<const ushort4*>(ta.pos + r);
+                buf[p4.x] = (T)val.x; buf[p4.y] = (T)val.y; buf[p4.z] = (T)val.z; buf[p4.w] = (T)val.w;
+            }
+        } else {
+            for (int r = tid; r < ta.tile; r += PERM_THREADS) {
+                const int hi = r / ta.pb, lo = r - hi * ta.pb;
+                buf[ta.pos[r]] = src[base_src + ta.hi_src[hi] + lo];
+            }
+        }
+        __syncthreads();
+        // ---- shared memory -> destination runs ----
+        if (VEC == 4) {
+            const int nvec = ta.tile >> 2, pav = ta.pa >> 2;
+            for (int v = tid; v < nvec; v += PERM_THREADS) {
+                const int hi = v / pav, lo = (v - hi * pav) << 2;
+                const int w = hi * ta.pa + lo;
+                const int s = skew_slot(w);                 // 4 consecutive slots: w % 4 == 0 keeps them inside one 32-group
+                float4 val = make_float4((float)buf[s], (float)buf[s + 1], (float)buf[s + 2], (float)buf[s + 3]);
+                if (do_scale) { val.x *= (float)scale; val.y *= (float)scale; val.z *= (float)scale; val.w *= (float)scale; }
+                *reinterpret_cast<float4*>(dst + base_dst + ta.hi_dst[hi] + lo) = val;
+            }
+        } else {
+            for (int w = tid; w < ta.tile; w += PERM_THREADS) {
+                const int hi = w / ta.pa, lo = w - hi * ta.pa;
+                T val = buf[skew_slot(w)];
+                if (do_scale) val = (T)((double)val * scale);
+                dst[base_dst + ta.hi_dst[hi] + lo] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Build the tiled form of a digit list (host).  Returns ok = false when the shape does not tile
+// (no unit-stride source digit, or the united digit set is too large): the gather kernel is used.
+static void build_tile_plan(const DigitList& dl, TilePlan& tp) {
+    const int J = dl.n;
+    const int MAX_TILE = 8192, TARGET = 32;
+    tp.ok = false;
+    if (J < 2) return;
+    std::vector<int64_t> dst_stride(J);
+    int64_t s = 1;
+    for (int j = J - 1; j >= 0; j--) { dst_stride[j] = s; s *= dl.extent[j]; }
+    std::vector<char> in_a(J, 0), in_b(J, 0);
+    // A: innermost destination digits
+    int64_t pa = 1;
+    for (int j = J - 1; j >= 0 && pa < TARGET; j--) { in_a[j] = 1; pa *= dl.extent[j]; }
+    // B: chain of smallest source strides starting at stride 1
+    int64_t pb = 1;
+    int64_t want = 1;
+    while (pb < TARGET) {
+        int found = -1;
+        for (int j = 0; j < J; j++)
+            if (!in_b[j] && dl.stride[j] == want) { found = j; break; }
+        if (found < 0) break;
+        in_b[found] = 1;
+        pb *= dl.extent[found];
+        want *= dl.extent[found];
+    }
+    if (pb < 2) return;
+    auto tile_size = [&]() { int64_t t = 1; for (int j = 0; j < J; j++) if (in_a[j] || in_b[j]) t *= dl.extent[j]; return t; };
+    if (tile_size() > MAX_TILE) return;
+    // grow A outwards while the tile stays small: longer destination runs, fewer tiles
+    for (int j = J - 1; j >= 0; j--) {
+        if (in_a[j]) continue;
+        int64_t grown = tile_size() * (in_b[j] ? 1 : dl.extent[j]);
+        if (grown > 4096) break;
+        in_a[j] = 1;
+        pa *= dl.extent[j];
+    }
+    const int64_t tile = tile_size();
+    if (tile > MAX_TILE || tile < 2) return;
+    // digit orders inside the tile
+    std::vector<int> wdig, rdig;           // write order (outer -> inner), read order (outer -> inner)
+    for (int j = 0; j < J; j++) if ((in_a[j] || in_b[j]) && !in_a[j]) wdig.push_back(j);   // B \ A: outer part of the write order
+    for (int j = 0; j < J; j++) if (in_a[j]) wdig.push_back(j);                              // A: inner, destination-contiguous
+    std::vector<int> bchain, arest;
+    for (int j = 0; j < J; j++) if (in_b[j]) bchain.push_back(j);
+    std::sort(bchain.begin(), bchain.end(), [&](int x, int y) { return dl.stride[x] > dl.stride[y]; });   // outer -> inner
+    for (int j = 0; j < J; j++) if (in_a[j] && !in_b[j]) arest.push_back(j);
+    std::sort(arest.begin(), arest.end(), [&](int x, int y) { return dl.stride[x] > dl.stride[y]; });
+    rdig = arest;
+    rdig.insert(rdig.end(), bchain.begin(), bchain.end());
+    tp.tile = (int)tile;
+    tp.pa = (int)pa;
+    tp.pb = (int)pb;
+    tp.hi_src.assign((size_t)(tile / pb), 0);
+    tp.hi_dst.assign((size_t)(tile / pa), 0);
+    tp.pos.assign((size_t)tile, 0);
+    std::vector<int> digit(J, 0);
+    for (int64_t r = 0; r < tile; r++) {
+        // decode read index r into digits (rdig, innermost last)
+        int64_t rem = r, soff = 0;
+        for (int k = (int)rdig.size() - 1; k >= 0; k--) {
+            int j = rdig[k];
+            digit[j] = (int)(rem % dl.extent[j]);
+            rem /= dl.extent[j];
+            soff += (int64_t)digit[j] * dl.stride[j];
+        }
+        if (r % pb == 0) tp.hi_src[(size_t)(r / pb)] = soff;
+        // write index of the same element
+        int64_t w = 0, doff = 0;
+        for (size_t k = 0; k < wdig.size(); k++) {
+            int j = wdig[k];
+            w = w * dl.extent[j] + digit[j];
+            doff += (int64_t)digit[j] * dst_stride[j];
+        }
+        if (w % pa == 0) tp.hi_dst[(size_t)(w / pa)] = doff;
+        tp.pos[(size_t)r] = (uint16_t)skew_slot((int)w);
+    }
+    // outer digits in destination order
+    tp.n_outer = 0;
+    tp.n_tiles = 1;
+    for (int j = 0; j < J; j++) {
+        if (in_a[j] || in_b[j]) continue;
+        tp.outer_extent[tp.n_outer] = dl.extent[j];
+        tp.outer_dst[tp.n_outer] = dst_stride[j];
+        tp.outer_src[tp.n_outer] = dl.stride[j];
+        tp.n_outer++;
+        tp.n_tiles *= dl.extent[j];
+    }
+    // worst bank-conflict degree of the scatter (32 consecutive read indices, 4-byte words)
+    int worst = 1;
+    for (int64_t r0 = 0; r0 + 32 <= tile; r0 += 32) {
+        int cnt[32] = {0};
+        for (int k = 0; k < 32; k++) cnt[tp.pos[(size_t)(r0 + k)] & 31]++;
+        for (int k = 0; k < 32; k++) worst = cnt[k] > worst ? cnt[k] : worst;
+    }
+    tp.conflict = worst;
+    tp.ok = true;
+}
+
+static int upload_tile_plan(TilePlan& tp, int device) {
+    if (tp.device == device && tp.d_pos) return NDMPS_OK;
+    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_src, tp.hi_src.size() * sizeof(int64_t)));
+    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_dst, tp.hi_dst.size() * sizeof(int64_t)));
+    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_pos, tp.pos.size() * sizeof(uint16_t)));
+    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_hi_src, tp.hi_src.data(), tp.hi_src.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_hi_dst, tp.hi_dst.data(), tp.hi_dst.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_pos, tp.pos.data(), tp.pos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    tp.device = device;
+    return NDMPS_OK;
+}
+
+template <class T>
+static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, double scale, bool do_scale) {
+    NDMPS_TRY(upload_tile_plan(tp, ctx->device));
+    TileArgs ta;
+    ta.tile = tp.tile; ta.pa = tp.pa; ta.pb = tp.pb; ta.n_outer = tp.n_outer; ta.n_tiles = tp.n_tiles;
+    for (int j = 0; j < tp.n_outer; j++) {
+        ta.outer_extent[j] = tp.outer_extent[j];
+        ta.outer_dst[j] = tp.outer_dst[j];
+        ta.outer_src[j] = tp.outer_src[j];
+    }
+    ta.hi_src = tp.d_hi_src; ta.hi_dst = tp.d_hi_dst; ta.pos = tp.d_pos;
+    const size_t smem = (size_t)(skew_slot(tp.tile) + 8) * sizeof(T);
+    int64_t grid = tp.n_tiles;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    // 16-byte accesses when every run and every run offset is a multiple of 4 elements (float32 only)
+    bool vec4 = sizeof(T) == 4 && (tp.pa % 4 == 0) && (tp.pb % 4 == 0) &&
+                (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+    if (vec4) {
+        for (size_t k = 0; k < tp.hi_src.size() && vec4; k++) vec4 = tp.hi_src[k] % 4 == 0;
+        for (size_t k = 0; k < tp.hi_dst.size() && vec4; k++) vec4 = tp.hi_dst[k] % 4 == 0;
+        for (int j = 0; j < tp.n_outer && vec4; j++) vec4 = tp.outer_dst[j] % 4 == 0 && tp.outer_src[j] % 4 == 0;
+    }
+    if (vec4) permute_tiled_kernel<T, 4><<<(unsigned)grid, PERM_THREADS, smem, ctx->stream>>>(src, dst, ta, scale, do_scale);
+    else permute_tiled_kernel<T, 1><<<(unsigned)grid, PERM_THREADS, smem, ctx->stream>>>(src, dst, ta, scale, do_scale);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
 template <class T>
 static int permute_typed(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const T* src, T* dst, double scale) {
     int64_t total = plan->total;
@@ -98,6 +316,8 @@ static int permute_typed(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, c
         return NDMPS_OK;
     }
     NDMPS_REQUIRE(src != dst, "ndmps permute: in-place permutation is not supported");
+    TilePlan& tp = const_cast<TilePlan&>(inverse ? plan->dec_tile : plan->enc_tile);
+    if (tp.ok && ctx->opt_permute_path != 2) return permute_tiled<T>(ctx, tp, src, dst, scale, do_scale);
     const DigitList& dl = inverse ? plan->dec : plan->enc;
     if (total < (int64_t(1) << 32))
         permute_gather_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(src, dst, dl, total, scale, do_scale);
@@ -125,7 +345,6 @@ int ndmps_plan_create(int ndim, const int64_t* shape, int levels, const int64_t*
     NDMPS_REQUIRE(levels >= 1 && levels * ndim <= NDMPS_MAX_DIGITS,
                   "ndmps_plan_create: levels*ndim = %d exceeds %d", levels * ndim, NDMPS_MAX_DIGITS);
     ndmps_plan* p = new ndmps_plan();
-    memset(p, 0, sizeof(*p));
     p->ndim = ndim;
     p->levels = levels;
     p->total = 1;
@@ -173,11 +392,22 @@ int ndmps_plan_create(int ndim, const int64_t* shape, int levels, const int64_t*
     finish(p->enc);
     finish(p->dec);
     p->identity = (p->enc.n == 1 && p->enc.stride[0] <= 1);
+    if (!p->identity) {
+        build_tile_plan(p->enc, p->enc_tile);
+        build_tile_plan(p->dec, p->dec_tile);
+    }
     *out = p;
     return NDMPS_OK;
 }
 
 int ndmps_plan_destroy(ndmps_plan_t* plan) {
+    if (plan) {
+        for (TilePlan* tp : {&plan->enc_tile, &plan->dec_tile}) {
+            if (tp->d_hi_src) cudaFree(tp->d_hi_src);
+            if (tp->d_hi_dst) cudaFree(tp->d_hi_dst);
+            if (tp->d_pos) cudaFree(tp->d_pos);
+        }
+    }
     delete plan;
     return NDMPS_OK;
 }
@@ -194,6 +424,57 @@ int ndmps_plan_debug_offsets(const ndmps_plan_t* plan, int inverse, int64_t firs
     const DigitList& dl = inverse ? plan->dec : plan->enc;
     for (int64_t i = 0; i < count; i++)
         out_host[i] = plan->identity ? first + i : digit_offset<uint64_t>(dl, (uint64_t)(first + i));
+    return NDMPS_OK;
+}
+
+int ndmps_plan_debug_tile_info(const ndmps_plan_t* plan, int inverse, int64_t* info_out) {
+    NDMPS_REQUIRE(plan && info_out, "ndmps_plan_debug_tile_info: NULL argument");
+    const TilePlan& tp = inverse ? plan->dec_tile : plan->enc_tile;
+    info_out[0] = tp.ok ? 1 : 0;
+    info_out[1] = tp.tile;
+    info_out[2] = tp.pa;
+    info_out[3] = tp.pb;
+    info_out[4] = tp.n_tiles;
+    info_out[5] = tp.conflict;
+    return NDMPS_OK;
+}
+
+int ndmps_plan_debug_apply_tiled(const ndmps_plan_t* plan, int inverse, const int32_t* src_host, int32_t* dst_host) {
+    NDMPS_REQUIRE(plan && src_host && dst_host, "ndmps_plan_debug_apply_tiled: NULL argument");
+    const TilePlan& tp = inverse ? plan->dec_tile : plan->enc_tile;
+    NDMPS_REQUIRE(tp.ok, "ndmps_plan_debug_apply_tiled: this shape does not tile");
+    std::vector<int32_t> buf((size_t)skew_slot(tp.tile) + 8);
+    const bool vec4 = tp.pa % 4 == 0 && tp.pb % 4 == 0;
+    for (int64_t tile = 0; tile < tp.n_tiles; tile++) {
+        int64_t rem = tile, base_dst = 0, base_src = 0;
+        for (int j = tp.n_outer - 1; j >= 0; j--) {
+            int64_t q = rem / tp.outer_extent[j], d = rem - q * tp.outer_extent[j];
+            base_dst += d * tp.outer_dst[j];
+            base_src += d * tp.outer_src[j];
+            rem = q;
+        }
+        if (vec4) {   // same grouping as the 16-byte kernel path
+            const int nvec = tp.tile >> 2, pbv = tp.pb >> 2, pav = tp.pa >> 2;
+            for (int v = 0; v < nvec; v++) {
+                const int hi = v / pbv, lo = (v - hi * pbv) << 2;
+                for (int e = 0; e < 4; e++) buf[tp.pos[(size_t)(hi * tp.pb + lo + e)]] = src_host[base_src + tp.hi_src[(size_t)hi] + lo + e];
+            }
+            for (int v = 0; v < nvec; v++) {
+                const int hi = v / pav, lo = (v - hi * pav) << 2;
+                const int s = skew_slot(hi * tp.pa + lo);
+                for (int e = 0; e < 4; e++) dst_host[base_dst + tp.hi_dst[(size_t)hi] + lo + e] = buf[(size_t)s + e];
+            }
+        } else {
+            for (int r = 0; r < tp.tile; r++) {
+                const int hi = r / tp.pb, lo = r - hi * tp.pb;
+                buf[tp.pos[(size_t)r]] = src_host[base_src + tp.hi_src[(size_t)hi] + lo];
+            }
+            for (int w = 0; w < tp.tile; w++) {
+                const int hi = w / tp.pa, lo = w - hi * tp.pa;
+                dst_host[base_dst + tp.hi_dst[(size_t)hi] + lo] = buf[(size_t)skew_slot(w)];
+            }
+        }
+    }
     return NDMPS_OK;
 }
 

@@ -85,6 +85,11 @@ int ndmps_plan_site_dims(const ndmps_plan_t* plan, int64_t* dims_out);
 /* host-only index check (no device work): source offsets the kernels read for
  * destination elements [first, first+count); inverse=0 encode, 1 decode. */
 int ndmps_plan_debug_offsets(const ndmps_plan_t* plan, int inverse, int64_t first, int64_t count, int64_t* out_host);
+/* host-only checks of the shared-memory tiling of the permutation (no device work):
+ * info_out[6] = {tiled?, tile elements, destination run, source run, tiles, worst bank conflict};
+ * apply_tiled walks the tile tables on int32 host arrays exactly as the kernel does. */
+int ndmps_plan_debug_tile_info(const ndmps_plan_t* plan, int inverse, int64_t* info_out);
+int ndmps_plan_debug_apply_tiled(const ndmps_plan_t* plan, int inverse, const int32_t* src_host, int32_t* dst_host);
 /* dst[site order] = scale * src[volume order]   (scale folds the 1/||x|| of core/ndmps.py:60-61) */
 int ndmps_encode(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void* src, void* dst, int dtype, double scale);
 /* dst[volume order] = src[site order] */

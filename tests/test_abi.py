@@ -69,3 +69,20 @@ def test_compute_without_gpu_fails_loudly():
     from imgcompressionmps.core.ndmps import NDMPS
     with pytest.raises(RuntimeError):
         NDMPS.from_tensor(np.zeros((8, 8), dtype=np.float32))
+
+
+@pytest.mark.parametrize("shape", [(8, 9), (12, 18, 10), (16, 16, 8, 20), (30, 40, 50), (256, 128), (512, 680), (64, 64, 64),
+                                   (32, 16, 8, 20), (6, 10, 15)])
+def test_tiled_permutation_tables_match_oracle(shape):
+    """The shared-memory tiling (source runs -> skewed slots -> destination runs) reproduces the
+    oracle's permutation when its tables are walked on the host exactly as the kernel walks them."""
+    from oracle import encoding as OE
+    factors, _ = get_factorlist(shape)
+    plan = N.Plan(shape, factors)
+    ramp = np.arange(int(np.prod(shape)), dtype=np.int32).reshape(shape)
+    want = OE.encode(ramp).reshape(-1)
+    enc, dec = plan.tile_info(False), plan.tile_info(True)
+    assert enc["tiled"] and dec["tiled"]
+    assert enc["tile"] <= 8192 and enc["tile"] * enc["tiles"] == ramp.size
+    assert np.array_equal(plan.apply_tiled_host(False, ramp), want)
+    assert np.array_equal(plan.apply_tiled_host(True, want), ramp.reshape(-1))
