@@ -172,31 +172,26 @@ static void build_tile_plan(const DigitList& dl, TilePlan& tp) {
     int64_t s = 1;
     for (int j = J - 1; j >= 0; j--) { dst_stride[j] = s; s *= dl.extent[j]; }
     std::vector<char> in_a(J, 0), in_b(J, 0);
-    // A: innermost destination digits
-    int64_t pa = 1;
-    for (int j = J - 1; j >= 0 && pa < TARGET; j--) { in_a[j] = 1; pa *= dl.extent[j]; }
-    // B: chain of smallest source strides starting at stride 1
-    int64_t pb = 1;
-    int64_t want = 1;
-    while (pb < TARGET) {
-        int found = -1;
-        for (int j = 0; j < J; j++)
-            if (!in_b[j] && dl.stride[j] == want) { found = j; break; }
-        if (found < 0) break;
-        in_b[found] = 1;
-        pb *= dl.extent[found];
-        want *= dl.extent[found];
-    }
-    if (pb < 2) return;
     auto tile_size = [&]() { int64_t t = 1; for (int j = 0; j < J; j++) if (in_a[j] || in_b[j]) t *= dl.extent[j]; return t; };
+    // next digit that would extend the source chain (stride == current run length), or -1
+    int64_t pa = 1, pb = 1;
+    auto next_b = [&]() { for (int j = 0; j < J; j++) if (!in_b[j] && dl.stride[j] == pb) return j; return -1; };
+    auto next_a = [&]() { for (int j = J - 1; j >= 0; j--) if (!in_a[j]) return j; return -1; };
+    // A: innermost destination digits, B: chain of smallest source strides, both to >= TARGET
+    while (pa < TARGET) { int j = next_a(); if (j < 0) break; in_a[j] = 1; pa *= dl.extent[j]; }
+    while (pb < TARGET) { int j = next_b(); if (j < 0) break; in_b[j] = 1; pb *= dl.extent[j]; }
+    if (pb < 2) return;
     if (tile_size() > MAX_TILE) return;
-    // grow A outwards while the tile stays small: longer destination runs, fewer tiles
-    for (int j = J - 1; j >= 0; j--) {
-        if (in_a[j]) continue;
-        int64_t grown = tile_size() * (in_b[j] ? 1 : dl.extent[j]);
-        if (grown > 4096) break;
-        in_a[j] = 1;
-        pa *= dl.extent[j];
+    // grow the shorter run first while the tile fits: long runs on BOTH sides keep DRAM pages open
+    for (;;) {
+        int ja = next_a(), jb = next_b();
+        int64_t ta = ja >= 0 ? tile_size() * (in_b[ja] ? 1 : dl.extent[ja]) : MAX_TILE + 1;
+        int64_t tb = jb >= 0 ? tile_size() * (in_a[jb] ? 1 : dl.extent[jb]) : MAX_TILE + 1;
+        bool can_a = ta <= MAX_TILE, can_b = tb <= MAX_TILE;
+        if (!can_a && !can_b) break;
+        bool pick_b = can_b && (!can_a || pb <= pa);
+        if (pick_b) { in_b[jb] = 1; pb *= dl.extent[jb]; }
+        else { in_a[ja] = 1; pa *= dl.extent[ja]; }
     }
     const int64_t tile = tile_size();
     if (tile > MAX_TILE || tile < 2) return;
