@@ -36,6 +36,13 @@ struct TilePlan {
     std::vector<int64_t> hi_src;         // tile/pb source offsets of the source runs (read order)
     std::vector<int64_t> hi_dst;         // tile/pa destination offsets of the destination runs (write order)
     std::vector<uint16_t> pos;           // read index -> (skewed) shared-memory slot
+    // bulk-copy (TMA-class) variant: source runs land in shared memory as they are (run r at
+    // r * (pb + run_pad)), threads gather them into destination order, destination runs leave
+    // by bulk store.  rslot[w] = shared-memory slot (in the padded source image) of write index w.
+    std::vector<uint16_t> rslot;
+    int run_pad = 0;
+    int gather_conflict = 0;
+    uint16_t* d_rslot = nullptr;
     // device copies, uploaded on first use
     int64_t* d_hi_src = nullptr;
     int64_t* d_hi_dst = nullptr;
@@ -131,7 +138,7 @@ struct ndmps_ctx {
     // options
     int64_t opt_gram_path = 0;      // 0: auto (FP64 tensor pipe when the shape allows), 2: force the SIMT kernel
     int64_t opt_jacobi_block = 0;   // 0: auto
-    int64_t opt_permute_path = 0;   // 0: tiled through shared memory when the shape tiles, 2: force the gather kernel
+    int64_t opt_permute_path = 0;   // 0: bulk-copy tiles when aligned, else ld/st tiles; 1: ld/st tiles; 2: gather kernel
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
     int64_t opt_chol_rows = 0;            // rows per CTA of the pivoted Cholesky (0: auto)
