@@ -124,12 +124,27 @@ permute_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, const TileA
         // ---- source runs -> shared memory (destination order) ----
         if (VEC == 4) {
             const int nvec = ta.tile >> 2, pbv = ta.pb >> 2;
-            for (int v = tid; v < nvec; v += PERM_THREADS) {
-                const int hi = v / pbv, lo = (v - hi * pbv) << 2;
-                const float4 val = *reinterpret_cast<const float4*>(src + base_src + ta.hi_src[hi] + lo);
-                const int r = hi * ta.pb + lo;
-                const ushort4 p4 = *reinterpret_cast<const ushort4*>(ta.pos + r);
-                buf[p4.x] = (T)val.x; buf[p4.y] = (T)val.y; buf[p4.z] = (T)val.z; buf[p4.w] = (T)val.w;
+            // four independent 16-byte loads in flight per thread before anything is stored
+            for (int v0 = tid; v0 < nvec; v0 += 4 * PERM_THREADS) {
+                float4 val[4];
+                int rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int v = v0 + u * PERM_THREADS;
+                    rr[u] = -1;
+                    if (v < nvec) {
+                        const int hi = v / pbv, lo = (v - hi * pbv) << 2;
+                        val[u] = __ldcs(reinterpret_cast<const float4*>(src + base_src + ta.hi_src[hi] + lo));
+                        rr[u] = hi * ta.pb + lo;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (rr[u] >= 0) {
+                        const ushort4 p4 = *reinterpret_cast<const ushort4*>(ta.pos + rr[u]);
+                        buf[p4.x] = (T)val[u].x; buf[p4.y] = (T)val[u].y; buf[p4.z] = (T)val[u].z; buf[p4.w] = (T)val[u].w;
+                    }
+                }
             }
         } else {
             for (int r = tid; r < ta.tile; r += PERM_THREADS) {
@@ -147,7 +162,7 @@ permute_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, const TileA
                 const int s = skew_slot(w);                 // 4 consecutive slots: w % 4 == 0 keeps them inside one 32-group
                 float4 val = make_float4((float)buf[s], (float)buf[s + 1], (float)buf[s + 2], (float)buf[s + 3]);
                 if (do_scale) { val.x *= (float)scale; val.y *= (float)scale; val.z *= (float)scale; val.w *= (float)scale; }
-                *reinterpret_cast<float4*>(dst + base_dst + ta.hi_dst[hi] + lo) = val;
+                __stcs(reinterpret_cast<float4*>(dst + base_dst + ta.hi_dst[hi] + lo), val);
             }
         } else {
             for (int w = tid; w < ta.tile; w += PERM_THREADS) {
@@ -433,7 +448,7 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
     // ---- bulk-copy (TMA-class) variant: every run and offset must be a multiple of 16 bytes ----
     {
         const int q = 16 / (int)sizeof(T);
-        bool aligned = ctx->opt_permute_path != 1 && tp.pa % q == 0 && tp.pb % q == 0 &&
+        bool aligned = ctx->opt_permute_path == 3 && tp.pa % q == 0 && tp.pb % q == 0 &&
                        reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
         for (size_t k = 0; k < tp.hi_src.size() && aligned; k++) aligned = tp.hi_src[k] % q == 0;
         for (size_t k = 0; k < tp.hi_dst.size() && aligned; k++) aligned = tp.hi_dst[k] % q == 0;
@@ -475,7 +490,7 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
         }
     }
     int64_t grid = tp.n_tiles;
-    const int64_t cap = (int64_t)ctx->sm_count * 6;
+    int64_t cap = (int64_t)ctx->sm_count * (ctx->opt_permute_ctas > 0 ? ctx->opt_permute_ctas : 6);
     if (grid > cap) grid = cap;
     // 16-byte accesses when every run and every run offset is a multiple of 4 elements (float32 only)
     bool vec4 = sizeof(T) == 4 && (tp.pa % 4 == 0) && (tp.pb % 4 == 0) &&
