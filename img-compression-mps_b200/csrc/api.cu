@@ -170,6 +170,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     NDMPS_REQUIRE(ctx != nullptr && name != nullptr, "ndmps_ctx_set_option: NULL argument");
     if (!strcmp(name, "gram_path")) ctx->opt_gram_path = value;
     else if (!strcmp(name, "jacobi_block")) ctx->opt_jacobi_block = value;
+    else if (!strcmp(name, "gemm_path")) ctx->opt_gemm_path = value;
     else if (!strcmp(name, "permute_path")) ctx->opt_permute_path = value;
     else if (!strcmp(name, "permute_ctas")) ctx->opt_permute_ctas = value;
     else if (!strcmp(name, "merge_cap")) ctx->opt_merge_cap = value;

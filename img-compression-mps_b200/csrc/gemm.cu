@@ -138,6 +138,10 @@ splitk_reduce_kernel(const double* __restrict__ partial, int splits, int64_t M, 
     }
 }
 
+int gemm_dmma(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int dtype_a, int64_t a_rs,
+              int64_t a_cs, const void* b, int dtype_b, int64_t b_rs, int64_t b_cs, void* c, int dtype_c, int64_t ldc,
+              bool* done);
+
 int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
          const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,
          const void* b, int dtype_b, int64_t b_rs, int64_t b_cs,
@@ -145,6 +149,11 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     NDMPS_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative size");
     NDMPS_REQUIRE(dtype_ok(dtype_a) && dtype_ok(dtype_b) && dtype_ok(dtype_c), "gemm: bad dtype");
     if (m == 0 || n == 0) return NDMPS_OK;
+    {   // large row-major products go to the FP64 tensor pipe (gemm_dmma.cu)
+        bool done = false;
+        NDMPS_TRY(gemm_dmma(ctx, m, n, k, alpha, a, dtype_a, a_rs, a_cs, b, dtype_b, b_rs, b_cs, c, dtype_c, ldc, &done));
+        if (done) return NDMPS_OK;
+    }
     int64_t tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
     int64_t tiles = tiles_m * tiles_n;
     NDMPS_REQUIRE(tiles < (int64_t(1) << 31), "gemm: %lld x %lld output too large for one launch", (long long)m, (long long)n);

@@ -92,7 +92,7 @@ scaled_transpose_kernel(const double* __restrict__ src, int64_t n, int64_t cols,
     int64_t total = n * cols, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int64_t j = i / cols, c = i - j * cols;
-        dst[i] = (T)(src[c * ld_src + j] * rowscale[j] * alpha);
+        dst[i] = (T)(src[c * ld_src + j] * (rowscale ? rowscale[j] : 1.0) * alpha);
     }
 }
 
@@ -300,7 +300,14 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             // T = P^T M   (rc x C)
             r_out = rc;
             NDMPS_TRY(ctx->ws.alloc((size_t)(r_out * C) * esz, &T));
-            { StageScope sc(ctx, ST_PROJECT); NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, P, NDMPS_F64, 1, r_out, M, dtype, C, 1, T, dtype, C)); }
+            {
+                StageScope sc(ctx, ST_PROJECT);
+                // P^T made explicit (r x D, tiny) so the big product reads both operands along their rows
+                double* Pt = nullptr;
+                NDMPS_TRY(ctx->ws.get<double>((size_t)(r_out * D), &Pt));
+                NDMPS_TRY(scaled_transpose(ctx, P, r_out, D, r_out, nullptr, 1.0, Pt, NDMPS_F64));
+                NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, Pt, NDMPS_F64, D, 1, M, dtype, C, 1, T, dtype, C));
+            }
         } else {
             // more rows than columns: Gram on the column side, G' = M^T M = V s^2 V^T
             double *G = nullptr, *evals = nullptr, *V = nullptr;
@@ -416,25 +423,47 @@ static int compress_bond(ndmps_ctx* ctx, const void* t1, const void* t2, int dty
 // ---------------------------------------------------------------------------------
 static int contract_dense(ndmps_ctx* ctx, const void* const* cores, int dtype, int L, const int64_t* dims,
                           const int64_t* ranks, void* dense_out) {
+    // Meet in the middle: X = product of the cores left of a split site s (P_s x r), W = product of
+    // the cores from s on (r x Q_s), dense = X W in ONE large product that writes every voxel once.
+    // Left and right chains are small; total flops ~ 2 N r instead of sum_k 2 P_k r d r.
     const size_t esz = dtype_size(dtype);
     if (L == 1) {
         NDMPS_CUDA_TRY(cudaMemcpyAsync(dense_out, cores[0], (size_t)dims[0] * esz, cudaMemcpyDeviceToDevice, ctx->stream));
         return NDMPS_OK;
     }
     StageScope sc(ctx, ST_CONTRACT);
-    const void* X = cores[0];        // (rows x r)
+    // split site: first s with P_s = prod_{k<s} d_k >= sqrt(N) (balanced), 1 <= s <= L-1
+    double logn = 0.0;
+    for (int k = 0; k < L; k++) logn += log((double)dims[k]);
+    int s = 1;
+    {
+        double acc = log((double)dims[0]);
+        while (s < L - 1 && acc < 0.5 * logn) { acc += log((double)dims[s]); s++; }
+    }
+    // left chain: X (rows x ranks[s-1])
+    const void* X = cores[0];
     int64_t rows = dims[0];
-    for (int k = 1; k < L; k++) {
-        int64_t rin = ranks[k - 1];
-        int64_t rout = k < L - 1 ? ranks[k] : 1;
-        int64_t ncols = dims[k] * rout;
-        void* out = dense_out;
-        if (k < L - 1) NDMPS_TRY(ctx->ws.alloc((size_t)(rows * ncols) * esz, &out));
+    for (int k = 1; k < s; k++) {
+        int64_t rin = ranks[k - 1], rout = ranks[k], ncols = dims[k] * rout;
+        void* out = nullptr;
+        NDMPS_TRY(ctx->ws.alloc((size_t)(rows * ncols) * esz, &out));
         NDMPS_TRY(gemm(ctx, rows, ncols, rin, 1.0, X, dtype, rin, 1, cores[k], dtype, ncols, 1, out, dtype, ncols));
         X = out;
         rows *= dims[k];
     }
-    return NDMPS_OK;
+    // right chain: W (ranks[s-1] x cols), built from the last core backwards
+    const void* W = cores[L - 1];                 // (r_{L-2} x d_{L-1})
+    int64_t cols = dims[L - 1];
+    for (int k = L - 2; k >= s; k--) {
+        int64_t rl = ranks[k - 1], rr = ranks[k];  // core k: (rl, d_k, rr) = (rl*d_k) x rr
+        void* out = nullptr;
+        NDMPS_TRY(ctx->ws.alloc((size_t)(rl * dims[k] * cols) * esz, &out));
+        NDMPS_TRY(gemm(ctx, rl * dims[k], cols, rr, 1.0, cores[k], dtype, rr, 1, W, dtype, cols, 1, out, dtype, cols));
+        W = out;
+        cols *= dims[k];
+    }
+    const int64_t r = ranks[s - 1];
+    return gemm(ctx, rows, cols, r, 1.0, X, dtype, r, 1, W, dtype, cols, 1, dense_out, dtype, cols);
 }
 
 // ---------------------------------------------------------------------------------
