@@ -570,6 +570,142 @@ pivoted_cholesky_kernel(const double* __restrict__ G, int n, int rows_per, doubl
     if (cta == 0 && tid == 0) ((int*)ctrl)[1] = rank;
 }
 
+// ---------------------------------------------------------------------------------------------
+// All-in-one solver for n <= 128: pivoted Cholesky, Jacobi on the factor's columns, sort and
+// eigenvector extraction in ONE CTA and ONE launch (no grid barrier, no host round trip).
+//
+// Shared memory holds the n x n working matrix column-major.  The Cholesky is right-looking on
+// the full symmetric Schur complement with a "dead" mask instead of row/column swaps; column k
+// of L is written into the storage of the column that step k eliminates (slot piv[k]), so the
+// factorisation is in place.  The Jacobi phase then sweeps the rank columns piv[0..rank) with
+// eight lanes per column pair.
+// ---------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(512)
+eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol2, double stop_rel,
+                  double* __restrict__ evals, double* __restrict__ evecs, int* __restrict__ info) {
+    extern __shared__ double S[];                    // n x n, column c at S + c*n
+    __shared__ int piv[128];                         // piv[k] = original index eliminated at step k = slot of L's column k
+    __shared__ int dead[128];
+    __shared__ double lcol[128];
+    __shared__ double red_val[16];
+    __shared__ int red_idx[16];
+    __shared__ double s_pval;
+    __shared__ int s_prow;
+    __shared__ double cnorm[128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    for (int i = tid; i < n * n; i += blockDim.x) S[i] = G[i];
+    if (tid < n) dead[tid] = 0;
+    __syncthreads();
+    // ---- pivoted Cholesky ----
+    double p0 = 0.0;
+    int rank = n;
+    for (int k = 0; k < n; k++) {
+        double best = -1.0;
+        int bi = -1;
+        if (tid < n && !dead[tid]) { best = S[(size_t)tid * n + tid]; bi = tid; }
+        if (warp < 4) {                              // n <= 128: candidates live in the first four warps
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
+            }
+            if (lane == 0) { red_val[warp] = best; red_idx[warp] = bi; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double b = -1.0;
+            int bj = -1;
+            for (int w = 0; w < 4; w++)
+                if (red_idx[w] >= 0 && (red_val[w] > b || (red_val[w] == b && (bj < 0 || red_idx[w] < bj)))) { b = red_val[w]; bj = red_idx[w]; }
+            s_pval = b;
+            s_prow = bj;
+        }
+        __syncthreads();
+        const double pval = s_pval;
+        const int prow = s_prow;
+        if (k == 0) p0 = pval;
+        if (prow < 0 || !(pval > stop_rel * p0) || !(pval > 0.0)) { rank = k; break; }
+        const double root = sqrt(pval), inv = 1.0 / root;
+        if (tid < n) {
+            double l = 0.0;
+            if (tid == prow) l = root;
+            else if (!dead[tid]) l = S[(size_t)prow * n + tid] * inv;     // column prow = row prow (symmetric)
+            lcol[tid] = l;
+        }
+        __syncthreads();
+        // Schur complement update of the live part; column prow is dead from now on
+        for (int idx = tid; idx < n * n; idx += blockDim.x) {
+            const int c = idx / n, r = idx - c * n;
+            if (c == prow) continue;
+            if (!dead[c] && !dead[r] && r != prow) S[idx] = fma(-lcol[r], lcol[c], S[idx]);
+        }
+        __syncthreads();
+        if (tid < n) S[(size_t)prow * n + tid] = lcol[tid];               // L's column k takes the dead slot
+        if (tid == 0) { dead[prow] = 1; piv[k] = prow; }
+        __syncthreads();
+    }
+    // ---- Jacobi on the rank columns (slots piv[0..rank)) ----
+    const double floor2 = (double)n * 2.220446049250313e-16 * (double)n * 2.220446049250313e-16 * p0;
+    const int grp = lane >> 3, li = lane & 7;
+    const int P = (rank + 1) & ~1;
+    const int matches = P / 2;
+    int sweep = 0;
+    int done = rank < 2 ? 1 : 0;
+    while (!done && sweep < max_sweeps) {
+        bool any = false;
+        for (int lr = 0; lr < P - 1; lr++) {
+            for (int m0 = warp * 4; m0 < matches; m0 += W * 4) {      // warp-uniform trip count
+                const int m = m0 + grp;
+                int s1 = 0, s2 = 0;
+                if (m < matches) tournament_pair(P, lr, m, s1, s2);
+                const bool valid = m < matches && s1 < rank && s2 < rank;
+                const int c1 = valid ? piv[s1] : 0, c2 = valid ? piv[s2] : 0;
+                any |= rotate_group<NR, 8>(S + (size_t)c1 * n, S + (size_t)c2 * n, n, li, valid, tol2, floor2);
+            }
+            __syncthreads();
+        }
+        sweep++;
+        done = !__syncthreads_or(any ? 1 : 0);
+    }
+    // ---- eigenvalues (squared column norms), descending order, eigenvectors ----
+    for (int c = warp; c < rank; c += W) {
+        const double* col = S + (size_t)piv[c] * n;
+        double s = 0.0;
+        for (int i = lane; i < n; i += 32) s = fma(col[i], col[i], s);
+        s = warp_sum(s);
+        if (lane == 0) cnorm[c] = sqrt(s);
+    }
+    __syncthreads();
+    for (int c = warp; c < n; c += W) {
+        if (c >= rank) {                                             // rank-deficient tail
+            if (lane == 0) evals[c] = 0.0;
+            for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + c] = 0.0;
+            continue;
+        }
+        const double mine = cnorm[c];
+        int cnt = 0;
+        for (int k = lane; k < rank; k += 32) {
+            double o = cnorm[k];
+            cnt += (o > mine || (o == mine && k < c)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) evals[cnt] = mine * mine;
+        const double invn = mine > 0.0 ? 1.0 / mine : 0.0;
+        const double* col = S + (size_t)piv[c] * n;
+        for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + cnt] = col[i] * invn;
+    }
+    if (tid == 0) { info[0] = done ? sweep : -(sweep + 1); info[1] = rank; }
+}
+
+template <class K>
+static int raise_smem_minus(K kernel, const ndmps_ctx* ctx, int reserve) {
+    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - reserve));
+    return NDMPS_OK;
+}
+
 template <class K>
 static int raise_smem(K kernel, const ndmps_ctx* ctx) {
     NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -710,6 +846,35 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     if (tol_override > tol) tol = tol_override;
     const double tol2 = tol * tol;
 
+    if (ctx->opt_eig_small && n >= 2 && n <= 128) {
+        // one launch, no host synchronisation: the result (and a convergence code) stay on the device;
+        // the code is checked at the next point where the host reads the eigenvalues anyway
+        int* info = nullptr;
+        NDMPS_TRY(ctx->ws.get<int>(4, &info));
+        const size_t smem = (size_t)n * n * sizeof(double);
+        double stop_rel = 2.220446049250313e-16;
+#define NDMPS_SMALL(NRV)                                                                                              \
+        do {                                                                                                            \
+            static bool attr_set = false;                                                                               \
+            if (!attr_set) { NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192)); attr_set = true; }        \
+            eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, evals_dev, evecs_dev, info); \
+        } while (0)
+        if (n <= 32) NDMPS_SMALL(4);
+        else if (n <= 64) NDMPS_SMALL(8);
+        else NDMPS_SMALL(16);
+#undef NDMPS_SMALL
+        NDMPS_LAUNCH_CHECK(ctx);
+        int* host_flag = reinterpret_cast<int*>(ctx->pinned);
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (host_flag[0] < 0) {
+            set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, single-CTA solver)", max_sweeps, n);
+            return NDMPS_ERR_NOCONV;
+        }
+        ctx->last_eig_sweeps = host_flag[0];
+        if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh n = %d: %d columns, %d sweeps (single CTA)\n", n, host_flag[1], host_flag[0]);
+        return NDMPS_OK;
+    }
     double* cols = a_in;      // the column set Jacobi works on
     int ncols = n;
     int square = 0;           // eigenvalue = column norm (Jacobi on G) or its square (Jacobi on L)
