@@ -571,7 +571,7 @@ pivoted_cholesky_kernel(const double* __restrict__ G, int n, int rows_per, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// All-in-one solver for n <= 128: pivoted Cholesky, Jacobi on the factor's columns, sort and
+// All-in-one solver for n <= 64 (beyond that one SM's shared-memory bandwidth is the limit): pivoted Cholesky, Jacobi on the factor's columns, sort and
 // eigenvector extraction in ONE CTA and ONE launch (no grid barrier, no host round trip).
 //
 // Shared memory holds the n x n working matrix column-major.  The Cholesky is right-looking on
@@ -584,7 +584,8 @@ template <int NR>
 __global__ void __launch_bounds__(512)
 eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol2, double stop_rel,
                   double* __restrict__ evals, double* __restrict__ evecs, int* __restrict__ info) {
-    extern __shared__ double S[];                    // n x n, column c at S + c*n
+    extern __shared__ double S[];                    // n columns of stride ld = n + 2 (the pad spreads columns over banks)
+    const int ld = n + 2;
     __shared__ int piv[128];                         // piv[k] = original index eliminated at step k = slot of L's column k
     __shared__ int dead[128];
     __shared__ double lcol[128];
@@ -594,7 +595,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     __shared__ int s_prow;
     __shared__ double cnorm[128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    for (int i = tid; i < n * n; i += blockDim.x) S[i] = G[i];
+    for (int i = tid; i < n * n; i += blockDim.x) { const int c = i / n, r = i - c * n; S[(size_t)c * ld + r] = G[i]; }
     if (tid < n) dead[tid] = 0;
     __syncthreads();
     // ---- pivoted Cholesky ----
@@ -603,7 +604,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     for (int k = 0; k < n; k++) {
         double best = -1.0;
         int bi = -1;
-        if (tid < n && !dead[tid]) { best = S[(size_t)tid * n + tid]; bi = tid; }
+        if (tid < n && !dead[tid]) { best = S[(size_t)tid * ld + tid]; bi = tid; }
         if (warp < 4) {                              // n <= 128: candidates live in the first four warps
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -631,7 +632,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
         if (tid < n) {
             double l = 0.0;
             if (tid == prow) l = root;
-            else if (!dead[tid]) l = S[(size_t)prow * n + tid] * inv;     // column prow = row prow (symmetric)
+            else if (!dead[tid]) l = S[(size_t)prow * ld + tid] * inv;     // column prow = row prow (symmetric)
             lcol[tid] = l;
         }
         __syncthreads();
@@ -639,10 +640,10 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
         for (int idx = tid; idx < n * n; idx += blockDim.x) {
             const int c = idx / n, r = idx - c * n;
             if (c == prow) continue;
-            if (!dead[c] && !dead[r] && r != prow) S[idx] = fma(-lcol[r], lcol[c], S[idx]);
+            if (!dead[c] && !dead[r] && r != prow) S[(size_t)c * ld + r] = fma(-lcol[r], lcol[c], S[(size_t)c * ld + r]);
         }
         __syncthreads();
-        if (tid < n) S[(size_t)prow * n + tid] = lcol[tid];               // L's column k takes the dead slot
+        if (tid < n) S[(size_t)prow * ld + tid] = lcol[tid];               // L's column k takes the dead slot
         if (tid == 0) { dead[prow] = 1; piv[k] = prow; }
         __syncthreads();
     }
@@ -662,7 +663,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
                 if (m < matches) tournament_pair(P, lr, m, s1, s2);
                 const bool valid = m < matches && s1 < rank && s2 < rank;
                 const int c1 = valid ? piv[s1] : 0, c2 = valid ? piv[s2] : 0;
-                any |= rotate_group<NR, 8>(S + (size_t)c1 * n, S + (size_t)c2 * n, n, li, valid, tol2, floor2);
+                any |= rotate_group<NR, 8>(S + (size_t)c1 * ld, S + (size_t)c2 * ld, n, li, valid, tol2, floor2);
             }
             __syncthreads();
         }
@@ -671,7 +672,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     }
     // ---- eigenvalues (squared column norms), descending order, eigenvectors ----
     for (int c = warp; c < rank; c += W) {
-        const double* col = S + (size_t)piv[c] * n;
+        const double* col = S + (size_t)piv[c] * ld;
         double s = 0.0;
         for (int i = lane; i < n; i += 32) s = fma(col[i], col[i], s);
         s = warp_sum(s);
@@ -694,7 +695,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) evals[cnt] = mine * mine;
         const double invn = mine > 0.0 ? 1.0 / mine : 0.0;
-        const double* col = S + (size_t)piv[c] * n;
+        const double* col = S + (size_t)piv[c] * ld;
         for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + cnt] = col[i] * invn;
     }
     if (tid == 0) { info[0] = done ? sweep : -(sweep + 1); info[1] = rank; }
@@ -846,12 +847,12 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     if (tol_override > tol) tol = tol_override;
     const double tol2 = tol * tol;
 
-    if (ctx->opt_eig_small && n >= 2 && n <= 128) {
+    if (ctx->opt_eig_small && n >= 2 && n <= 64) {
         // one launch, no host synchronisation: the result (and a convergence code) stay on the device;
         // the code is checked at the next point where the host reads the eigenvalues anyway
         int* info = nullptr;
         NDMPS_TRY(ctx->ws.get<int>(4, &info));
-        const size_t smem = (size_t)n * n * sizeof(double);
+        const size_t smem = (size_t)n * (n + 2) * sizeof(double);
         double stop_rel = 2.220446049250313e-16;
 #define NDMPS_SMALL(NRV)                                                                                              \
         do {                                                                                                            \
@@ -860,8 +861,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
             eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, evals_dev, evecs_dev, info); \
         } while (0)
         if (n <= 32) NDMPS_SMALL(4);
-        else if (n <= 64) NDMPS_SMALL(8);
-        else NDMPS_SMALL(16);
+        else NDMPS_SMALL(8);
 #undef NDMPS_SMALL
         NDMPS_LAUNCH_CHECK(ctx);
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
