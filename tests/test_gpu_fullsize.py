@@ -81,13 +81,13 @@ def test_chi_sweep_properties_256(volume256):
 
 def test_sharded_batch_and_dct(volume256):
     from imgcompressionmps.distributed import compress_and_score, run_sharded
-    vols = [volume256[:64, :64, :64].contiguous() * (1.0 + 0.1 * i) for i in range(3)]
+    vols = [volume256[96:160, 96:160, 96:160].contiguous() * (1.0 + 0.1 * i) for i in range(3)]      # central crop: the corners are background
     res = run_sharded(vols, lambda i, v: compress_and_score(i, v, max_bond=16))
     assert [r["index"] for r in res] == [0, 1, 2]
     assert all(r["bond_dims"] == res[0]["bond_dims"] for r in res)            # scaling the data does not change ranks
     assert all(abs(r["fidelity"] - res[0]["fidelity"]) < 1e-6 for r in res)
     from imgcompressionmps.core.ndmps import NDMPS
-    v = volume256[:128, :128, :96].contiguous()
+    v = volume256[64:192, 64:192, 80:176].contiguous()
     d = NDMPS.from_tensor(v, mode="DCT")
     rec = d.to_tensor_device()
     assert float((rec - v).abs().max()) < 5e-4 * float(v.abs().max())
@@ -102,7 +102,7 @@ def test_fmri_like_4d():
     t = torch.linspace(0, 6.28, 100, device="cuda").reshape(1, 1, 1, -1)
     x = (base * (1.0 + 0.05 * torch.sin(t)) + 0.01 * torch.rand((64, 64, 32, 100), device="cuda", generator=g)).float().contiguous()
     obj = NDMPS.from_tensor(x, max_bond=32)
-    assert obj.mps.site_dims == [40, 20, 32, 16, 32] or len(obj.mps.site_dims) == 5
+    assert int(np.prod(obj.mps.site_dims)) == x.numel() and max(obj.bond_sizes()) <= 32
     rec = obj.to_tensor_device()
     assert float(torch.linalg.vector_norm(rec - x) / torch.linalg.vector_norm(x)) < 0.05
     s = compute_ssim_by_dim(rec, x)
