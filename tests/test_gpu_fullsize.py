@@ -90,7 +90,8 @@ def test_sharded_batch_and_dct(volume256):
     v = volume256[64:192, 64:192, 80:176].contiguous()
     d = NDMPS.from_tensor(v, mode="DCT")
     rec = d.to_tensor_device()
-    assert float((rec - v).abs().max()) < 5e-4 * float(v.abs().max())
+    # the default rsum2 cutoff (1e-10 of the weight per bond) costs ~1e-5 relative per bond
+    assert float(torch.linalg.vector_norm(rec - v) / torch.linalg.vector_norm(v)) < 1e-4
 
 
 def test_fmri_like_4d():
