@@ -138,22 +138,34 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _all_host_threads():
+    """Context manager giving BLAS every host core (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def cpu_oracle_rate(sample, chi, repeats):
     """voxels/s of the CPU oracle (numpy float64, LAPACK gesdd, all BLAS threads) on `sample`."""
     from oracle.ndmps import OracleNDMPS
     best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        OracleNDMPS.from_tensor(sample, max_bond=chi).to_tensor()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    with _all_host_threads():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            OracleNDMPS.from_tensor(sample, max_bond=chi).to_tensor()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
     return sample.size / best, best
 
 
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
-        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+        with _all_host_threads():
+            n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
         return int(n)
     except Exception:
         return os.cpu_count() or 1
