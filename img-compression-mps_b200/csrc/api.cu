@@ -166,6 +166,18 @@ int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, 
     return NDMPS_OK;
 }
 
+int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, int reset) {
+    NDMPS_REQUIRE(ctx && name && value_out, "ndmps_ctx_get_stat: NULL argument");
+    if (!strcmp(name, "eig_flops")) { *value_out = ctx->eig_flops; if (reset) ctx->eig_flops = 0.0; }
+    else if (!strcmp(name, "eig_calls")) { *value_out = (double)ctx->eig_calls; if (reset) ctx->eig_calls = 0; }
+    else if (!strcmp(name, "workspace_bytes")) { *value_out = (double)ctx->ws.high_water; }
+    else {
+        set_error("ndmps_ctx_get_stat: unknown statistic '%s'", name);
+        return NDMPS_ERR_INVALID;
+    }
+    return NDMPS_OK;
+}
+
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     NDMPS_REQUIRE(ctx != nullptr && name != nullptr, "ndmps_ctx_set_option: NULL argument");
     if (!strcmp(name, "gram_path")) ctx->opt_gram_path = value;

@@ -143,13 +143,15 @@ struct ndmps_ctx {
     int64_t opt_permute_ctas = 0;   // persistent CTAs per SM of the tiled kernel (0: 6)
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
-    int64_t opt_chol_cluster = 1;         // pivoted Cholesky inside one thread-block cluster when it fits
+    int64_t opt_chol_cluster = 0;         // pivoted Cholesky inside one thread-block cluster (measured slower: DSMEM row broadcast)
     int64_t opt_chol_rows = 0;            // rows per CTA of the pivoted Cholesky (0: auto)
     int64_t opt_eig_small = 1;            // n <= 128: single-CTA all-in-one solver
     int64_t opt_eig_cholesky = 1;         // pivoted-Cholesky preconditioning of the Jacobi solve
     int64_t opt_verbose = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;
+    double eig_flops = 0.0;        // 7 n per rotation x pairs x sweeps (+ n r^2 for the Cholesky), accumulated
+    int64_t eig_calls = 0;
     // stage profiler
     bool profile = false;
     struct Pending { int stage; cudaEvent_t beg, end; };

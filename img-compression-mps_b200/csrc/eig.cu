@@ -1021,6 +1021,8 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
             return NDMPS_ERR_NOCONV;
         }
         ctx->last_eig_sweeps = host_flag[0];
+        ctx->eig_calls++;
+        ctx->eig_flops += 7.0 * n * 0.5 * host_flag[1] * (host_flag[1] - 1.0) * host_flag[0] + (double)n * host_flag[1] * host_flag[1];
         if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh n = %d: %d columns, %d sweeps (single CTA)\n", n, host_flag[1], host_flag[0]);
         return NDMPS_OK;
     }
@@ -1062,6 +1064,8 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         NDMPS_TRY(jacobi_columns(ctx, cols, n, ncols, tol2, floor2, &sweeps_used));
     }
     ctx->last_eig_sweeps = sweeps_used;
+    ctx->eig_calls++;
+    ctx->eig_flops += 7.0 * n * 0.5 * ncols * (ncols - 1.0) * sweeps_used + (use_chol ? (double)n * ncols * ncols : 0.0);
     if (ctx->opt_verbose)
         fprintf(stderr, "[ndmps] eigh n = %d: %d columns, %d sweeps%s\n", n, ncols, sweeps_used, use_chol ? " (pivoted Cholesky)" : "");
     if (ncols >= 1) {

@@ -122,6 +122,104 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Slice-batched variants for families whose SLICE INDEX is the contiguous memory dimension
+// (3-D: slices along the last axis; 4-D: every family, the frame index runs fastest).  A CTA
+// takes 32 consecutive slices, lane = slice: every global load is a coalesced 128-byte line
+// and the shared-memory patch [position][slice] is bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+constexpr int BT_H = 8, BT_W = 8, BT_SLICES = 32;
+
+template <class T>
+__global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
+                                                                  double* __restrict__ range) {
+    __shared__ double s_lo[8][BT_SLICES], s_hi[8][BT_SLICES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * BT_SLICES + lane;
+    double lo = INFINITY, hi = -INFINITY;
+    if (s < f.S) {
+        const int64_t base = slice_base(f, s);
+        const int64_t total = f.H * f.W;
+        for (int64_t e = warp; e < total; e += 8) {
+            int64_t h = e / f.W, w = e - h * f.W;
+            int64_t off = base + h * f.sh + w * f.sw;
+            double x = (double)a[off];
+            double y = fmax((double)b[off], 0.0);
+            lo = fmin(lo, fmin(x, y));
+            hi = fmax(hi, fmax(x, y));
+        }
+    }
+    s_lo[warp][lane] = lo;
+    s_hi[warp][lane] = hi;
+    __syncthreads();
+    if (warp == 0 && s < f.S) {
+        for (int w = 1; w < 8; w++) { lo = fmin(lo, s_lo[w][lane]); hi = fmax(hi, s_hi[w][lane]); }
+        range[s] = hi - lo;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
+                         int tiles_y, int tiles_x, double* __restrict__ partial) {
+    extern __shared__ unsigned char bt_smem[];
+    const int win = f.win, pad = (win - 1) / 2;
+    const int ph = BT_H + win - 1, pw = BT_W + win - 1;
+    T* pa = reinterpret_cast<T*>(bt_smem);                       // [ph*pw][32]
+    T* pb = pa + (size_t)ph * pw * BT_SLICES;
+    __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t bid = blockIdx.x;
+    const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+    const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+    const int64_t s = bid * BT_SLICES + lane;
+    const bool live = s < f.S;
+    const int64_t base = live ? slice_base(f, s) : 0;
+    const int64_t oy = (int64_t)ty * BT_H, ox = (int64_t)tx * BT_W;
+    for (int e = warp; e < ph * pw; e += 8) {
+        const int r = e / pw, c = e - r * pw;
+        const int64_t h = oy + r, w = ox + c;
+        T va = (T)0, vb = (T)0;
+        if (live && h < f.H && w < f.W) {
+            const int64_t off = base + h * f.sh + w * f.sw;
+            va = a[off];
+            vb = b[off];
+            vb = vb > (T)0 ? vb : (T)0;
+        }
+        pa[(size_t)e * BT_SLICES + lane] = va;
+        pb[(size_t)e * BT_SLICES + lane] = vb;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (live) {
+        const double R = range[s];
+        const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
+        const double np = (double)(win * win);
+        const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+        const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
+        for (int pix = warp; pix < BT_H * BT_W; pix += 8) {
+            const int y = pix / BT_W, x = pix - y * BT_W;
+            if (oy + y >= ih || ox + x >= iw) continue;
+            double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+            for (int i = 0; i < win; i++) {
+                const size_t rowbase = ((size_t)(y + i) * pw + x) * BT_SLICES + lane;
+                for (int j = 0; j < win; j++) {
+                    const double xv = (double)pa[rowbase + (size_t)j * BT_SLICES];
+                    const double yv = (double)pb[rowbase + (size_t)j * BT_SLICES];
+                    sx += xv; sy += yv;
+                    sxx = fma(xv, xv, sxx); syy = fma(yv, yv, syy); sxy = fma(xv, yv, sxy);
+                }
+            }
+            const double ux = sx * inv_np, uy = sy * inv_np;
+            const double vx = cov_norm * (sxx * inv_np - ux * ux), vy = cov_norm * (syy * inv_np - uy * uy);
+            const double vxy = cov_norm * (sxy * inv_np - ux * uy);
+            acc += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 // out[fam] = sum(partial[begin..end)) * scale, one CTA per family
 __global__ void __launch_bounds__(256) ssim_final_kernel(const double* __restrict__ partial, const int64_t* __restrict__ bounds,
                                                           const double* __restrict__ scale, double* __restrict__ out) {
@@ -173,14 +271,18 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
     int64_t bounds_h[4] = {0, 0, 0, 0};
     double scale_h[3] = {0, 0, 0};
     int tiles_y[3], tiles_x[3];
+    bool batched[3];
     int64_t total_tiles = 0, total_slices = 0;
     for (int k = 0; k < nfam; k++) {
         const SliceFamily& f = fams[k];
         int pad = (f.win - 1) / 2;
         int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
-        tiles_y[k] = (int)((ih + TILE_H - 1) / TILE_H);
-        tiles_x[k] = (int)((iw + TILE_W - 1) / TILE_W);
-        int64_t nt = f.S * tiles_y[k] * tiles_x[k];
+        // consecutive slice indices are consecutive addresses: frames (4-D) or the last axis (3-D)
+        batched[k] = f.S >= 8 && ((f.nT > 1 && f.s_t == 1) || (f.nT == 1 && f.s_axis == 1));
+        const int th = batched[k] ? BT_H : TILE_H, tw = batched[k] ? BT_W : TILE_W;
+        tiles_y[k] = (int)((ih + th - 1) / th);
+        tiles_x[k] = (int)((iw + tw - 1) / tw);
+        int64_t nt = (batched[k] ? (f.S + BT_SLICES - 1) / BT_SLICES : f.S) * tiles_y[k] * tiles_x[k];
         NDMPS_REQUIRE(nt < (int64_t(1) << 31), "ssim: too many tiles");
         bounds_h[k] = total_tiles;
         total_tiles += nt;
@@ -200,12 +302,26 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
     int64_t slice_off = 0;
     for (int k = 0; k < nfam; k++) {
         const SliceFamily& f = fams[k];
-        ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
-        NDMPS_LAUNCH_CHECK(ctx);
         int64_t nt = bounds_h[k + 1] - bounds_h[k];
-        ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
-                                                                  partial + bounds_h[k]);
-        NDMPS_LAUNCH_CHECK(ctx);
+        if (batched[k]) {
+            const size_t bsm = (size_t)2 * (BT_H + f.win - 1) * (BT_W + f.win - 1) * BT_SLICES * sizeof(T);
+            static bool attr_set = false;
+            if (!attr_set) {
+                NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                attr_set = true;
+            }
+            ssim_range_batched_kernel<T><<<(unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
+            NDMPS_LAUNCH_CHECK(ctx);
+            ssim_tile_batched_kernel<T><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
+                                                                                 partial + bounds_h[k]);
+            NDMPS_LAUNCH_CHECK(ctx);
+        } else {
+            ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
+            NDMPS_LAUNCH_CHECK(ctx);
+            ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
+                                                                      partial + bounds_h[k]);
+            NDMPS_LAUNCH_CHECK(ctx);
+        }
         slice_off += f.S;
     }
     ssim_final_kernel<<<nfam, 256, 0, ctx->stream>>>(partial, bounds_dev, scale_dev, out_dev);

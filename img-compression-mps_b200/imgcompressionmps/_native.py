@@ -36,6 +36,7 @@ PROTOTYPES = {
     "ndmps_ctx_sync": (ci, [vp]),
     "ndmps_ctx_launch_count": (i64, [vp]),
     "ndmps_ctx_set_option": (ci, [vp, C.c_char_p, i64]),
+    "ndmps_ctx_get_stat": (ci, [vp, C.c_char_p, p_f64, ci]),
     "ndmps_ctx_profile": (ci, [vp, ci]),
     "ndmps_stage_count": (ci, []),
     "ndmps_stage_name": (C.c_char_p, [ci]),
@@ -132,6 +133,11 @@ class Context:
 
     def set_option(self, name: str, value: int):
         check(self.lib.ndmps_ctx_set_option(self.handle, name.encode(), int(value)), "ndmps_ctx_set_option")
+
+    def stat(self, name: str, reset: bool = False) -> float:
+        out = C.c_double()
+        check(self.lib.ndmps_ctx_get_stat(self.handle, name.encode(), C.byref(out), int(bool(reset))), "ndmps_ctx_get_stat")
+        return out.value
 
     def profile(self, enable: bool):
         check(self.lib.ndmps_ctx_profile(self.handle, int(bool(enable))), "ndmps_ctx_profile")

@@ -69,6 +69,9 @@ int ndmps_ctx_profile(ndmps_ctx_t* ctx, int enable);
 int ndmps_stage_count(void);
 const char* ndmps_stage_name(int stage);
 int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, int reset);
+/* counters: "eig_flops" (rotation + factorisation flops of the bond eigensolves), "eig_calls",
+ * "workspace_bytes" (arena high-water mark). */
+int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, int reset);
 /* tuning knobs, e.g. "gram_path" 0=auto 2=force SIMT, "jacobi_block" */
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value);
 
