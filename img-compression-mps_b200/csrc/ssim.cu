@@ -158,12 +158,12 @@ __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __rest
     }
 }
 
-template <class T>
+template <class T, int WIN>
 __global__ void __launch_bounds__(256)
 ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                          int tiles_y, int tiles_x, double* __restrict__ partial) {
     extern __shared__ unsigned char bt_smem[];
-    const int win = f.win, pad = (win - 1) / 2;
+    constexpr int win = WIN, pad = (WIN - 1) / 2;
     const int ph = BT_H + win - 1, pw = BT_W + win - 1;
     T* pa = reinterpret_cast<T*>(bt_smem);                       // [ph*pw][32]
     T* pb = pa + (size_t)ph * pw * BT_SLICES;
@@ -194,26 +194,42 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     if (live) {
         const double R = range[s];
         const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
-        const double np = (double)(win * win);
-        const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+        constexpr double np = (double)(WIN * WIN);
+        constexpr double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
         const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
-        for (int pix = warp; pix < BT_H * BT_W; pix += 8) {
-            const int y = pix / BT_W, x = pix - y * BT_W;
-            if (oy + y >= ih || ox + x >= iw) continue;
-            double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
-            for (int i = 0; i < win; i++) {
-                const size_t rowbase = ((size_t)(y + i) * pw + x) * BT_SLICES + lane;
-                for (int j = 0; j < win; j++) {
+        // one output column per warp: horizontal WIN-tap sums per patch row, vertical running sum over
+        // a register ring of the last WIN rows (everything unrolled, the ring is static registers)
+        const int x = warp;
+        if (ox + x < iw) {
+            double ring[WIN][5];
+            double vs[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < BT_H + WIN - 1; r++) {
+                double hsum[5] = {0, 0, 0, 0, 0};
+                const size_t rowbase = ((size_t)r * pw + x) * BT_SLICES + lane;
+#pragma unroll
+                for (int j = 0; j < WIN; j++) {
                     const double xv = (double)pa[rowbase + (size_t)j * BT_SLICES];
                     const double yv = (double)pb[rowbase + (size_t)j * BT_SLICES];
-                    sx += xv; sy += yv;
-                    sxx = fma(xv, xv, sxx); syy = fma(yv, yv, syy); sxy = fma(xv, yv, sxy);
+                    hsum[0] += xv; hsum[1] += yv;
+                    hsum[2] = fma(xv, xv, hsum[2]); hsum[3] = fma(yv, yv, hsum[3]); hsum[4] = fma(xv, yv, hsum[4]);
+                }
+#pragma unroll
+                for (int q = 0; q < 5; q++) {
+                    if (r >= WIN) vs[q] -= ring[r % WIN][q];
+                    vs[q] += hsum[q];
+                    ring[r % WIN][q] = hsum[q];
+                }
+                if (r >= WIN - 1) {
+                    const int y = r - (WIN - 1);
+                    if (oy + y < ih) {
+                        const double ux = vs[0] * inv_np, uy = vs[1] * inv_np;
+                        const double vx = cov_norm * (vs[2] * inv_np - ux * ux), vy = cov_norm * (vs[3] * inv_np - uy * uy);
+                        const double vxy = cov_norm * (vs[4] * inv_np - ux * uy);
+                        acc += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+                    }
                 }
             }
-            const double ux = sx * inv_np, uy = sy * inv_np;
-            const double vx = cov_norm * (sxx * inv_np - ux * ux), vy = cov_norm * (syy * inv_np - uy * uy);
-            const double vxy = cov_norm * (sxy * inv_np - ux * uy);
-            acc += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
         }
     }
     acc = block_sum(acc, scratch);
@@ -278,7 +294,7 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         int pad = (f.win - 1) / 2;
         int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
         // consecutive slice indices are consecutive addresses: frames (4-D) or the last axis (3-D)
-        batched[k] = f.S >= 8 && ((f.nT > 1 && f.s_t == 1) || (f.nT == 1 && f.s_axis == 1));
+        batched[k] = f.win == 7 && f.S >= 8 && ((f.nT > 1 && f.s_t == 1) || (f.nT == 1 && f.s_axis == 1));
         const int th = batched[k] ? BT_H : TILE_H, tw = batched[k] ? BT_W : TILE_W;
         tiles_y[k] = (int)((ih + th - 1) / th);
         tiles_x[k] = (int)((iw + tw - 1) / tw);
@@ -307,12 +323,12 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
             const size_t bsm = (size_t)2 * (BT_H + f.win - 1) * (BT_W + f.win - 1) * BT_SLICES * sizeof(T);
             static bool attr_set = false;
             if (!attr_set) {
-                NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                 attr_set = true;
             }
             ssim_range_batched_kernel<T><<<(unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
             NDMPS_LAUNCH_CHECK(ctx);
-            ssim_tile_batched_kernel<T><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
+            ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
                                                                                  partial + bounds_h[k]);
             NDMPS_LAUNCH_CHECK(ctx);
         } else {
