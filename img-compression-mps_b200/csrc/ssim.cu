@@ -130,9 +130,22 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
 // ---------------------------------------------------------------------------------------------
 constexpr int BT_H = 8, BT_W = 8, BT_SLICES = 32;
 
+// order-preserving map double -> uint64 so that min / max can be done with integer atomics
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+constexpr int RANGE_CHUNK = 2048;   // slice positions per CTA
+
+// keys[2s] = min key, keys[2s+1] = max key (initialised to all-ones / zero by the host)
 template <class T>
 __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
-                                                                  double* __restrict__ range) {
+                                                                  unsigned long long* __restrict__ keys) {
     __shared__ double s_lo[8][BT_SLICES], s_hi[8][BT_SLICES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t s = (int64_t)blockIdx.x * BT_SLICES + lane;
@@ -140,7 +153,9 @@ __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __rest
     if (s < f.S) {
         const int64_t base = slice_base(f, s);
         const int64_t total = f.H * f.W;
-        for (int64_t e = warp; e < total; e += 8) {
+        const int64_t e0 = (int64_t)blockIdx.y * RANGE_CHUNK;
+        const int64_t e1 = e0 + RANGE_CHUNK < total ? e0 + RANGE_CHUNK : total;
+        for (int64_t e = e0 + warp; e < e1; e += 8) {
             int64_t h = e / f.W, w = e - h * f.W;
             int64_t off = base + h * f.sh + w * f.sw;
             double x = (double)a[off];
@@ -154,8 +169,17 @@ __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __rest
     __syncthreads();
     if (warp == 0 && s < f.S) {
         for (int w = 1; w < 8; w++) { lo = fmin(lo, s_lo[w][lane]); hi = fmax(hi, s_hi[w][lane]); }
-        range[s] = hi - lo;
+        if (lo <= hi) {
+            atomicMin(keys + 2 * s, dkey(lo));
+            atomicMax(keys + 2 * s + 1, dkey(hi));
+        }
     }
+}
+
+__global__ void __launch_bounds__(256) ssim_range_finalize_kernel(const unsigned long long* __restrict__ keys, int64_t S,
+                                                                   double* __restrict__ range) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) range[s] = dkey_inv(keys[2 * s + 1]) - dkey_inv(keys[2 * s]);
 }
 
 template <class T, int WIN>
@@ -326,7 +350,15 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
                 NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                 attr_set = true;
             }
-            ssim_range_batched_kernel<T><<<(unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
+            unsigned long long* keys = nullptr;
+            NDMPS_TRY(ctx->ws.get<unsigned long long>((size_t)(2 * f.S), &keys));
+            // min keys start at all-ones, max keys at zero: 0xFF.. / 0x00.. interleaved per slice
+            NDMPS_CUDA_TRY(cudaMemset2DAsync(keys, 16, 0xFF, 8, (size_t)f.S, ctx->stream));
+            NDMPS_CUDA_TRY(cudaMemset2DAsync(keys + 1, 16, 0x00, 8, (size_t)f.S, ctx->stream));
+            dim3 rgrid((unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), (unsigned)((f.H * f.W + RANGE_CHUNK - 1) / RANGE_CHUNK));
+            ssim_range_batched_kernel<T><<<rgrid, 256, 0, ctx->stream>>>(a, b, f, keys);
+            NDMPS_LAUNCH_CHECK(ctx);
+            ssim_range_finalize_kernel<<<(unsigned)((f.S + 255) / 256), 256, 0, ctx->stream>>>(keys, f.S, range + slice_off);
             NDMPS_LAUNCH_CHECK(ctx);
             ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
                                                                                  partial + bounds_h[k]);
