@@ -265,21 +265,52 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, 
     const int colp0 = p * b, colq0 = q * b;
     int cntp = ncols - colp0; cntp = cntp < 0 ? 0 : (cntp > b ? b : cntp);
     int cntq = ncols - colq0; cntq = cntq < 0 ? 0 : (cntq > b ? b : cntq);
-    for (int lc = warp; lc < 2 * b; lc += b) {
-        const bool isq = lc >= b;
-        const int l = isq ? lc - b : lc;
-        double acc = 0.0;
-        if (l < (isq ? cntq : cntp)) {
-            const double* src = A + (size_t)((isq ? colq0 : colp0) + l) * n;
-            double* dst = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) {
-                double v = __ldcg(src + i);
-                dst[i] = v;
-                acc = fma(v, v, acc);
-            }
+    if constexpr (NR > 0) {
+        // both columns of this warp are fetched with all loads in flight before anything is stored:
+        // a load -> store loop would serialise 2*NR L2 round trips per global round
+        double vp[NR], vq[NR];
+        const bool hp = warp < cntp, hq = warp < cntq;
+        const double* sp = A + (size_t)(colp0 + warp) * n;
+        const double* sq = A + (size_t)(colq0 + warp) * n;
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            vp[t] = (hp && i < n) ? __ldcg(sp + i) : 0.0;
+            vq[t] = (hq && i < n) ? __ldcg(sq + i) : 0.0;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) norm2[lc] = acc;
+        double ap = 0.0, aq = 0.0;
+        double* dp = S + (size_t)warp * n;
+        double* dq = S + (size_t)(b + warp) * n;
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            if (i < n) {
+                if (hp) dp[i] = vp[t];
+                if (hq) dq[i] = vq[t];
+            }
+            ap = fma(vp[t], vp[t], ap);
+            aq = fma(vq[t], vq[t], aq);
+        }
+        ap = warp_sum(ap);
+        aq = warp_sum(aq);
+        if (lane == 0) { norm2[warp] = ap; norm2[b + warp] = aq; }
+    } else {
+        for (int lc = warp; lc < 2 * b; lc += b) {
+            const bool isq = lc >= b;
+            const int l = isq ? lc - b : lc;
+            double acc = 0.0;
+            if (l < (isq ? cntq : cntp)) {
+                const double* src = A + (size_t)((isq ? colq0 : colp0) + l) * n;
+                double* dst = S + (size_t)lc * n;
+                for (int i = lane; i < n; i += 32) {
+                    double v = __ldcg(src + i);
+                    dst[i] = v;
+                    acc = fma(v, v, acc);
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) norm2[lc] = acc;
+        }
     }
     __syncthreads();
     bool any = false;
@@ -304,13 +335,36 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, 
             __syncthreads();
         }
     }
-    for (int lc = warp; lc < 2 * b; lc += b) {
-        const bool isq = lc >= b;
-        const int l = isq ? lc - b : lc;
-        if (l < (isq ? cntq : cntp)) {
-            double* dst = A + (size_t)((isq ? colq0 : colp0) + l) * n;
-            const double* src = S + (size_t)lc * n;
-            for (int i = lane; i < n; i += 32) __stcg(dst + i, src[i]);
+    if constexpr (NR > 0) {
+        const bool hp = warp < cntp, hq = warp < cntq;
+        double* gp = A + (size_t)(colp0 + warp) * n;
+        double* gq = A + (size_t)(colq0 + warp) * n;
+        const double* sp = S + (size_t)warp * n;
+        const double* sq = S + (size_t)(b + warp) * n;
+        double vp[NR], vq[NR];
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            vp[t] = (hp && i < n) ? sp[i] : 0.0;
+            vq[t] = (hq && i < n) ? sq[i] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < NR; t++) {
+            const int i = lane + 32 * t;
+            if (i < n) {
+                if (hp) __stcg(gp + i, vp[t]);
+                if (hq) __stcg(gq + i, vq[t]);
+            }
+        }
+    } else {
+        for (int lc = warp; lc < 2 * b; lc += b) {
+            const bool isq = lc >= b;
+            const int l = isq ? lc - b : lc;
+            if (l < (isq ? cntq : cntp)) {
+                double* dst = A + (size_t)((isq ? colq0 : colp0) + l) * n;
+                const double* src = S + (size_t)lc * n;
+                for (int i = lane; i < n; i += 32) __stcg(dst + i, src[i]);
+            }
         }
     }
     return any;
