@@ -909,7 +909,8 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
     // block size: as many columns as shared memory allows, at most 16 warps, tunable
     int b = (int)((smem_cap - 512) / (16 * (size_t)n));
     if (b > 16) b = 16;
-    if (ctx->opt_jacobi_block > 0 && ctx->opt_jacobi_block < b) b = (int)ctx->opt_jacobi_block;
+    if (ctx->opt_jacobi_block > 0) { if (ctx->opt_jacobi_block < b) b = (int)ctx->opt_jacobi_block; }
+    else if (b > 8) b = 8;                                // measured best: more CTAs, cheaper rounds
     NDMPS_REQUIRE(b >= 1, "eigh: n = %d does not fit a column pair in shared memory", n);
     while (b > 1 && (ncols + b - 1) / b < 2) b /= 2;      // at least two blocks
     int nb = (ncols + b - 1) / b;

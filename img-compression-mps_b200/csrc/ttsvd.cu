@@ -213,7 +213,7 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
                  int64_t svals_stride) {
     const size_t esz = dtype_size(dtype);
     // cores stored in float32 need eigenvectors orthogonal to ~1e-8, not 1e-15: one sweep less
-    const double eig_tol = dtype == NDMPS_F32 ? 1e-11 : 0.0;
+    const double eig_tol = dtype == NDMPS_F32 ? 1e-10 : 0.0;
     int64_t total = 1;
     for (int i = 0; i < L; i++) total *= dims[i];
     if (svals_out)
