@@ -189,6 +189,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "jacobi_max_sweeps")) ctx->opt_jacobi_max_sweeps = value;
     else if (!strcmp(name, "eig_cholesky")) ctx->opt_eig_cholesky = value;
     else if (!strcmp(name, "eig_small")) ctx->opt_eig_small = value;
+    else if (!strcmp(name, "chol_blocked")) ctx->opt_chol_blocked = value;
     else if (!strcmp(name, "chol_cluster")) ctx->opt_chol_cluster = value;
     else if (!strcmp(name, "chol_rows")) ctx->opt_chol_rows = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;

@@ -143,6 +143,7 @@ struct ndmps_ctx {
     int64_t opt_permute_ctas = 0;   // persistent CTAs per SM of the tiled kernel (0: 6)
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
+    int64_t opt_chol_blocked = 1;         // 8 pivots per pair of grid barriers
     int64_t opt_chol_cluster = 0;         // pivoted Cholesky inside one thread-block cluster (measured slower: DSMEM row broadcast)
     int64_t opt_chol_rows = 0;            // rows per CTA of the pivoted Cholesky (0: auto)
     int64_t opt_eig_small = 1;            // n <= 128: single-CTA all-in-one solver
