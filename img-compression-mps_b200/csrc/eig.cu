@@ -376,17 +376,44 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, 
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_persistent_kernel(double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                         const double* floor2_ptr) {
+                         const double* floor2_ptr, unsigned* stamps) {
     extern __shared__ double S[];
+    __shared__ int s_skip;
     const double floor2 = *floor2_ptr;
+    // stamps[0..nb): time a block was last modified; stamps[nb + p*nb + q]: time the pair (p, q) was
+    // last found orthogonal.  A pair verified after both blocks' last modification is still
+    // orthogonal and is skipped entirely - the late sweeps, where almost nothing rotates, and the
+    // final verification sweep then cost little more than their barriers.
+    unsigned* mod = stamps;
+    unsigned* okt = stamps + nb;
     unsigned epoch = 0;
     int sweep = 0;
     bool converged = false;
     while (sweep < max_sweeps) {
         for (int round = 0; round < nb - 1; round++) {
-            bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, floor2);
-            if (any && (threadIdx.x & 31) == 0) atomicOr(ctrl + 2 + sweep, 1u);
+            int bp, bq;
+            tournament_pair(nb, round, blockIdx.x, bp, bq);
+            if (bp > bq) { int t = bp; bp = bq; bq = t; }
+            if (threadIdx.x == 0) {
+                const unsigned ok = __ldcg(okt + (size_t)bp * nb + bq);
+                s_skip = ok != 0 && ok >= __ldcg(mod + bp) && ok >= __ldcg(mod + bq);
+            }
+            __syncthreads();
+            const bool skip = s_skip != 0;
             epoch++;
+            if (!skip) {
+                bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, floor2);
+                any = __syncthreads_or(any ? 1 : 0) != 0;
+                if (threadIdx.x == 0) {
+                    if (any) {
+                        atomicOr(ctrl + 2 + sweep, 1u);
+                        __stcg(mod + bp, epoch);
+                        __stcg(mod + bq, epoch);
+                    } else {
+                        __stcg(okt + (size_t)bp * nb + bq, epoch);
+                    }
+                }
+            }
             grid_barrier(ctrl, epoch * gridDim.x);
         }
         unsigned flag = __ldcg(ctrl + 2 + sweep);
@@ -710,7 +737,23 @@ pivoted_cholesky_blocked_kernel(const double* __restrict__ G, int n, int rows_pe
         }
         epoch++;
         grid_barrier(ctrl, epoch * ncta);
-        for (int idx = tid; idx < nsel * n; idx += blockDim.x) rowsB[idx] = __ldcg(rows_g + (size_t)par * CHB * n + idx);
+        {   // all loads in flight before the first store (a load -> store loop serialises L2 round trips)
+            const double* src = rows_g + (size_t)par * CHB * n;
+            const int total = nsel * n;
+            for (int base = 0; base < total; base += 8 * 256) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = base + u * 256 + tid;
+                    v[u] = idx < total ? __ldcg(src + idx) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = base + u * 256 + tid;
+                    if (idx < total) rowsB[idx] = v[u];
+                }
+            }
+        }
         if (tid < CHB) { taken[tid] = 0; dd[tid] = 0.0; }
         __syncthreads();
         // ---- (4) factor the block, pivoting among the candidates ----
@@ -1011,7 +1054,10 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, in
                           double tol2, const double* floor2, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
-    void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2};
+    unsigned* stamps = nullptr;
+    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)nb * nb + nb, &stamps));
+    NDMPS_CUDA_TRY(cudaMemsetAsync(stamps, 0, ((size_t)nb * nb + nb) * sizeof(unsigned), ctx->stream));
+    void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &stamps};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
