@@ -1045,7 +1045,8 @@ static int raise_smem_minus(K kernel, const ndmps_ctx* ctx, int reserve) {
 
 template <class K>
 static int raise_smem(K kernel, const ndmps_ctx* ctx) {
-    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    // leave room for the kernels' few bytes of static shared memory
+    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
     return NDMPS_OK;
 }
 
@@ -1087,7 +1088,7 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
 // Jacobi sweeps over the ncols columns (length n) stored at A + j*n, block path.
 static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double tol2, const double* floor2, int* sweeps_used) {
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
-    const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 1024 : 0;
+    const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0;
     unsigned* ctrl = nullptr;   // [0] barrier counter, [1] sweeps used, [2..] per-sweep rotation flags
     NDMPS_TRY(ctx->ws.get<unsigned>((size_t)max_sweeps + 4, &ctrl));
     NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, ((size_t)max_sweeps + 4) * sizeof(unsigned), ctx->stream));
@@ -1261,7 +1262,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     NDMPS_REQUIRE(n64 >= 1 && n64 <= 16384, "eigh: n = %lld outside 1..16384", (long long)n64);
     const int n = (int)n64;
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
-    const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 1024 : 0;
+    const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0;
     NDMPS_TRY(ensure_pinned(ctx, 64));
     int sweeps_used = 0;
     double* norms = nullptr;
