@@ -85,7 +85,8 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
 // use the full mask); `valid` masks out groups without a pair.  Squared norms are
 // recomputed at every visit: three interleaved butterflies.
 template <int NR, int LP>
-__device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li, bool valid, double tol2, double floor2) {
+__device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li, bool valid, double tol2, double floor2,
+                                             float& relmax) {
     double xr[NR], yr[NR];
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
@@ -108,6 +109,7 @@ __device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li
     // round-off and would keep the sweep from ever reporting convergence
     if (!valid || !(alpha > floor2) || !(beta > floor2)) return false;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    relmax = fmaxf(relmax, (float)(gamma * gamma * rcp_approx(alpha * beta)));
     double c, s, t;
     rotation(alpha, beta, gamma, c, s, t);
 #pragma unroll
@@ -122,7 +124,8 @@ __device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li
 }
 
 // same for columns of any length (n > 512): one pair per warp, two passes over shared memory
-__device__ __forceinline__ bool rotate_generic(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2) {
+__device__ __forceinline__ bool rotate_generic(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2,
+                                               float& relmax) {
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
     if (valid) {
         for (int i = lane; i < n; i += 32) {
@@ -140,6 +143,7 @@ __device__ __forceinline__ bool rotate_generic(double* x, double* y, int n, int 
     }
     if (!valid || !(alpha > floor2) || !(beta > floor2)) return false;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    relmax = fmaxf(relmax, (float)(gamma * gamma * rcp_approx(alpha * beta)));
     double c, s, t;
     rotation(alpha, beta, gamma, c, s, t);
     for (int i = lane; i < n; i += 32) {
@@ -151,9 +155,10 @@ __device__ __forceinline__ bool rotate_generic(double* x, double* y, int n, int 
 }
 
 template <int NR>
-__device__ __forceinline__ bool rotate_warp(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2) {
-    if constexpr (NR > 0) return rotate_group<NR, 32>(x, y, n, lane, valid, tol2, floor2);
-    else return rotate_generic(x, y, n, lane, valid, tol2, floor2);
+__device__ __forceinline__ bool rotate_warp(double* x, double* y, int n, int lane, bool valid, double tol2, double floor2,
+                                            float& relmax) {
+    if constexpr (NR > 0) return rotate_group<NR, 32>(x, y, n, lane, valid, tol2, floor2, relmax);
+    else return rotate_generic(x, y, n, lane, valid, tol2, floor2, relmax);
 }
 
 // The b cross rounds of one block pair with the P column held in REGISTERS: warp w keeps
@@ -164,7 +169,7 @@ __device__ __forceinline__ bool rotate_warp(double* x, double* y, int n, int lan
 // column collapses (catastrophic cancellation) and at every block load.
 template <int NR>
 __device__ __forceinline__ bool cross_rounds_stationary(double* S, double* norm2, int n, int b, int cntp, int cntq,
-                                                        int warp, int lane, double tol2, double floor2) {
+                                                        int warp, int lane, double tol2, double floor2, float& relmax) {
     double xr[NR];
     double* x = S + (size_t)warp * n;
     const bool have_x = warp < cntp;
@@ -191,6 +196,7 @@ __device__ __forceinline__ bool cross_rounds_stationary(double* S, double* norm2
         double gamma = warp_sum((g4[0] + g4[1]) + (g4[2] + g4[3]));
         const double beta = valid ? norm2[b + j] : 0.0;
         if (valid && alpha > floor2 && beta > floor2 && gamma * gamma > tol2 * alpha * beta) {
+            relmax = fmaxf(relmax, (float)(gamma * gamma * rcp_approx(alpha * beta)));
             double c, s, t;
             rotation(alpha, beta, gamma, c, s, t);
             double ra = 0.0, rb = 0.0;
@@ -257,7 +263,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 // L2, rotate, store back.  S: 2*b*n doubles followed by 2*b cached squared norms.
 template <int NR>
 __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, int b, int nb, int round, int cta,
-                                                   double* S, double tol2, double floor2) {
+                                                   double* S, double tol2, double floor2, float& relmax) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* norm2 = S + (size_t)2 * b * n;
     int p, q;
@@ -321,17 +327,17 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, 
             tournament_pair(P, lr, warp, s1, s2);
             const bool v1 = s1 < b ? s1 < cntp : (s1 - b) < cntq;
             const bool v2 = s2 < b ? s2 < cntp : (s2 - b) < cntq;
-            any |= rotate_warp<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, v1 && v2, tol2, floor2);
+            any |= rotate_warp<NR>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, lane, v1 && v2, tol2, floor2, relmax);
             __syncthreads();
         }
     } else if constexpr (NR > 0) {
-        any = cross_rounds_stationary<NR>(S, norm2, n, b, cntp, cntq, warp, lane, tol2, floor2);
+        any = cross_rounds_stationary<NR>(S, norm2, n, b, cntp, cntq, warp, lane, tol2, floor2, relmax);
         __syncthreads();
     } else {
         for (int k = 0; k < b; k++) {
             int j = warp + k;
             j = j >= b ? j - b : j;
-            any |= rotate_warp<0>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, warp < cntp && j < cntq, tol2, floor2);
+            any |= rotate_warp<0>(S + (size_t)warp * n, S + (size_t)(b + j) * n, n, lane, warp < cntp && j < cntq, tol2, floor2, relmax);
             __syncthreads();
         }
     }
@@ -376,7 +382,7 @@ __device__ __forceinline__ bool process_block_pair(double* A, int n, int ncols, 
 template <int NR>
 __global__ void __launch_bounds__(512)
 jacobi_persistent_kernel(double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl, double tol2,
-                         const double* floor2_ptr, unsigned* stamps) {
+                         const double* floor2_ptr, unsigned* stamps, float quad_stop2) {
     extern __shared__ double S[];
     __shared__ int s_skip;
     const double floor2 = *floor2_ptr;
@@ -402,11 +408,13 @@ jacobi_persistent_kernel(double* A, int n, int ncols, int b, int nb, int max_swe
             const bool skip = s_skip != 0;
             epoch++;
             if (!skip) {
-                bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, floor2);
+                float relmax = 0.f;
+                bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, floor2, relmax);
                 any = __syncthreads_or(any ? 1 : 0) != 0;
+                // largest squared relative off-diagonal rotated away in this sweep (positive floats order as uints)
+                if (relmax > 0.f && (threadIdx.x & 31) == 0) atomicMax(ctrl + 2 + sweep, __float_as_uint(relmax));
                 if (threadIdx.x == 0) {
                     if (any) {
-                        atomicOr(ctrl + 2 + sweep, 1u);
                         __stcg(mod + bp, epoch);
                         __stcg(mod + bq, epoch);
                     } else {
@@ -418,7 +426,9 @@ jacobi_persistent_kernel(double* A, int n, int ncols, int b, int nb, int max_swe
         }
         unsigned flag = __ldcg(ctrl + 2 + sweep);
         sweep++;
-        if (flag == 0) { converged = true; break; }
+        // no rotation at all, or every rotated pair was already so close to orthogonal that - Jacobi
+        // converging quadratically - what is left is below the threshold: skip the verification sweep
+        if (flag == 0 || __uint_as_float(flag) < quad_stop2) { converged = true; break; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ((int*)ctrl)[1] = converged ? sweep : -sweep;
 }
@@ -430,7 +440,8 @@ __global__ void __launch_bounds__(512)
 jacobi_round_kernel(double* A, int n, int ncols, int b, int nb, int round, unsigned* flag, double tol2,
                     const double* floor2_ptr) {
     extern __shared__ double S[];
-    bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr);
+    float relmax = 0.f;
+    bool any = process_block_pair<NR>(A, n, ncols, b, nb, round, blockIdx.x, S, tol2, *floor2_ptr, relmax);
     if (any && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
@@ -450,6 +461,7 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
     const int matches = P / 2;
     int sweep = 0;
     int done = n < 2 ? 1 : 0;
+    float relmax = 0.f;
     while (!done && sweep < max_sweeps) {
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
@@ -458,7 +470,7 @@ jacobi_single_kernel(double* A, int n, int max_sweeps, unsigned* ctrl, double to
                 int s1 = 0, s2 = 0;
                 if (m < matches) tournament_pair(P, lr, m, s1, s2);
                 const bool valid = m < matches && s1 < n && s2 < n;
-                any |= rotate_group<NR, 8>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, li, valid, tol2, floor2);
+                any |= rotate_group<NR, 8>(S + (size_t)s1 * n, S + (size_t)s2 * n, n, li, valid, tol2, floor2, relmax);
             }
             __syncthreads();
         }
@@ -990,6 +1002,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     const int matches = P / 2;
     int sweep = 0;
     int done = rank < 2 ? 1 : 0;
+    float relmax = 0.f;
     while (!done && sweep < max_sweeps) {
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
@@ -999,7 +1012,7 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
                 if (m < matches) tournament_pair(P, lr, m, s1, s2);
                 const bool valid = m < matches && s1 < rank && s2 < rank;
                 const int c1 = valid ? piv[s1] : 0, c2 = valid ? piv[s2] : 0;
-                any |= rotate_group<NR, 8>(S + (size_t)c1 * ld, S + (size_t)c2 * ld, n, li, valid, tol2, floor2);
+                any |= rotate_group<NR, 8>(S + (size_t)c1 * ld, S + (size_t)c2 * ld, n, li, valid, tol2, floor2, relmax);
             }
             __syncthreads();
         }
@@ -1052,13 +1065,13 @@ static int raise_smem(K kernel, const ndmps_ctx* ctx) {
 
 template <int NR>
 static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl,
-                          double tol2, const double* floor2, size_t smem) {
+                          double tol2, const double* floor2, size_t smem, float quad_stop2) {
     static bool attr_set = false;
     if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
     unsigned* stamps = nullptr;
     NDMPS_TRY(ctx->ws.get<unsigned>((size_t)nb * nb + nb, &stamps));
     NDMPS_CUDA_TRY(cudaMemsetAsync(stamps, 0, ((size_t)nb * nb + nb) * sizeof(unsigned), ctx->stream));
-    void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &stamps};
+    void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &stamps, &quad_stop2};
     NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -1086,7 +1099,8 @@ static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweep
 }
 
 // Jacobi sweeps over the ncols columns (length n) stored at A + j*n, block path.
-static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double tol2, const double* floor2, int* sweeps_used) {
+static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double tol2, const double* floor2, int* sweeps_used,
+                          float quad_stop2) {
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
     const size_t smem_cap = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0;
     unsigned* ctrl = nullptr;   // [0] barrier counter, [1] sweeps used, [2..] per-sweep rotation flags
@@ -1107,9 +1121,9 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
     const size_t smem = ((size_t)2 * b * n + 2 * b) * sizeof(double);
     if (nb / 2 <= ctx->sm_count) {
         switch (nr) {
-            case 8: NDMPS_TRY(run_persistent<8>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
-            case 16: NDMPS_TRY(run_persistent<16>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
-            default: NDMPS_TRY(run_persistent<0>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem)); break;
+            case 8: NDMPS_TRY(run_persistent<8>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
+            case 16: NDMPS_TRY(run_persistent<16>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
+            default: NDMPS_TRY(run_persistent<0>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
         }
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1339,7 +1353,10 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         }
         sweeps_used = host_flag[0];
     } else if (ncols >= 2) {
-        NDMPS_TRY(jacobi_columns(ctx, cols, n, ncols, tol2, floor2, &sweeps_used));
+        // float32 payloads (loosened tolerance): a sweep whose largest rotated off-diagonal was below
+        // 1e-7 relative leaves less than the tolerance behind (quadratic convergence), so it is the last
+        const float quad_stop2 = tol_override > 0.0 ? 1e-14f : 0.f;
+        NDMPS_TRY(jacobi_columns(ctx, cols, n, ncols, tol2, floor2, &sweeps_used, quad_stop2));
     }
     ctx->last_eig_sweeps = sweeps_used;
     ctx->eig_calls++;
