@@ -208,6 +208,52 @@ struct TrimOpts {
     int renorm;
 };
 
+// Bond cap set and the matrix much larger than the cap: try the leading-eigenpair solver
+// (eig_topk.cu).  It is used only when the host can PROVE from its output that the trimming rule
+// (n_keep above) lands on the cap: the weight outside the k leading eigenvalues, trace(G) minus
+// their sum, must exceed the cutoff target with a margin far above the rounding error of that
+// difference, and lambda_k must be well above the absolute error floor of the tridiagonal
+// reduction (~ n eps lambda_1).  Anything else: *capped = false and the caller runs the full
+// solver, so ranks never depend on which solver ran.  U: mj x mj buffer, eigenvector t in column t.
+static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nmax, const TrimOpts& opt, double* evals_dev,
+                       double* U, std::vector<double>& sv, int64_t* n_out, double* f_out, bool* capped) {
+    *capped = false;
+    const int64_t k = opt.max_bond;
+    if (!ctx->opt_eig_topk || k <= 0 || mj < 4 * k || mj < 192 || nmax <= k) return NDMPS_OK;
+    const bool sum2 = opt.mode == NDMPS_CUT_SUM2 || opt.mode == NDMPS_CUT_RSUM2;
+    if (opt.cutoff > 0.0 && !sum2) return NDMPS_OK;
+    if (opt.renorm != 0 && opt.renorm != 2) return NDMPS_OK;
+    double* out = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)k + 2, &out));
+    bool done = false;
+    { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh_topk(ctx, Gj, mj, k, out, U, mj, &done)); }
+    if (!done) return NDMPS_OK;
+    NDMPS_TRY(ensure_pinned(ctx, (size_t)k + 64));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const double* ev = ctx->pinned;
+    const double trace = ev[k], rank_loss = ev[k + 1];
+    double kept = 0.0;
+    for (int64_t i = 0; i < k; i++) kept += ev[i];
+    const double tail = trace - kept;
+    const double target = opt.cutoff > 0.0 ? opt.cutoff * (opt.mode == NDMPS_CUT_RSUM2 ? trace : 1.0) : 0.0;
+    bool ok = rank_loss == 0.0 && trace > 0.0 && ev[0] > 0.0 && ev[k - 1] > 1e-9 * ev[0];
+    ok = ok && tail > 2.0 * target + 1e-11 * trace;
+    for (int64_t i = 1; ok && i < k; i++) ok = ev[i] <= ev[i - 1];
+    if (ctx->opt_verbose)
+        fprintf(stderr, "[ndmps] capped eigh n = %lld, k = %lld: lambda_k / lambda_1 = %.3e, discarded weight %.3e of trace -> %s\n",
+                (long long)mj, (long long)k, ev[0] > 0.0 ? ev[k - 1] / ev[0] : 0.0, trace > 0.0 ? tail / trace : 0.0,
+                ok ? "cap binds" : "full solver");
+    if (!ok) return NDMPS_OK;
+    sv.assign((size_t)mj, 0.0);
+    for (int64_t i = 0; i < k; i++) sv[(size_t)i] = sqrt(ev[i]);
+    *n_out = k;
+    *f_out = opt.renorm == 2 ? sqrt(trace / kept) : 1.0;
+    (void)evals_dev;
+    *capped = true;
+    return NDMPS_OK;
+}
+
 static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int64_t* dims, const TrimOpts& opt,
                  void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out, double* svals_out,
                  int64_t svals_stride) {
@@ -272,13 +318,19 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
                 double *evals = nullptr, *U = nullptr;
                 NDMPS_TRY(ctx->ws.get<double>((size_t)mj, &evals));
                 NDMPS_TRY(ctx->ws.get<double>((size_t)(mj * mj), &U));
-                { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, Gj, mj, evals, U, eig_tol)); }
-                NDMPS_TRY(fetch_svals(ctx, evals, mj, sv));
                 // rank of this unfolding is at most min(rows, cols)
                 int64_t cols_j = C * rest;
                 int64_t nmax = mj < cols_j ? mj : cols_j;
-                int64_t n = n_keep(sv.data(), nmax, opt.cutoff, opt.mode, opt.max_bond);
-                double f = renorm_factor(sv.data(), nmax, n, opt.renorm);
+                int64_t n = 0;
+                double f = 1.0;
+                bool capped = false;
+                NDMPS_TRY(capped_eigh(ctx, Gj, mj, nmax, opt, evals, U, sv, &n, &f, &capped));
+                if (!capped) {
+                    { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, Gj, mj, evals, U, eig_tol)); }
+                    NDMPS_TRY(fetch_svals(ctx, evals, mj, sv));
+                    n = n_keep(sv.data(), nmax, opt.cutoff, opt.mode, opt.max_bond);
+                    f = renorm_factor(sv.data(), nmax, n, opt.renorm);
+                }
                 const int s_idx = site + j;
                 ranks_out[s_idx] = n;
                 if (svals_out)

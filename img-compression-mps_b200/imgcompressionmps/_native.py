@@ -55,6 +55,7 @@ PROTOTYPES = {
     "ndmps_dct_last_axis": (ci, [vp, vp, vp, i64, i64, ci, ci]),
     "ndmps_gram": (ci, [vp, vp, i64, i64, i64, ci, ci, vp]),
     "ndmps_eigh": (ci, [vp, vp, i64, vp, vp, C.POINTER(ci)]),
+    "ndmps_eigh_topk": (ci, [vp, vp, i64, i64, vp, vp]),
     "ndmps_gemm": (ci, [vp, i64, i64, i64, f64, vp, ci, i64, i64, vp, ci, i64, i64, vp, ci, i64]),
     "ndmps_ttsvd": (ci, [vp, vp, ci, ci, p_i64, f64, ci, i64, ci, p_vp, p_i64, p_i64, p_f64, i64]),
     "ndmps_compress_bond": (ci, [vp, vp, vp, ci, i64, i64, i64, f64, ci, i64, ci, vp, vp, p_i64, p_f64]),

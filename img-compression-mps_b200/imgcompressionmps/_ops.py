@@ -127,6 +127,21 @@ def eigh(a):
     return evals, evecs, sweeps.value
 
 
+def eigh_topk(a, k: int):
+    """Leading k eigenpairs of a symmetric PSD float64 matrix; returns (evals[k] descending, evecs[n, k], trace, health)."""
+    torch = _torch()
+    _dev(a)
+    if a.dtype != torch.float64 or a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("eigh_topk expects a square float64 matrix")
+    n, k = int(a.shape[0]), int(k)
+    a = a.contiguous()
+    out = torch.empty(k + 2, dtype=torch.float64, device=a.device)
+    evecs = torch.empty((n, k), dtype=torch.float64, device=a.device)
+    N.check(N.load_library().ndmps_eigh_topk(N.handle(), N.ptr(a), n, k, N.ptr(out), N.ptr(evecs)), "ndmps_eigh_topk")
+    host = out.cpu()
+    return out[:k], evecs, float(host[k]), int(host[k + 1])
+
+
 def gemm(a, b, out_dtype=None, alpha: float = 1.0):
     """a @ b for 2-D (possibly transposed-view) device tensors through ndmps_gemm."""
     torch = _torch()

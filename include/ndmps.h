@@ -120,6 +120,13 @@ int ndmps_gram(ndmps_ctx_t* ctx, const void* m, int64_t rows, int64_t cols, int6
  * a_dev (n x n) is destroyed.  evals_dev: n values, descending.  evecs_dev:
  * n x n row-major, column j is the j-th eigenvector. */
 int ndmps_eigh(ndmps_ctx_t* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, int* sweeps_out_host);
+/* Leading k eigenpairs of a symmetric positive semi-definite matrix (what a capped bond needs:
+ * quimb's max_bond at core/ndmps.py:74,104-106 keeps the k largest singular triplets and only the
+ * total weight of the rest).  a_dev (n x n) is NOT modified.  evals_dev: k + 2 values = k
+ * eigenvalues descending, trace(a), and a health flag (0 = ok).  evecs_dev: n x k row-major,
+ * column j is the j-th eigenvector.  Supported: 96 <= n <= 1024, 2k <= n, k <= ~100;
+ * other shapes return NDMPS_ERR_INVALID (use ndmps_eigh). */
+int ndmps_eigh_topk(ndmps_ctx_t* ctx, const double* a_dev, int64_t n, int64_t k, double* evals_dev, double* evecs_dev);
 /* C (m x n, ldc) = alpha * A(m x k) * B(k x n) with arbitrary element strides, float64 accumulation. */
 int ndmps_gemm(ndmps_ctx_t* ctx, int64_t m, int64_t n, int64_t k, double alpha,
                const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,

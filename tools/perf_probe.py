@@ -44,6 +44,34 @@ def main(which):
                 except Exception as exc:
                     print(f"eigh n={n} cholesky={chol}: FAILED {exc}", flush=True)
         ctx.set_option("eig_cholesky", 1)
+    if "topk" in which:
+        from bench import synthetic_volume
+        vol = torch.from_numpy(synthetic_volume((128, 128, 128), 7)).cuda().double()
+        cases = []
+        for n in (256, 360, 512, 1024):
+            a = torch.randn(n, 4 * n, dtype=torch.float64, device="cuda", generator=g)
+            cases.append((f"random n={n}", a @ a.T))
+            m = vol.reshape(-1)[: (vol.numel() // n) * n].reshape(n, -1)
+            cases.append((f"volume unfolding n={n}", m @ m.T))
+            w = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g))[0]
+            lam = torch.cat([torch.full((20,), 3.0), torch.full((20,), 3.0 - 1e-13), torch.logspace(0, -6, n - 40)]).double().cuda()
+            cases.append((f"clustered n={n}", (w * lam) @ w.T))
+        for name, gm in cases:
+            n = gm.shape[0]
+            k = 64
+            gm = 0.5 * (gm + gm.T)
+            try:
+                ev, vec, tr, health = _ops.eigh_topk(gm, k)
+                ms = timeit(lambda: _ops.eigh_topk(gm, k), reps=3, warm=1)
+            except Exception as exc:
+                print(f"topk {name}: FAILED {exc}", flush=True)
+                continue
+            ref = torch.linalg.eigvalsh(gm).flip(0)
+            rel = ((ev - ref[:k]).abs() / ref[0]).max().item()
+            orth = (vec.T @ vec - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item()
+            res = ((gm @ vec - vec * ev).norm(dim=0) / ref[0]).max().item()
+            print(f"topk {name}: {ms:.3f} ms  health={health} |dlam|/lam1={rel:.2e} orth={orth:.2e} resid={res:.2e} "
+                  f"trace err={(tr - ref.sum().item()) / ref.sum().item():.1e}", flush=True)
     if "gram" in which:
         for rows, cols in ((8, 1 << 21), (64, 1 << 18), (512, 1 << 15), (512, 1 << 12), (512, 512), (512, 1 << 18)):
             m = torch.randn(rows, cols, dtype=torch.float32, device="cuda", generator=g)
