@@ -193,7 +193,6 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "chol_cluster")) ctx->opt_chol_cluster = value;
     else if (!strcmp(name, "chol_rows")) ctx->opt_chol_rows = value;
     else if (!strcmp(name, "eig_topk")) ctx->opt_eig_topk = value;
-    else if (!strcmp(name, "topk_rows")) ctx->opt_topk_rows = value;
     else if (!strcmp(name, "topk_passes")) ctx->opt_topk_passes = value;
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;

@@ -149,7 +149,6 @@ struct ndmps_ctx {
     int64_t opt_eig_small = 1;            // n <= 128: single-CTA all-in-one solver
     int64_t opt_eig_cholesky = 1;         // pivoted-Cholesky preconditioning of the Jacobi solve
     int64_t opt_eig_topk = 1;             // bond cap set: leading-eigenpair solver (eig_topk.cu) instead of the full one
-    int64_t opt_topk_rows = 0;            // rows per CTA of the tridiagonalisation (0: 8)
     int64_t opt_topk_passes = 0;          // bisection passes (0: 8, each divides the bracket by 129)
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
     int64_t opt_verbose = 0;
@@ -200,6 +199,7 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
 int gram(ndmps_ctx* ctx, const void* m, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev);
 // tol_override > 0 loosens the relative off-diagonal threshold (float32 payloads do not need 1e-15)
 int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, double tol_override = 0.0);
+int eigh_small_async(ndmps_ctx* ctx, double* a_dev, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev);
 // leading k eigenpairs (eig_topk.cu); out_dev: k Ritz values, trace(G), rank-loss count
 int eigh_topk(ndmps_ctx* ctx, const double* g_dev, int64_t n, int64_t k, double* out_dev, double* evecs_dev, int64_t ldu, bool* done);
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);

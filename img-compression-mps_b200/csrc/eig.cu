@@ -930,7 +930,7 @@ pivoted_cholesky_cluster_kernel(const double* __restrict__ G, int n, int rows_pe
 // ---------------------------------------------------------------------------------------------
 template <int NR>
 __global__ void __launch_bounds__(512)
-eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol2, double stop_rel,
+eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol2, double stop_rel, float quad_stop2,
                   double* __restrict__ evals, double* __restrict__ evecs, int* __restrict__ info) {
     extern __shared__ double S[];                    // n columns of stride ld = n + 2 (the pad spreads columns over banks)
     const int ld = n + 2;
@@ -1018,6 +1018,10 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
         }
         sweep++;
         done = !__syncthreads_or(any ? 1 : 0);
+        // quadratic convergence: a sweep whose largest rotated off-diagonal was below sqrt(quad_stop2)
+        // relative leaves less than quad_stop2 behind
+        if (quad_stop2 > 0.f && !__syncthreads_or(relmax >= quad_stop2 ? 1 : 0)) done = 1;
+        relmax = 0.f;
     }
     // ---- eigenvalues (squared column norms), descending order, eigenvectors ----
     for (int c = warp; c < rank; c += W) {
@@ -1272,6 +1276,32 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     return NDMPS_OK;
 }
 
+// Single-CTA solver for 2 <= n <= 64, no host synchronisation: *info_dev points at {sweeps (negative:
+// not converged), rank} on the device.  quad_stop2 > 0: also stop after a sweep whose largest rotated
+// off-diagonal, squared and relative, was below it.
+int eigh_small_async(ndmps_ctx* ctx, double* a_in, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev) {
+    NDMPS_REQUIRE(n >= 2 && n <= 64, "eigh_small_async: n = %d outside 2..64", n);
+    const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
+    const double tol = jacobi_tol(n);
+    const double tol2 = tol * tol;
+    int* info = nullptr;
+    NDMPS_TRY(ctx->ws.get<int>(4, &info));
+    const size_t smem = (size_t)n * (n + 2) * sizeof(double);
+    const double stop_rel = 2.220446049250313e-16;
+#define NDMPS_SMALL(NRV)                                                                                              \
+    do {                                                                                                            \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) { NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192)); attr_set = true; }        \
+        eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, quad_stop2, evals_dev, evecs_dev, info); \
+    } while (0)
+    if (n <= 32) NDMPS_SMALL(4);
+    else NDMPS_SMALL(8);
+#undef NDMPS_SMALL
+    NDMPS_LAUNCH_CHECK(ctx);
+    *info_dev = info;
+    return NDMPS_OK;
+}
+
 int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* evecs_dev, double tol_override) {
     NDMPS_REQUIRE(n64 >= 1 && n64 <= 16384, "eigh: n = %lld outside 1..16384", (long long)n64);
     const int n = (int)n64;
@@ -1289,22 +1319,9 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
     const double tol2 = tol * tol;
 
     if (ctx->opt_eig_small && n >= 2 && n <= 64) {
-        // one launch, no host synchronisation: the result (and a convergence code) stay on the device;
-        // the code is checked at the next point where the host reads the eigenvalues anyway
+        // one launch; the convergence code is read back here because the eigenvalues are needed on the host next
         int* info = nullptr;
-        NDMPS_TRY(ctx->ws.get<int>(4, &info));
-        const size_t smem = (size_t)n * (n + 2) * sizeof(double);
-        double stop_rel = 2.220446049250313e-16;
-#define NDMPS_SMALL(NRV)                                                                                              \
-        do {                                                                                                            \
-            static bool attr_set = false;                                                                               \
-            if (!attr_set) { NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192)); attr_set = true; }        \
-            eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, evals_dev, evecs_dev, info); \
-        } while (0)
-        if (n <= 32) NDMPS_SMALL(4);
-        else NDMPS_SMALL(8);
-#undef NDMPS_SMALL
-        NDMPS_LAUNCH_CHECK(ctx);
+        NDMPS_TRY(eigh_small_async(ctx, a_in, n, evals_dev, evecs_dev, tol_override > 0.0 ? 1e-14f : 0.f, &info));
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

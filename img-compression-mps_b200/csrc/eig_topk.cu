@@ -29,7 +29,7 @@ namespace ndmps {
 namespace topk {
 
 constexpr int TDT = 256;   // threads per CTA of the tridiagonalisation
-constexpr int KM = 4;      // vector elements per thread -> n <= 1024
+constexpr int NMAX = 1024; // largest matrix of this path (32 columns per lane)
 constexpr int BIS = 128;   // shifts per pass and eigenvalue in the bisection
 
 __device__ __forceinline__ double rcp_fast(double x) {      // MUFU seed + 2 Newton steps, normal range
@@ -40,14 +40,26 @@ __device__ __forceinline__ double rcp_fast(double x) {      // MUFU seed + 2 New
     return r;
 }
 
+__device__ __forceinline__ double rsqrt_fast(double x) {    // MUFU seed + 2 Newton steps, normal range
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+
+// arrive: fence + relaxed add; wait: acquire loads.  Everything read after it goes through L2 (ld.cg).
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        while (*((volatile unsigned*)counter) < target) {
-        }
-        __threadfence();
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
     }
     __syncthreads();
 }
@@ -63,38 +75,48 @@ __device__ __forceinline__ double block_sum_all(double v, double* scratch) {
     return s;
 }
 
+#ifdef NDMPS_TOPK_PROF
+__device__ unsigned long long g_prof[8];
+#define PROF_MARK(i) do { if (tid == 224 && cta == 0) { long long now = clock64(); g_prof[i] += (unsigned long long)(now - t_last); t_last = now; } } while (0)
+#else
+#define PROF_MARK(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
-// 1. Householder tridiagonalisation.  Rows are dealt cyclically to the CTAs (row i lives in CTA
-// i mod C, shared memory, full rows: the symmetric half is not exploited, the 2x flops are
-// free next to the barrier).  Per column jn every CTA redundantly derives, from the partial
+// 1. Householder tridiagonalisation.  Rows are dealt cyclically to the warps of the grid (row i
+// lives in warp i / C of CTA i mod C, in REGISTERS, full rows: the symmetric half is not
+// exploited, the 2x flops are free next to the barrier).  Per column jn every CTA redundantly derives, from the partial
 // products p = A u and the pivot row that were published before the barrier, the vector w of
 // the rank-2 update of the PREVIOUS reflector and the NEXT reflector u'; then one fused pass
 // over its rows applies A -= u w^T + w u^T and accumulates p' = A u', publishes p' and the next
 // pivot row, and meets the others at the barrier.  One barrier per column.
 // V row j = reflector j (unit at j+1, zero before), H_j = I - tau_j v_j v_j^T.
 // ---------------------------------------------------------------------------------------------
+template <int NEQ>
 __global__ void __launch_bounds__(TDT)
-tridiag_kernel(const double* __restrict__ G, int n, int nr, double* __restrict__ V, double* __restrict__ tau_g,
+tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
                double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
-    extern __shared__ double sm[];
-    double* A = sm;                                      // nr x n
-    double* ub0 = A + (size_t)nr * n;                    // n
-    double* ub1 = ub0 + n;                               // n
-    double* wv = ub1 + n;                                // n
+    __shared__ double ub0[32 * NEQ], ub1[32 * NEQ], wv[32 * NEQ];
     __shared__ double red0[TDT / 32], red1[TDT / 32];
     __shared__ double s_alpha;
+    constexpr int KM = (32 * NEQ) / TDT;                 // vector elements per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
-    for (int rl = 0; rl < nr; rl++) {
-        const int gi = rl * C + cta;
-        if (gi >= n) break;
-        for (int c = tid; c < n; c += TDT) A[(size_t)rl * n + c] = G[(size_t)gi * n + c];
+    const int gi = warp * C + cta;                       // this warp's row, held in registers: lane l has columns l + 32 q
+    double a[NEQ];
+#pragma unroll
+    for (int q = 0; q < NEQ; q++) {
+        const int k = lane + 32 * q;
+        a[q] = (gi < n && k < n) ? G[(size_t)gi * n + k] : 0.0;
     }
-    for (int c = tid; c < n; c += TDT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
+    for (int c = tid; c < 32 * NEQ; c += TDT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
     double* u = ub0;
     double* un = ub1;
     double tau = 0.0;
     unsigned epoch = 0;
     __syncthreads();
+#ifdef NDMPS_TOPK_PROF
+    long long t_last = clock64();
+#endif
     for (int jn = 0; jn <= n - 2; jn++) {
         const int par = jn & 1;
         double r[KM];                                    // row jn of the current matrix, columns >= jn
@@ -118,11 +140,10 @@ tridiag_kernel(const double* __restrict__ G, int n, int nr, double* __restrict__
             const double pj = __ldcg(pb + jn);
             double part = 0.0;
 #pragma unroll
-            for (int m = 0; m < KM; m++) {
-                const int k = tid + m * TDT;
-                if (k < n) part = fma(pf[m], u[k], part);
-            }
+            for (int m = 0; m < KM; m++) part = fma(pf[m], u[tid + m * TDT], part);
+            PROF_MARK(0);
             const double s = block_sum_all(part, red0);
+            PROF_MARK(1);
             const double K = -0.5 * tau * tau * s;
             const double wj = fma(tau, pj, K);           // u[jn] = 1
 #pragma unroll
@@ -146,10 +167,10 @@ tridiag_kernel(const double* __restrict__ G, int n, int nr, double* __restrict__
         if (jn == n - 2) {                               // last 2 x 2 block: no reflector left
             __syncthreads();
             if (cta == 0 && tid == 0) { e_g[jn] = s_alpha; tau_g[jn] = 0.0; }
-            if ((n - 1) % C == cta && tid == 0) {
-                double v = A[(size_t)((n - 1) / C) * n + (n - 1)];
-                if (jn > 0) v -= 2.0 * u[n - 1] * wv[n - 1];
-                d_g[n - 1] = v;
+            if (gi == n - 1) {
+#pragma unroll
+                for (int q = 0; q < NEQ; q++)
+                    if (lane + 32 * q == n - 1) d_g[n - 1] = a[q] - (jn > 0 ? 2.0 * u[n - 1] * wv[n - 1] : 0.0);
             }
             break;
         }
@@ -159,62 +180,54 @@ tridiag_kernel(const double* __restrict__ G, int n, int nr, double* __restrict__
             const int k = tid + m * TDT;
             if (k >= jn + 2 && k < n) part = fma(r[m], r[m], part);
         }
+        PROF_MARK(2);
         const double sigma = block_sum_all(part, red1);  // the barrier inside also publishes s_alpha and wv
+        PROF_MARK(3);
         const double alpha = s_alpha;
         double beta = alpha, taun = 0.0, scal = 0.0;
         if (sigma > 1e-280) {
-            const double nrm = sqrt(fma(alpha, alpha, sigma));
-            beta = -copysign(nrm, alpha);
-            taun = (beta - alpha) / beta;
-            scal = 1.0 / (alpha - beta);
+            const double h2 = fma(alpha, alpha, sigma);
+            beta = -copysign(h2 * rsqrt_fast(h2), alpha);
+            taun = (beta - alpha) * rcp_fast(beta);
+            scal = rcp_fast(alpha - beta);
         }
 #pragma unroll
         for (int m = 0; m < KM; m++) {
             const int k = tid + m * TDT;
-            if (k < n) {
-                const double v = k == jn + 1 ? 1.0 : (k >= jn + 2 ? r[m] * scal : 0.0);
-                un[k] = v;
-                if (cta == jn % C) V[(size_t)jn * n + k] = v;
-            }
+            const double v = k == jn + 1 ? 1.0 : ((k >= jn + 2 && k < n) ? r[m] * scal : 0.0);
+            un[k] = v;
+            if (cta == jn % C && k < n) V[(size_t)jn * ldv + k] = v;
         }
         if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
         __syncthreads();
-        // fused rank-2 update (reflector jn-1) + product with reflector jn, rows and columns >= jn+1
-        double* pw = pbuf + (size_t)par * n;
-        double* rw = rowbuf + (size_t)par * n;
-        const int kbase = (jn + 1) & ~31;
-        for (int rl = warp; rl < nr; rl += TDT / 32) {
-            const int gi = rl * C + cta;
-            if (gi >= n || gi < jn + 1) continue;
-            double* Ar = A + (size_t)rl * n;
+        PROF_MARK(4);
+        // fused rank-2 update (reflector jn-1) + product with reflector jn, this warp's row, columns >= jn+1
+        if (gi >= jn + 1 && gi < n) {
+            double* pw = pbuf + (size_t)par * n;
+            double* rw = rowbuf + (size_t)par * n;
             const bool pub = gi == jn + 1;
-            double acc = 0.0;
-            if (jn > 0) {
-                const double ui = u[gi], wi = wv[gi];
-                for (int k = kbase + lane; k < n; k += 32) {
-                    if (k >= jn + 1) {
-                        double a = Ar[k];
-                        a = fma(-ui, wv[k], a);
-                        a = fma(-wi, u[k], a);
-                        Ar[k] = a;
-                        acc = fma(a, un[k], acc);
-                        if (pub) __stcg(rw + k, a);
-                    }
-                }
-            } else {
-                for (int k = kbase + lane; k < n; k += 32) {
-                    if (k >= jn + 1) {
-                        const double a = Ar[k];
-                        acc = fma(a, un[k], acc);
-                        if (pub) __stcg(rw + k, a);
-                    }
+            const double ui = u[gi], wi = wv[gi];        // zero while jn == 0
+            const int q0 = (jn + 1) >> 5;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NEQ; q++) {
+                const int k = lane + 32 * q;
+                if (q >= q0 && k >= jn + 1 && k < n) {
+                    double v = a[q];
+                    v = fma(-ui, wv[k], v);
+                    v = fma(-wi, u[k], v);
+                    a[q] = v;
+                    if (q & 1) acc1 = fma(v, un[k], acc1); else acc0 = fma(v, un[k], acc0);
+                    if (pub) __stcg(rw + k, v);
                 }
             }
-            acc = warp_sum(acc);
-            if (lane == 0) __stcg(pw + gi, acc);
+            const double p = warp_sum(acc0 + acc1);
+            if (lane == 0) __stcg(pw + gi, p);
         }
+        PROF_MARK(5);
         epoch++;
         grid_barrier(ctrl, epoch * C);
+        PROF_MARK(6);
         double* t = u; u = un; un = t;
         tau = taun;
     }
@@ -223,50 +236,66 @@ tridiag_kernel(const double* __restrict__ G, int n, int nr, double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // 2. Bisection: CTA t finds the t-th largest eigenvalue of T.  Every pass evaluates the Sturm
 // count at 128 interior points of the bracket (one per thread), so a pass divides the bracket
-// by 129.  bounds[0] = max |Gershgorin bound| (scale of T) for the later kernels.
+// by 129.  The count is the number of sign changes of the leading principal minors
+// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}: one dependent FMA per row instead of the
+// reciprocal of the usual pivot recurrence.  T is scaled to unit size and the pair (p_i, p_{i-1})
+// is renormalised by a power of two every four rows, so nothing overflows or dies out.
+// bounds[0] = max |Gershgorin bound| (scale of T) for the later kernels.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BIS)
 bisect_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int n, int passes, double* __restrict__ lam,
               double* __restrict__ bounds) {
     extern __shared__ double sm[];
-    double* d = sm;            // n
-    double* e2 = sm + n;       // n (e2[n-1] = 0)
+    double* d = sm;            // n, scaled
+    double* e2 = sm + n;       // n, scaled (e2[n-1] = 0)
     __shared__ double scratch[32];
-    __shared__ double s_lo, s_hi, s_e2max;
+    __shared__ double s_lo, s_hi;
     const int tid = threadIdx.x;
-    double gl = INFINITY, gu = -INFINITY, em = 0.0;
+    double gl = INFINITY, gu = -INFINITY;
     for (int i = tid; i < n; i += BIS) {
         const double di = d_g[i];
         const double el = i > 0 ? fabs(e_g[i - 1]) : 0.0, er = i < n - 1 ? fabs(e_g[i]) : 0.0;
-        d[i] = di;
-        e2[i] = er * er;
         gl = fmin(gl, di - el - er);
         gu = fmax(gu, di + el + er);
-        em = fmax(em, er * er);
     }
     gl = block_min(gl, scratch);
     if (tid == 0) s_lo = gl;
     gu = block_max(gu, scratch);
     if (tid == 0) s_hi = gu;
-    em = block_max(em, scratch);
-    if (tid == 0) s_e2max = em;
     __syncthreads();
-    const double scale = fmax(fabs(s_lo), fabs(s_hi));
-    const double pad = 2.220446049250313e-16 * n * scale + 1e-300;
-    double lo = s_lo - pad, hi = s_hi + pad;
-    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, s_e2max) * 4.0;
+    const double scale = fmax(fmax(fabs(s_lo), fabs(s_hi)), 1e-300);
+    const double inv_scale = 1.0 / scale;
+    for (int i = tid; i < n; i += BIS) {
+        d[i] = d_g[i] * inv_scale;
+        const double er = i < n - 1 ? e_g[i] * inv_scale : 0.0;
+        e2[i] = er * er;
+    }
+    __syncthreads();
+    const double pad = 2.220446049250313e-16 * n;
+    double lo = s_lo * inv_scale - pad, hi = s_hi * inv_scale + pad;
     const int idx = n - 1 - (int)blockIdx.x;             // ascending index of the wanted eigenvalue
     for (int pass = 0; pass < passes; pass++) {
         const double step = (hi - lo) * (1.0 / (BIS + 1));
         const double x = fma(step, (double)(tid + 1), lo);
-        int cnt = 0;
-        double q = d[0] - x;
-        if (fabs(q) < pivmin) q = -pivmin;
-        cnt += q < 0.0;
+        double pp = 1.0, pc = d[0] - x;
+        bool neg = pc < 0.0 || pc == 0.0;                // an exact zero counts as a change (pivot -> -0)
+        int cnt = neg ? 1 : 0;
         for (int i = 1; i < n; i++) {
-            q = (d[i] - x) - e2[i - 1] * rcp_fast(q);
-            if (fabs(q) < pivmin) q = -pivmin;
-            cnt += q < 0.0;
+            const double pn = fma(d[i] - x, pc, -e2[i - 1] * pp);
+            const bool nneg = pn < 0.0 ? true : (pn > 0.0 ? false : !neg);
+            cnt += nneg != neg;
+            neg = nneg;
+            pp = pc;
+            pc = pn;
+            if ((i & 3) == 3) {
+                const double mx = fmax(fabs(pp), fabs(pc));
+                const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+                if (ex > 0 && ex < 2046) {
+                    const double f = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex)
+                    pp *= f;
+                    pc *= f;
+                }
+            }
         }
         const int L = __syncthreads_count(cnt <= idx);   // points still at or below the eigenvalue
         const double nlo = L > 0 ? fma(step, (double)L, lo) : lo;
@@ -275,7 +304,7 @@ bisect_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, in
         hi = nhi;
     }
     if (tid == 0) {
-        lam[blockIdx.x] = 0.5 * (lo + hi);
+        lam[blockIdx.x] = 0.5 * (lo + hi) * scale;
         if (blockIdx.x == 0) bounds[0] = scale;
     }
 }
@@ -294,7 +323,8 @@ __device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
 
 __global__ void __launch_bounds__(32)
 invit_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int n, const double* __restrict__ lam,
-             const double* __restrict__ bounds, const double* __restrict__ Bt, double* __restrict__ Xt) {
+             const double* __restrict__ bounds, const double* __restrict__ Bt, double* __restrict__ Xt,
+             double* __restrict__ factors, int reuse) {
     extern __shared__ double sm[];
     double* dd = sm;               // d - mu, later the reciprocal pivots
     double* ee = dd + n;           // off-diagonal
@@ -306,13 +336,20 @@ invit_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int
     const int lane = threadIdx.x, t = blockIdx.x;
     const double mu = lam[t];
     const double tiny = fmax(bounds[0] * 2.220446049250313e-16, 1e-290);
+    // factors of shift t: L, reciprocal pivots, U1, U2 (n doubles each) then n pivot bytes (padded to 8)
+    double* fac = factors + (size_t)t * (4 * (size_t)n + ((size_t)n + 7) / 8);
     for (int i = lane; i < n; i += 32) {
-        dd[i] = d_g[i] - mu;
-        ee[i] = i < n - 1 ? e_g[i] : 0.0;
+        if (reuse) {
+            L[i] = fac[i]; dd[i] = fac[n + i]; U1[i] = fac[2 * (size_t)n + i]; U2[i] = fac[3 * (size_t)n + i];
+            piv[i] = reinterpret_cast<const unsigned char*>(fac + 4 * (size_t)n)[i];
+        } else {
+            dd[i] = d_g[i] - mu;
+            ee[i] = i < n - 1 ? e_g[i] : 0.0;
+        }
         x[i] = Bt ? Bt[(size_t)t * n + i] : hash_unit((unsigned)t, (unsigned)i);
     }
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && !reuse) {
         double dcur = dd[0], ucur = ee[0];
         for (int i = 0; i < n - 1; i++) {
             const double sub = ee[i], dnext = dd[i + 1], unext = ee[i + 1];   // ee[n-1] = 0
@@ -331,6 +368,16 @@ invit_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int
         }
         if (fabs(dcur) < tiny) dcur = dcur < 0.0 ? -tiny : tiny;
         dd[n - 1] = rcp_fast(dcur);
+        L[n - 1] = 0.0; U1[n - 1] = 0.0; U2[n - 1] = 0.0; piv[n - 1] = 0;
+    }
+    __syncwarp();
+    if (!reuse) {
+        for (int i = lane; i < n; i += 32) {
+            fac[i] = L[i]; fac[n + i] = dd[i]; fac[2 * (size_t)n + i] = U1[i]; fac[3 * (size_t)n + i] = U2[i];
+            reinterpret_cast<unsigned char*>(fac + 4 * (size_t)n)[i] = piv[i];
+        }
+    }
+    if (lane == 0) {
         // forward substitution with the interchanges
         double cur = x[0];
         for (int i = 0; i < n - 1; i++) {
@@ -403,53 +450,79 @@ combine_rows_kernel(const double* __restrict__ Cf, int64_t crs, int64_t ccs, con
         if (c0 + cc < m) out[(size_t)(c0 + cc) * n + i] = acc[cc];
 }
 
-// S = L L^T (m <= 128, one CTA), Linv = L^-1 (lower triangular, row-major).  A pivot that drops
-// below m eps of its original diagonal means the block lost rank numerically: counted in
-// info[0] (the caller falls back to the full solver) and regularised so the kernel terminates.
-__global__ void __launch_bounds__(256)
+// S = L L^T (m <= 128, one CTA), Linv = L^-1 (lower triangular, row-major).  Left-looking by
+// columns: thread r owns row r; column j needs one barrier (the pivot and the dot products of
+// all rows with row j read only finished columns).  A pivot that drops below m eps of its
+// original diagonal means the block lost rank numerically: counted in info[0] (the caller falls
+// back to the full solver) and regularised so the kernel terminates.  The inverse is then one
+// forward substitution per column, four accumulators deep.
+__global__ void __launch_bounds__(128)
 chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Linv, int* __restrict__ info) {
     extern __shared__ double sm[];
-    double* Lm = sm;                 // m x (m + 1)
-    double* Y = sm + (size_t)m * (m + 1);   // m x (m + 1)
+    double* Lm = sm;                         // m x (m + 1), lower triangle = L
+    double* Y = sm + (size_t)m * (m + 1);    // m x (m + 1)
     __shared__ int s_bad;
     const int tid = threadIdx.x, ld = m + 1;
     if (tid == 0) s_bad = 0;
-    for (int e = tid; e < m * m; e += 256) {
+    for (int e = tid; e < m * m; e += 128) {
         const int r = e / m, c = e - r * m;
         Lm[r * ld + c] = 0.5 * (S[(size_t)r * m + c] + S[(size_t)c * m + r]);
     }
     __syncthreads();
+    const int r = tid;
     for (int j = 0; j < m; j++) {
-        double piv = Lm[j * ld + j];
+        // v = S[r][j] - sum_{q<j} L[r][q] L[j][q]   (row j's finished part is broadcast-read)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (r >= j && r < m) {
+            const double* lr = Lm + r * ld;
+            const double* lj = Lm + j * ld;
+            int q = 0;
+#pragma unroll 4
+            for (; q + 3 < j; q += 4) {
+                v0 = fma(lr[q], lj[q], v0);
+                v1 = fma(lr[q + 1], lj[q + 1], v1);
+                v2 = fma(lr[q + 2], lj[q + 2], v2);
+                v3 = fma(lr[q + 3], lj[q + 3], v3);
+            }
+            for (; q < j; q++) v0 = fma(lr[q], lj[q], v0);
+        }
+        const double mine = (r >= j && r < m) ? Lm[r * ld + j] - ((v0 + v1) + (v2 + v3)) : 0.0;
+        if (r == j) Y[0] = mine;                          // pivot candidate
+        __syncthreads();
+        double piv = Y[0];
         const double floor_j = 2.220446049250313e-16 * m * fabs(S[(size_t)j * m + j]);
         if (!(piv > floor_j)) {
             if (tid == 0) s_bad++;
             piv = floor_j > 0.0 ? floor_j : 1e-300;
         }
-        const double root = sqrt(piv), inv = 1.0 / root;
-        __syncthreads();
-        for (int r = j + tid; r < m; r += 256) Lm[r * ld + j] = r == j ? root : Lm[r * ld + j] * inv;
-        __syncthreads();
-        const int rem = m - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int r = j + 1 + e / rem, c = j + 1 + e % rem;
-            if (c <= r) Lm[r * ld + c] = fma(-Lm[r * ld + j], Lm[c * ld + j], Lm[r * ld + c]);
-        }
+        const double inv_root = rsqrt_fast(piv);
+        if (r == j) Lm[r * ld + j] = piv * inv_root;
+        else if (r > j && r < m) Lm[r * ld + j] = mine * inv_root;
         __syncthreads();
     }
     // column c of Y = L^-1 e_c by forward substitution, one thread per column
-    for (int c = tid; c < m; c += 256) {
-        for (int r = 0; r < m; r++) {
-            double v = r == c ? 1.0 : 0.0;
-            if (r < c) { Y[r * ld + c] = 0.0; continue; }
-            for (int q = c; q < r; q++) v = fma(-Lm[r * ld + q], Y[q * ld + c], v);
-            Y[r * ld + c] = v / Lm[r * ld + r];
+    if (tid < m) {
+        const int c = tid;
+        for (int rr = 0; rr < m; rr++) {
+            if (rr < c) { Y[rr * ld + c] = 0.0; continue; }
+            double a0 = rr == c ? 1.0 : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* lr = Lm + rr * ld;
+            int q = c;
+#pragma unroll 4
+            for (; q + 3 < rr; q += 4) {
+                a0 = fma(-lr[q], Y[q * ld + c], a0);
+                a1 = fma(-lr[q + 1], Y[(q + 1) * ld + c], a1);
+                a2 = fma(-lr[q + 2], Y[(q + 2) * ld + c], a2);
+                a3 = fma(-lr[q + 3], Y[(q + 3) * ld + c], a3);
+            }
+            for (; q < rr; q++) a0 = fma(-lr[q], Y[q * ld + c], a0);
+            Y[rr * ld + c] = ((a0 + a1) + (a2 + a3)) * rcp_fast(lr[rr]);
         }
     }
     __syncthreads();
-    for (int e = tid; e < m * m; e += 256) {
-        const int r = e / m, c = e - r * m;
-        Linv[e] = Y[r * ld + c];
+    for (int e = tid; e < m * m; e += 128) {
+        const int rr = e / m, c = e - rr * m;
+        Linv[e] = Y[rr * ld + c];
     }
     if (tid == 0) atomicAdd(info, s_bad);
 }
@@ -480,12 +553,15 @@ __global__ void __launch_bounds__(256) symmetrise_kernel(double* H, int m) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 5. Back-transformation: one warp per Ritz vector, z <- H_0 H_1 ... H_{n-3} z with the
-// reflector rows streamed from L2 one step ahead of their use.  U[i * ldu + t] = z_i.
+// 5. Back-transformation: one warp per Ritz vector (four per CTA, sharing the reflector rows
+// through L1), z <- H_0 H_1 ... H_{n-3} z.  The next reflector is loaded into registers while the
+// current one is applied; 32-column chunks that lie entirely in the zero part of a reflector
+// are skipped.  U[i * ldu + t] = z_i.
+// (Staging the rows through a shared-memory cp.async ring was measured slower.)
 // ---------------------------------------------------------------------------------------------
 template <int NE>
 __global__ void __launch_bounds__(128)
-backtransform_kernel(const double* __restrict__ V, const double* __restrict__ tau_g, int n, const double* __restrict__ Zt,
+backtransform_kernel(const double* __restrict__ V, int ldv, const double* __restrict__ tau_g, int n, const double* __restrict__ Zt,
                      int m, double* __restrict__ U, int64_t ldu) {
     const int lane = threadIdx.x & 31, t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= m) return;
@@ -496,29 +572,36 @@ backtransform_kernel(const double* __restrict__ V, const double* __restrict__ ta
         z[q] = k < n ? Zt[(size_t)t * n + k] : 0.0;
     }
     auto load = [&](double* dst, int j) {
-        const double* v = V + (size_t)j * n;
+        const double* v = V + (size_t)j * ldv;
+        const int q0 = (j + 1) >> 5;
 #pragma unroll
         for (int q = 0; q < NE; q++) {
             const int k = lane + 32 * q;
-            dst[q] = (k > j && k < n) ? __ldg(v + k) : 0.0;
+            dst[q] = (q >= q0 && k > j && k < n) ? __ldg(v + k) : 0.0;
         }
     };
-    auto apply = [&](const double* v, double tau) {
-        double dot = 0.0;
+    auto apply = [&](const double* v, int j) {
+        const double tau = __ldg(tau_g + j);
+        const int q0 = (j + 1) >> 5;
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < NE; q++) dot = fma(v[q], z[q], dot);
-        dot = warp_sum(dot) * tau;
+        for (int q = 0; q < NE; q += 2) {
+            if (q >= q0) d0 = fma(v[q], z[q], d0);
+            if (q + 1 >= q0) d1 = fma(v[q + 1], z[q + 1], d1);
+        }
+        const double dot = warp_sum(d0 + d1) * tau;
 #pragma unroll
-        for (int q = 0; q < NE; q++) z[q] = fma(-dot, v[q], z[q]);
+        for (int q = 0; q < NE; q++)
+            if (q >= q0) z[q] = fma(-dot, v[q], z[q]);
     };
     int j = n - 3;
     if (j >= 0) load(va, j);
     while (j >= 0) {
         if (j >= 1) load(vb, j - 1);
-        apply(va, tau_g[j]);
+        apply(va, j);
         if (j >= 1) {
             if (j >= 2) load(va, j - 2);
-            apply(vb, tau_g[j - 1]);
+            apply(vb, j - 1);
         }
         j -= 2;
     }
@@ -533,19 +616,19 @@ backtransform_kernel(const double* __restrict__ V, const double* __restrict__ ta
 // Cholesky-QR steps (0 when healthy)
 __global__ void __launch_bounds__(256)
 finish_kernel(const double* __restrict__ G, int n, const double* __restrict__ hev, int k, const int* __restrict__ info,
-              double* __restrict__ out) {
+              const int* __restrict__ rr_info, double* __restrict__ out) {
     __shared__ double scratch[32];
     double tr = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) tr += G[(size_t)i * n + i];
     tr = block_sum(tr, scratch);
     for (int i = threadIdx.x; i < k; i += 256) out[i] = hev[i];
-    if (threadIdx.x == 0) { out[k] = tr; out[k + 1] = (double)info[0]; }
+    if (threadIdx.x == 0) { out[k] = tr; out[k + 1] = (double)info[0] + ((rr_info && rr_info[0] < 0) ? 1e6 : 0.0); }
 }
 
 static int orthonormalise(ndmps_ctx* ctx, const double* Xin, int m, int n, double* S, double* Linv, int* info, double* Xout) {
     rows_dot_kernel<<<m, 256, (size_t)n * sizeof(double), ctx->stream>>>(Xin, Xin, m, n, S);
     NDMPS_LAUNCH_CHECK(ctx);
-    chol_inverse_kernel<<<1, 256, (size_t)2 * m * (m + 1) * sizeof(double), ctx->stream>>>(S, m, Linv, info);
+    chol_inverse_kernel<<<1, 128, (size_t)2 * m * (m + 1) * sizeof(double), ctx->stream>>>(S, m, Linv, info);
     NDMPS_LAUNCH_CHECK(ctx);
     combine_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8)), 128, 0, ctx->stream>>>(Linv, m, 1, Xin, m, n, Xout);
     NDMPS_LAUNCH_CHECK(ctx);
@@ -561,24 +644,14 @@ static int orthonormalise(ndmps_ctx* ctx, const double* Xin, int m, int n, doubl
 int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double* out_dev, double* U, int64_t ldu, bool* done) {
     using namespace topk;
     *done = false;
-    if (n64 < 96 || n64 > TDT * KM || k64 < 1 || k64 > 128 || 2 * k64 > n64) return NDMPS_OK;
+    if (n64 < 96 || n64 > NMAX || k64 < 1 || k64 > 128 || 2 * k64 > n64) return NDMPS_OK;
     const int n = (int)n64, m = (int)k64;
-    int C = (n + 7) / 8;                                 // 8 rows per CTA: one warp per row
-    const int cmax = ctx->sm_count < 128 ? ctx->sm_count : 128;
-    if (ctx->opt_topk_rows > 0) C = (int)((n + ctx->opt_topk_rows - 1) / ctx->opt_topk_rows);
-    if (C > cmax) C = cmax;
-    if (C < 1) C = 1;
-    int nr = (n + C - 1) / C;
-    const size_t smem_td = ((size_t)nr * n + 3 * (size_t)n) * sizeof(double);
+    const int C = (n + TDT / 32 - 1) / (TDT / 32);       // one row per warp
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
-    if (smem_td + 2048 > ctx->smem_optin || smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
+    if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
     {
-        static size_t td_set = 0, iv_set = 0, ch_set = 0;
-        if (smem_td > td_set) {
-            NDMPS_CUDA_TRY(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_td));
-            td_set = smem_td;
-        }
+        static size_t iv_set = 0, ch_set = 0;
         if (smem_iv > iv_set) {
             NDMPS_CUDA_TRY(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_iv));
             iv_set = smem_iv;
@@ -588,10 +661,11 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
             ch_set = smem_ch;
         }
     }
-    double *V, *tau, *d, *e, *pbuf, *rowbuf, *lam, *bounds, *Xa, *Xb, *S, *Linv, *TQ, *H, *hev, *W;
+    double *V, *tau, *d, *e, *pbuf, *rowbuf, *lam, *bounds, *Xa, *Xb, *S, *Linv, *TQ, *H, *hev, *W, *factors;
     unsigned* ctrl;
     int* info;
-    NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &V));
+    const int ldv = (n + 1) & ~1;                        // even: 16-byte row starts for the cp.async ring
+    NDMPS_TRY(ctx->ws.get<double>((size_t)n * ldv, &V));
     NDMPS_TRY(ctx->ws.get<double>((size_t)n, &tau));
     NDMPS_TRY(ctx->ws.get<double>((size_t)n, &d));
     NDMPS_TRY(ctx->ws.get<double>((size_t)n, &e));
@@ -607,26 +681,40 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &H));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m, &hev));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &W));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)m * (4 * (size_t)n + ((size_t)n + 7) / 8), &factors));
     NDMPS_TRY(ctx->ws.get<unsigned>(8, &ctrl));
     info = reinterpret_cast<int*>(ctrl + 4);
     NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned), ctx->stream));
 
     // 1. tridiagonalise
     {
-        int n_arg = n, nr_arg = nr;
-        void* args[] = {(void*)&G, &n_arg, &nr_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
-        NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(C), dim3(TDT), args, smem_td, ctx->stream));
+        int n_arg = n, ldv_arg = ldv;
+        void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
+        void* fn = n <= 256 ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
+        NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(C), dim3(TDT), args, 0, ctx->stream));
         ctx->launches++;
+#ifdef NDMPS_TOPK_PROF
+        {
+            unsigned long long h[8];
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+            fprintf(stderr, "[prof] n=%d cycles: load+dot %llu, sum_s %llu, w,r %llu, sum_sigma %llu, householder+sync %llu, fused %llu, barrier %llu\n",
+                    n, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+            unsigned long long z[8] = {0};
+            cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+        }
+#endif
     }
     // 2. shifts
     const int passes = ctx->opt_topk_passes > 0 ? (int)ctx->opt_topk_passes : 8;
     bisect_kernel<<<m, BIS, (size_t)2 * n * sizeof(double), ctx->stream>>>(d, e, n, passes, lam, bounds);
     NDMPS_LAUNCH_CHECK(ctx);
-    // 3. inverse iteration, re-orthonormalised between steps; the last basis is orthonormalised twice
+    // 3. inverse iteration (the LU factors of step 1 are reused), re-orthonormalised between steps;
+    //    the last basis is orthonormalised twice
     const int iters = ctx->opt_topk_iters > 0 ? (int)ctx->opt_topk_iters : 3;
     const double* rhs = nullptr;
     for (int it = 0; it < iters; it++) {
-        invit_kernel<<<m, 32, smem_iv, ctx->stream>>>(d, e, n, lam, bounds, rhs, Xa);
+        invit_kernel<<<m, 32, smem_iv, ctx->stream>>>(d, e, n, lam, bounds, rhs, Xa, factors, it > 0 ? 1 : 0);
         NDMPS_LAUNCH_CHECK(ctx);
         NDMPS_TRY(orthonormalise(ctx, Xa, m, n, S, Linv, info, Xb));
         rhs = Xb;
@@ -639,17 +727,19 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_LAUNCH_CHECK(ctx);
     symmetrise_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(H, m);
     NDMPS_LAUNCH_CHECK(ctx);
-    NDMPS_TRY(eigh(ctx, H, m, hev, W, 0.0));
+    int* rr_info = nullptr;
+    if (m >= 2 && m <= 64) NDMPS_TRY(eigh_small_async(ctx, H, m, hev, W, 1e-16f, &rr_info));   // no host round trip
+    else NDMPS_TRY(eigh(ctx, H, m, hev, W, 0.0));
     // Zt[c] = sum_r W[r][c] Q[r]
     combine_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8)), 128, 0, ctx->stream>>>(W, 1, m, Xa, m, n, Xb);
     NDMPS_LAUNCH_CHECK(ctx);
     // 5. back-transform
-    if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, tau, n, Xb, m, U, ldu);
-    else backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, tau, n, Xb, m, U, ldu);
+    if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
+    else backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
     NDMPS_LAUNCH_CHECK(ctx);
-    finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, out_dev);
+    finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, rr_info, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
-    if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh_topk n = %d, k = %d: %d CTAs x %d rows\n", n, m, C, nr);
+    if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh_topk n = %d, k = %d: %d CTAs\n", n, m, C);
     *done = true;
     return NDMPS_OK;
 }
