@@ -99,7 +99,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
     __shared__ double ub0[32 * NEQ], ub1[32 * NEQ], wv[32 * NEQ];
     __shared__ double red0[TDT / 32], red1[TDT / 32];
     __shared__ double s_alpha;
-    constexpr int KM = (32 * NEQ) / TDT;                 // vector elements per thread
+    constexpr int KM = (32 * NEQ) / TDT > 0 ? (32 * NEQ) / TDT : 1;                 // vector elements per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
     const int gi = warp * C + cta;                       // this warp's row, held in registers: lane l has columns l + 32 q
     double a[NEQ];
@@ -690,7 +690,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     {
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
-        void* fn = n <= 256 ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
+        void* fn = (n <= 256 && TDT <= 256) ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
         NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(C), dim3(TDT), args, 0, ctx->stream));
         ctx->launches++;
 #ifdef NDMPS_TOPK_PROF

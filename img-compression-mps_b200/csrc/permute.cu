@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ndmps {
@@ -420,7 +422,10 @@ static void build_tile_plan(const DigitList& dl, TilePlan& tp) {
     tp.ok = true;
 }
 
+static std::mutex g_upload_mutex;   // plans are shared between host threads (batch.py); the upload happens once
+
 static int upload_tile_plan(TilePlan& tp, int device) {
+    std::lock_guard<std::mutex> lock(g_upload_mutex);
     if (tp.device == device && tp.d_pos) return NDMPS_OK;
     NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_src, tp.hi_src.size() * sizeof(int64_t)));
     NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_dst, tp.hi_dst.size() * sizeof(int64_t)));
