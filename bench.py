@@ -4,15 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload cfg2|cfg3] [--chi 64]
 
-A step is one pass of the hot path over one synthetic volume:
-``NDMPS.from_tensor(vol, max_bond=chi)`` (permute to site order, TT-SVD sweep, boundary
-list, norm) followed by ``to_tensor`` (contract, inverse permute).  Default workload is
+A step is one pass of the hot path over one BATCH of synthetic volumes (independent items, as
+the reference's benchmark loop processes them): per volume ``NDMPS.from_tensor(vol,
+max_bond=chi)`` (permute to site order, TT-SVD sweep, boundary list, norm) followed by
+``to_tensor`` (contract, inverse permute); ``--in-flight`` volumes run concurrently on one
+GPU (``imgcompressionmps.batch.VolumePipeline``: host threads x CUDA streams).  Default workload is
 BASELINE.json configs[1]: a 256^3 float32 synthetic MRI volume at chi = 64; ``cfg3`` is
 the 512^3 volume of the north-star target.
 
-* ``value``  : device-resident - the volume already sits in HBM, the reconstruction stays
+* ``value``  : device-resident - the volumes already sit in HBM, the reconstructions stay
   in HBM.  K steps timed with CUDA events, L2 flushed between steps (outside the event
   pairs), barrier + synchronize on both sides, max over ranks.
+* ``single_volume`` : the same path one volume at a time (latency), with the stage profiler on;
+  the per-kernel rooflines come from this pass.
 * ``e2e``    : the same step through the C ABI on HOST buffers (``ndmps_roundtrip_host``:
   H2D copy, encode, sweep, contract, decode, D2H copy inside the timed region).
 * N > 1     : one process per GPU (torchrun); every rank runs the whole path on its own
@@ -42,8 +46,8 @@ for _p in (str(ROOT), str(ROOT / "img-compression-mps_b200")):
 METRIC = "ndmps_encode_truncate_reconstruct_voxels_per_s"
 UNIT = "voxels/s"
 WORKLOADS = {
-    "cfg2": {"shape": (256, 256, 256), "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume"},
-    "cfg3": {"shape": (512, 512, 512), "name": "configs[2]: 512x512x512 fp32 synthetic volume (north-star target)"},
+    "cfg2": {"shape": (256, 256, 256), "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume", "in_flight": 4},
+    "cfg3": {"shape": (512, 512, 512), "name": "configs[2]: 512x512x512 fp32 synthetic volume (north-star target)", "in_flight": 3},
 }
 CPU_SAMPLE_SHAPE = (128, 128, 128)
 
@@ -235,70 +239,97 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from imgcompressionmps.batch import VolumePipeline
+
     wl = WORKLOADS[args.workload]
     shape = wl["shape"]
     nvox = int(np.prod(shape))
-    host = synthetic_volume(shape, 2026 + rank)                    # every rank its own volume
-    pinned = torch.from_numpy(host).pin_memory()
-    vol = pinned.cuda(non_blocking=False)
+    in_flight = args.in_flight or wl["in_flight"]
+    batch = args.volumes or 2 * in_flight                            # volumes per step
+    n_distinct = min(batch, 4)                                       # distinct inputs (each >= 64 MB; L2 is flushed between steps)
+    hosts = [synthetic_volume(shape, 2026 + 16 * rank + i) for i in range(n_distinct)]
+    pinned = [torch.from_numpy(h).pin_memory() for h in hosts]
+    vols_distinct = [p.cuda(non_blocking=False) for p in pinned]
+    vols = [vols_distinct[i % n_distinct] for i in range(batch)]
+    vol = vols[0]
     ctx = _native.context()
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    pipe = VolumePipeline(workers=in_flight)
 
-    def step():
+    def single():
         obj = NDMPS.from_tensor(vol, max_bond=args.chi)
         rec = obj.to_tensor_device()
         return obj, rec
 
+    def step():
+        pipe.roundtrip(vols, max_bond=args.chi, keep=False)
+
     for _ in range(max(args.warmup, 3)):
-        obj, rec = step()
+        obj, rec = single()
+        step()
     torch.cuda.synchronize()
     ranks = obj.bond_sizes()
     dims = obj.mps.site_dims
     err = float(torch.linalg.vector_norm((rec - vol).double()) / torch.linalg.vector_norm(vol.double()))
 
-    # ---- device-resident timing -------------------------------------------------------------------
+    # ---- device-resident timing: `batch` volumes per step, `in_flight` of them concurrently -------------
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ctx.profile(True)
-    ctx.stage_times(reset=True)
-    ctx.stat("eig_flops", reset=True)
-    launches0 = ctx.launch_count()
+    launches0 = pipe.launch_count()
     barrier()
     with ClockSampler(local) as clocks:
         for i in range(args.steps):
             flush_buf.fill_(i & 0xFF)                                # evict L2 (outside the event pair)
             starts[i].record()
-            step()
+            step()                                                   # workers wait for the submitting stream, then are joined
             stops[i].record()
         barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
-    launches = ctx.launch_count() - launches0
-    stages = ctx.stage_times(reset=True)
-    ctx_eig_flops = ctx.stat("eig_flops", reset=True)
-    ctx.profile(False)
+    launches = pipe.launch_count() - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * nvox * args.steps / (total_ms * 1e-3)
+    value = world * batch * nvox * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the C ABI on host buffers ----------------------------------------------
-    src = pinned.numpy()
-    dst = torch.empty_like(pinned).pin_memory().numpy()
-    for _ in range(2):
-        _ops.roundtrip_host(src, max_bond=args.chi, out=dst)
+    # ---- one volume at a time, stage profiler on: latency and the per-kernel rooflines ------------------
+    p_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    p_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ctx.profile(True)
+    ctx.stage_times(reset=True)
+    ctx.stat("eig_flops", reset=True)
+    barrier()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)
+        p_starts[i].record()
+        single()
+        p_stops[i].record()
+    barrier()
+    single_ms = sum(s.elapsed_time(e) for s, e in zip(p_starts, p_stops)) / args.steps
+    stages = ctx.stage_times(reset=True)
+    ctx_eig_flops = ctx.stat("eig_flops", reset=True)
+    ctx.profile(False)
+
+    # ---- end to end through the C ABI on host buffers, same batch, same concurrency ----------------------
+    srcs = [pinned[i % n_distinct].numpy() for i in range(batch)]
+    dst_t = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(batch)]
+    dsts = [d.numpy() for d in dst_t]
+    for _ in range(3):
+        pipe.roundtrip_host(srcs, dsts, max_bond=args.chi)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _ops.roundtrip_host(src, max_bond=args.chi, out=dst)
+        pipe.roundtrip_host(srcs, dsts, max_bond=args.chi)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e_value = world * nvox * args.steps / e2e_s
+    e2e_value = world * batch * nvox * args.steps / e2e_s
+    src, dst = srcs[0], dsts[0]
     e2e_err = float(np.linalg.norm(dst.astype(np.float64) - src) / np.linalg.norm(src.astype(np.float64)))
+    pipe.close()
 
     if rank != 0:
         if world > 1:
@@ -315,7 +346,7 @@ def run_ours(args):
     work = algorithmic_work(dims, ranks)
     per_step = {k: (v[0] / args.steps, v[1] / max(args.steps, 1)) for k, v in stages.items()}
     step_ms = total_ms / args.steps
-    shares = {k: round(v[0] / step_ms, 4) for k, v in per_step.items() if v[1]}
+    shares = {k: round(v[0] / single_ms, 4) for k, v in per_step.items() if v[1]}
     rooflines = {}
     gram_ms, gram_calls = per_step["gram"]
     if gram_calls:
@@ -340,7 +371,8 @@ def run_ours(args):
     if eig_calls:
         ach = eig_flops / (eig_ms * 1e-3) / 1e12
         rooflines["eig"] = {
-            "kernel": "pivoted_cholesky_kernel + jacobi_persistent_kernel (float64 SIMT)", "bound": "latency (neither hbm nor tensor)",
+            "kernel": "eig_topk.cu (tridiag_kernel, bisect, invit, Rayleigh-Ritz) for capped bonds; eig.cu Jacobi otherwise (float64 SIMT)",
+            "bound": "latency (neither hbm nor tensor)",
             "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s (fp64)", "frac": ach / FP64_PEAK_TFLOPS, "traffic": None,
             "ms_per_step": eig_ms, "calls_per_step": eig_calls, "flops_per_step": eig_flops}
     dominant = max(shares, key=shares.get) if shares else None
@@ -354,16 +386,21 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "shape": list(shape), "chi": args.chi, "mode": "Std", "site_dims": dims,
-                   "bond_dims": ranks, "volumes_per_gpu": 1, "l2_flush_between_steps": True,
-                   "parallelism": f"{world} independent volume(s), one per GPU, no data-path collective",
+                   "bond_dims": ranks, "volumes_per_step_per_gpu": batch, "volumes_in_flight_per_gpu": in_flight,
+                   "l2_flush_between_steps": True,
+                   "parallelism": f"{world} GPU(s) x {batch} independent volumes per step, {in_flight} in flight per GPU "
+                                  f"(host threads x CUDA streams), no data-path collective",
                    "reconstruction_rel_error_vs_input": err},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvox * 4, "d2h_bytes_per_step": nvox * 4,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "entry": "ndmps_roundtrip_host (C ABI, pinned host buffers)",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * nvox * 4, "d2h_bytes_per_step": batch * nvox * 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "entry": "VolumePipeline.roundtrip_host -> ndmps_roundtrip_host (C ABI, pinned host buffers)",
                 "reconstruction_rel_error_vs_input": e2e_err},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof,
-        "stage_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items() if v[1]},
+        "single_volume": {"ms": single_ms, "value": nvox / (single_ms * 1e-3), "unit": UNIT,
+                          "note": "one volume at a time on one stream (latency); the stage times and rooflines are from this pass",
+                          "stage_ms": {k: round(v[0], 4) for k, v in per_step.items() if v[1]}},
         "speed_of_light": {"hbm_floor_ms": (work["encode_bytes"] + work["decode_bytes"] + work["sweep_bytes"] + work["recon_bytes"])
                            / (peaks["hbm_gbs"] * 1e6), "note": "SURVEY 8(d) algorithmic bytes / measured HBM peak"},
     }
@@ -387,6 +424,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--chi", type=int, default=64)
+    ap.add_argument("--in-flight", type=int, default=0, help="volumes processed concurrently per GPU (0: workload default)")
+    ap.add_argument("--volumes", type=int, default=0, help="volumes per step per GPU (0: twice the number in flight)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -740,6 +740,8 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, rr_info, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
     if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh_topk n = %d, k = %d: %d CTAs\n", n, m, C);
+    ctx->eig_calls++;
+    ctx->eig_flops += 2.0 * n * (double)n * n + 4.0 * (double)n * n * m;   // full-matrix rank-2 updates + products; back-transformation
     *done = true;
     return NDMPS_OK;
 }

@@ -33,14 +33,19 @@ class VolumePipeline:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.workers = int(workers)
         self._tls = threading.local()
+        self._ctx_lock = threading.Lock()
+        self._contexts = []                             # the workers' native contexts (for launch counts / options)
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="ndmps-worker",
                                         initializer=self._init_worker)
 
     # -- worker side ---------------------------------------------------------------------------
     def _init_worker(self):
         import torch
+        from . import _native
         torch.cuda.set_device(self.device)
         self._tls.stream = torch.cuda.Stream(device=self.device)
+        with self._ctx_lock:
+            self._contexts.append(_native.context())
 
     def _run(self, fn: Callable, item, ready_event):
         import torch
@@ -88,6 +93,11 @@ class VolumePipeline:
             return _ops.roundtrip_host(src, max_bond=max_bond, cutoff=cutoff, out=dst)
 
         return self.map(one, list(zip(sources, outs)))
+
+    def launch_count(self) -> int:
+        """Kernels launched so far by all workers of this pipeline."""
+        with self._ctx_lock:
+            return sum(c.launch_count() for c in self._contexts)
 
     def close(self):
         self._pool.shutdown(wait=True)

@@ -148,6 +148,54 @@ def test_eigh_graded_and_rank_deficient(ops, n):
     print(f"graded n={n}: {sweeps} sweeps")
 
 
+# ---- leading-eigenpair solver (capped bonds) -----------------------------------------------------
+def _topk_check(ops, g, k, res_tol=1e-12):
+    evals, evecs, trace, health = ops.eigh_topk(dev(g), k)
+    evals, evecs = evals.cpu().numpy(), evecs.cpu().numpy()
+    want = np.linalg.eigvalsh(g)[::-1]
+    assert health == 0
+    assert np.all(np.diff(evals) <= 0)
+    assert np.allclose(evals, want[:k], rtol=0, atol=1e-13 * want[0])
+    assert abs(trace - np.trace(g)) <= 1e-13 * np.trace(g)
+    assert np.allclose(evecs.T @ evecs, np.eye(k), atol=1e-12)
+    assert np.max(np.linalg.norm(g @ evecs - evecs * evals[None, :], axis=0)) <= res_tol * want[0]
+    return evals, evecs
+
+
+@pytest.mark.parametrize("n,k", [(96, 16), (200, 64), (256, 64), (357, 64), (512, 64), (512, 100), (1000, 64)])
+def test_eigh_topk_random_gram(ops, n, k):
+    rng = np.random.default_rng(7 * n + k)
+    a = rng.standard_normal((n, 2 * n + 3))
+    _topk_check(ops, a @ a.T, k)
+
+
+@pytest.mark.parametrize("n", [256, 512])
+def test_eigh_topk_clusters_and_rank_deficiency(ops, n):
+    """Repeated and nearly repeated leading eigenvalues (the block is re-orthonormalised between
+    inverse-iteration steps and rotated by Rayleigh-Ritz) and a null space behind the kept part."""
+    rng = np.random.default_rng(n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.zeros(n)
+    lam[:16] = 5.0
+    lam[16:32] = 5.0 - 1e-13
+    lam[32:48] = 2.0 * (1.0 - 1e-9 * np.arange(16))
+    lam[48:150] = 10.0 ** np.linspace(0, -9, 102)
+    g = (q * lam[None, :]) @ q.T
+    g = 0.5 * (g + g.T)
+    evals, evecs = _topk_check(ops, g, 64, res_tol=5e-12)
+    # the 48 leading vectors span the same subspace as the true ones
+    proj = q[:, :48].T @ evecs[:, :48]
+    assert np.allclose(np.linalg.svd(proj, compute_uv=False), 1.0, atol=1e-9)
+
+
+def test_eigh_topk_rejects_unsupported_shapes(ops):
+    g = np.eye(64)
+    with pytest.raises(ValueError):
+        ops.eigh_topk(dev(g), 8)          # n < 96
+    with pytest.raises(ValueError):
+        ops.eigh_topk(dev(np.eye(256)), 200)   # 2k > n
+
+
 # ---- DCT --------------------------------------------------------------------------------------------
 def test_dct_against_scipy_fftpack_fixture(ops, golden_dct):
     g = golden_dct

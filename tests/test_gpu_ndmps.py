@@ -233,3 +233,83 @@ def test_roundtrip_host_entry():
     assert ranks == o.bond_sizes()
     ro = o.to_tensor()
     assert np.linalg.norm(rec - ro) / np.linalg.norm(ro) < 1e-5
+
+
+# ---- capped bonds: leading-eigenpair solver vs the full solver ---------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_capped_sweep_same_as_full_solver(NDMPS, dtype):
+    """With a bond cap the sweep may take the leading-eigenpair route (eig_topk.cu); ranks are
+    identical by construction, singular values and reconstruction agree with the full Jacobi solve
+    and with the oracle."""
+    from imgcompressionmps import _native
+    x = phantom((128, 128, 128), seed=11, background=0.01).astype(dtype)
+    ctx = _native.context()
+    ctx.set_option("eig_topk", 1)
+    calls0 = ctx.stat("eig_calls")
+    a = NDMPS.from_tensor(x, max_bond=64)
+    ctx.set_option("eig_topk", 0)
+    try:
+        b = NDMPS.from_tensor(x, max_bond=64)
+    finally:
+        ctx.set_option("eig_topk", 1)
+    assert ctx.stat("eig_calls") > calls0
+    assert a.bond_sizes() == b.bond_sizes()
+    assert max(a.bond_sizes()) == 64
+    tol = 1e-6 if dtype == np.float32 else 1e-9
+    for sa, sb in zip(a.singular_values, b.singular_values):
+        assert np.allclose(sa, sb, rtol=0, atol=tol * sb[0])
+    ra, rb = a.to_tensor().astype(np.float64), b.to_tensor().astype(np.float64)
+    assert np.linalg.norm(ra - rb) / np.linalg.norm(rb) < (1e-5 if dtype == np.float32 else 1e-8)
+    o = OracleNDMPS.from_tensor(x, max_bond=64)
+    assert a.bond_sizes() == o.bond_sizes()
+    ro = o.to_tensor()
+    assert np.linalg.norm(ra - ro) / np.linalg.norm(ro) < (1e-5 if dtype == np.float32 else 1e-8)
+
+
+def test_cap_that_does_not_bind_falls_back():
+    """A tensor whose exact bond dimension (40) sits below a generous cap (64): the sweep tries the
+    leading-eigenpair route on the 320 x 320 Gram matrices, finds no discarded weight, declines, and the
+    full solver must return the cutoff's ranks, as the oracle does."""
+    from imgcompressionmps import _native, _ops
+    rng = np.random.default_rng(3)
+    dims, r = [8] * 6, 40
+    bonds = [8, r, r, r, 8]
+    cores = [rng.standard_normal((dims[0], bonds[0]))]
+    for i in range(1, 5):
+        cores.append(rng.standard_normal((bonds[i - 1], dims[i], bonds[i])) / np.sqrt(bonds[i - 1]))
+    cores.append(rng.standard_normal((bonds[-1], dims[-1])))
+    dense = OMPS.contract_dense(cores)
+    ctx = _native.context()
+    ctx.set_option("verbose", 1)
+    try:
+        got, ranks, svals = _ops.ttsvd(torch.from_numpy(dense).cuda(), dims, max_bond=64)
+    finally:
+        ctx.set_option("verbose", 0)
+    want, wsv = OMPS.tt_svd(dense, dims, max_bond=64, return_svals=True)
+    assert ranks == bonds == OMPS.bond_sizes(want)
+    for sg, so in zip(svals, wsv):
+        assert np.allclose(sg, so, rtol=0, atol=1e-9 * so[0])
+    rec = OMPS.contract_dense([c.cpu().numpy() for c in got])
+    assert np.linalg.norm(rec - dense) / np.linalg.norm(dense) < 1e-9
+
+
+# ---- several volumes in flight ------------------------------------------------------------------------
+def test_volume_pipeline_matches_sequential(NDMPS):
+    from imgcompressionmps.batch import VolumePipeline
+    vols = [torch.from_numpy(phantom((64, 64, 64), seed=40 + i, background=0.01).astype(np.float32)).cuda() for i in range(6)]
+    seq = []
+    for v in vols:
+        obj = NDMPS.from_tensor(v, max_bond=32)
+        seq.append((obj.bond_sizes(), obj.to_tensor_device().clone()))
+    with VolumePipeline(workers=3) as pipe:
+        out = pipe.roundtrip(vols, max_bond=32)
+        assert pipe.launch_count() > 0
+        host_src = [v.cpu().numpy() for v in vols]
+        host_dst = [np.empty_like(h) for h in host_src]
+        res = pipe.roundtrip_host(host_src, host_dst, max_bond=32)
+    for (bonds, rec), (obj, got) in zip(seq, out):
+        assert obj.bond_sizes() == bonds
+        assert torch.equal(got, rec)                                   # same calls, same bits
+    for (bonds, rec), dst, (_, ranks) in zip(seq, host_dst, res):
+        assert ranks == bonds
+        assert np.array_equal(dst, rec.cpu().numpy())

@@ -68,3 +68,16 @@ def test_quantise_helpers(golden_quantise):
             q = scale_to_dtype(a, dt)
             assert np.array_equal(q, g[f"q{i}_{name}"])
             assert np.array_equal(scale_back(q, a.min(), a.max(), dt), g[f"back{i}_{name}"])
+
+
+def test_volume_pipeline_needs_a_gpu():
+    """No CPU fallback: the pipeline refuses to start without a device."""
+    import torch
+    from imgcompressionmps import _native
+    from imgcompressionmps.batch import VolumePipeline
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError):
+        VolumePipeline(workers=2)
+    with pytest.raises(ValueError):
+        VolumePipeline(workers=0)
