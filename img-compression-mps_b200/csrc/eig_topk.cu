@@ -22,6 +22,8 @@
 // The caller (ttsvd.cu) checks on the host that the cap really binds (discarded weight well
 // above the cutoff target, lambda_k well above the rounding floor of T) and otherwise falls
 // back to the full solver, so rank decisions stay identical to the oracle's.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ndmps {
@@ -462,12 +464,22 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
     double* Lm = sm;                         // m x (m + 1), lower triangle = L
     double* Y = sm + (size_t)m * (m + 1);    // m x (m + 1)
     __shared__ int s_bad;
+    __shared__ double diag0[128];
     const int tid = threadIdx.x, ld = m + 1;
     if (tid == 0) s_bad = 0;
+    double dev = 0.0;                                    // max |S - I|
     for (int e = tid; e < m * m; e += 128) {
         const int r = e / m, c = e - r * m;
-        Lm[r * ld + c] = 0.5 * (S[(size_t)r * m + c] + S[(size_t)c * m + r]);
+        const double v = 0.5 * (S[(size_t)r * m + c] + S[(size_t)c * m + r]);
+        Lm[r * ld + c] = v;
+        dev = fmax(dev, fabs(v - (r == c ? 1.0 : 0.0)));
     }
+    const int far = __syncthreads_or(dev > 4.0 * 2.220446049250313e-16 * m ? 1 : 0);
+    if (!far) {                                          // already orthonormal to rounding: L = I
+        for (int e = tid; e < m * m; e += 128) Linv[e] = (e / m == e % m) ? 1.0 : 0.0;
+        return;
+    }
+    for (int j = tid; j < m; j += 128) diag0[j] = fabs(Lm[j * ld + j]);
     __syncthreads();
     const int r = tid;
     for (int j = 0; j < m; j++) {
@@ -490,7 +502,7 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
         if (r == j) Y[0] = mine;                          // pivot candidate
         __syncthreads();
         double piv = Y[0];
-        const double floor_j = 2.220446049250313e-16 * m * fabs(S[(size_t)j * m + j]);
+        const double floor_j = 2.220446049250313e-16 * m * diag0[j];
         if (!(piv > floor_j)) {
             if (tid == 0) s_bad++;
             piv = floor_j > 0.0 ? floor_j : 1e-300;
@@ -650,16 +662,17 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
-    {
-        static size_t iv_set = 0, ch_set = 0;
-        if (smem_iv > iv_set) {
-            NDMPS_CUDA_TRY(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_iv));
-            iv_set = smem_iv;
-        }
-        if (smem_ch > ch_set) {
-            NDMPS_CUDA_TRY(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ch));
-            ch_set = smem_ch;
-        }
+    {   // fixed ceilings, set once: contexts on several host threads share these function attributes
+        static std::once_flag once;
+        static cudaError_t once_rc = cudaSuccess;
+        const int ceiling = (int)ctx->smem_optin - 2048;
+        std::call_once(once, [&]() {
+            once_rc = cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+            if (once_rc == cudaSuccess)
+                once_rc = cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+        });
+        NDMPS_CUDA_TRY(once_rc);
+        if (smem_iv > (size_t)ceiling) return NDMPS_OK;
     }
     double *V, *tau, *d, *e, *pbuf, *rowbuf, *lam, *bounds, *Xa, *Xb, *S, *Linv, *TQ, *H, *hev, *W, *factors;
     unsigned* ctrl;
