@@ -254,9 +254,24 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     return NDMPS_OK;
 }
 
+// Column-sharded sweep: this rank holds the slice of the dense site array
+// with the last site index in its block, i.e. a column block of every unfolding.  The left factor
+// of a step depends only on G = M M^T, a SUM over column blocks: local Gram, allreduce through the
+// caller's hook (NCCL on the launching stream), then the identical small eigenproblem on every rank
+// and a local projection.  The sweep stops being sharded (stop_site) once the remainder is small.
+struct ShardCtl {
+    int world = 1;
+    ndmps_allreduce_fn allreduce = nullptr;
+    void* user = nullptr;
+    int64_t stop_bytes = 0;        // hand back once the GLOBAL remainder is at most this many bytes
+    int sites_done = 0;            // out
+    const void* remainder = nullptr;   // out: (r_prev x remaining_local), in the workspace
+    int64_t remainder_rows = 1, remainder_cols = 0;
+};
+
 static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int64_t* dims, const TrimOpts& opt,
                  void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out, double* svals_out,
-                 int64_t svals_stride) {
+                 int64_t svals_stride, ShardCtl* sh = nullptr) {
     const size_t esz = dtype_size(dtype);
     // cores stored in float32 need eigenvectors orthogonal to ~1e-8, not 1e-15: one sweep less
     const double eig_tol = dtype == NDMPS_F32 ? 1e-10 : 0.0;
@@ -283,15 +298,30 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             int64_t Dn = D * dims[site + k], Cn = C / dims[site + k];
             if (Dn <= ctx->opt_merge_cap && Dn <= Cn) { D = Dn; C = Cn; k++; } else break;
         }
+        if (sh) {
+            // sharded phase ends when the global remainder is small or the local block gets wider than long
+            const int64_t glob_bytes = r_prev * remaining * (int64_t)sh->world * (int64_t)esz;
+            if (glob_bytes <= sh->stop_bytes || D > C || site + k >= L - 1) {
+                sh->sites_done = site;
+                sh->remainder = M;
+                sh->remainder_rows = r_prev;
+                sh->remainder_cols = remaining;
+                return NDMPS_OK;
+            }
+        }
         if (ctx->opt_verbose)
-            fprintf(stderr, "[ndmps] sweep site %d: group of %d, unfolding %lld x %lld (%s Gram)\n", site, k,
-                    (long long)D, (long long)C, D <= C ? "row" : "column");
+            fprintf(stderr, "[ndmps] sweep site %d: group of %d, unfolding %lld x %lld (%s Gram)%s\n", site, k,
+                    (long long)D, (long long)C, D <= C ? "row" : "column", sh ? " [column shard]" : "");
         int64_t r_out = 0;
         void* T = nullptr;
         if (D <= C) {
             double* G = nullptr;
             NDMPS_TRY(ctx->ws.get<double>((size_t)(D * D), &G));
             { StageScope sc(ctx, ST_GRAM); NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 0, G)); }
+            if (sh && sh->world > 1) {
+                const int rc_hook = sh->allreduce(sh->user, G, D * D, (void*)ctx->stream);
+                if (rc_hook != 0) { set_error("ttsvd: the allreduce hook failed (%d)", rc_hook); return NDMPS_ERR_CUDA; }
+            }
             double* P = nullptr;       // (pd x rc) accumulated isometry (times renorm factors); nullptr = identity
             int64_t pd = r_prev, rc = r_prev;
             for (int j = 0; j < k; j++) {
@@ -319,7 +349,7 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
                 NDMPS_TRY(ctx->ws.get<double>((size_t)mj, &evals));
                 NDMPS_TRY(ctx->ws.get<double>((size_t)(mj * mj), &U));
                 // rank of this unfolding is at most min(rows, cols)
-                int64_t cols_j = C * rest;
+                int64_t cols_j = C * rest * (sh ? sh->world : 1);
                 int64_t nmax = mj < cols_j ? mj : cols_j;
                 int64_t n = 0;
                 double f = 1.0;
@@ -396,6 +426,10 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
         r_prev = r_out;
         remaining = C;
         site += k;
+    }
+    if (sh) {   // not reached: the sharded phase always hands back before the last site
+        set_error("ttsvd: sharded sweep ran to the last site");
+        return NDMPS_ERR_INVALID;
     }
     // last core = final remainder (r_{L-2} x d_{L-1})
     int64_t last = r_prev * dims[L - 1];
@@ -555,6 +589,17 @@ static int overlap(ndmps_ctx* ctx, const void* const* ca, const int64_t* ra, int
     return dot(ca[L - 1], da, F, NDMPS_F64, al * d);
 }
 
+// out[r][c][g][t] = gathered[g][r][c][t]: the column blocks of `world` ranks put back in site order
+template <class T>
+__global__ void __launch_bounds__(256)
+interleave_shards_kernel(const T* __restrict__ gathered, int world, int64_t rows, int64_t cmid, int64_t dl, T* __restrict__ out) {
+    const int64_t total = (int64_t)world * rows * cmid * dl;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t t = i % dl, g = (i / dl) % world, c = (i / (dl * world)) % cmid, r = i / (dl * world * cmid);
+        out[i] = gathered[((g * rows + r) * cmid + c) * dl + t];
+    }
+}
+
 }  // namespace ndmps
 
 using namespace ndmps;
@@ -574,6 +619,52 @@ int ndmps_ttsvd(ndmps_ctx_t* ctx, const void* dense, int dtype, int levels, cons
     TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
     NDMPS_TRY(ttsvd(ctx, dense, dtype, levels, dims, opt, cores_out, core_cap, ranks_out_host, svals_out_host, svals_stride));
     NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return NDMPS_OK;
+}
+
+int ndmps_ttsvd_sharded(ndmps_ctx_t* ctx, const void* dense_local, int dtype, int levels, const int64_t* dims_local,
+                        int world, ndmps_allreduce_fn allreduce, void* user, int64_t stop_bytes,
+                        double cutoff, int cutoff_mode, int64_t max_bond, int renorm,
+                        void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out_host,
+                        double* svals_out_host, int64_t svals_stride,
+                        int* sites_done_host, void* remainder_out, int64_t remainder_cap, int64_t* remainder_shape_host) {
+    NDMPS_REQUIRE(ctx && dense_local && dims_local && cores_out && core_cap && ranks_out_host, "ndmps_ttsvd_sharded: NULL argument");
+    NDMPS_REQUIRE(sites_done_host && remainder_out && remainder_shape_host, "ndmps_ttsvd_sharded: NULL output");
+    NDMPS_REQUIRE(levels >= 2 && dtype_ok(dtype), "ndmps_ttsvd_sharded: bad levels or dtype");
+    NDMPS_REQUIRE(world >= 1 && (world == 1 || allreduce), "ndmps_ttsvd_sharded: world %d needs an allreduce hook", world);
+    NDMPS_REQUIRE(cutoff_mode >= NDMPS_CUT_ABS && cutoff_mode <= NDMPS_CUT_RSUM1, "ndmps_ttsvd_sharded: bad cutoff_mode %d", cutoff_mode);
+    for (int i = 0; i < levels; i++) NDMPS_REQUIRE(dims_local[i] >= 1, "ndmps_ttsvd_sharded: bad dims at %d", i);
+    NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
+    ShardCtl sh;
+    sh.world = world;
+    sh.allreduce = allreduce;
+    sh.user = user;
+    sh.stop_bytes = stop_bytes;
+    NDMPS_TRY(ttsvd(ctx, dense_local, dtype, levels, dims_local, opt, cores_out, core_cap, ranks_out_host, svals_out_host,
+                    svals_stride, &sh));
+    const int64_t count = sh.remainder_rows * sh.remainder_cols;
+    NDMPS_REQUIRE(count <= remainder_cap, "ndmps_ttsvd_sharded: remainder needs %lld elements, capacity %lld", (long long)count,
+                  (long long)remainder_cap);
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(remainder_out, sh.remainder, (size_t)count * dtype_size(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
+    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *sites_done_host = sh.sites_done;
+    remainder_shape_host[0] = sh.remainder_rows;
+    remainder_shape_host[1] = sh.remainder_cols;
+    return NDMPS_OK;
+}
+
+int ndmps_interleave_shards(ndmps_ctx_t* ctx, const void* gathered, int dtype, int world, int64_t rows, int64_t cmid, int64_t dl,
+                            void* out) {
+    NDMPS_REQUIRE(ctx && gathered && out && gathered != out, "ndmps_interleave_shards: NULL or aliased argument");
+    NDMPS_REQUIRE(dtype_ok(dtype) && world >= 1 && rows >= 1 && cmid >= 1 && dl >= 1, "ndmps_interleave_shards: bad shape or dtype");
+    const int64_t total = (int64_t)world * rows * cmid * dl;
+    const int g = ew_grid(ctx, total);
+    if (dtype == NDMPS_F32)
+        interleave_shards_kernel<float><<<g, 256, 0, ctx->stream>>>((const float*)gathered, world, rows, cmid, dl, (float*)out);
+    else
+        interleave_shards_kernel<double><<<g, 256, 0, ctx->stream>>>((const double*)gathered, world, rows, cmid, dl, (double*)out);
+    NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
 

@@ -25,6 +25,8 @@ _tls = threading.local()
 
 i64, f64, vp, ci = C.c_int64, C.c_double, C.c_void_p, C.c_int
 p_i64, p_f64, p_vp = C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_void_p)
+# int (*ndmps_allreduce_fn)(void* user, double* buf_dev, int64_t count, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 # name -> (restype, argtypes); kept in one table so the symbol test can walk it
 PROTOTYPES = {
@@ -56,6 +58,9 @@ PROTOTYPES = {
     "ndmps_gram": (ci, [vp, vp, i64, i64, i64, ci, ci, vp]),
     "ndmps_eigh": (ci, [vp, vp, i64, vp, vp, C.POINTER(ci)]),
     "ndmps_eigh_topk": (ci, [vp, vp, i64, i64, vp, vp]),
+    "ndmps_ttsvd_sharded": (ci, [vp, vp, ci, ci, p_i64, ci, ALLREDUCE_FN, vp, i64, f64, ci, i64, ci,
+                                p_vp, p_i64, p_i64, p_f64, i64, C.POINTER(ci), vp, i64, p_i64]),
+    "ndmps_interleave_shards": (ci, [vp, vp, ci, ci, i64, i64, i64, vp]),
     "ndmps_gemm": (ci, [vp, i64, i64, i64, f64, vp, ci, i64, i64, vp, ci, i64, i64, vp, ci, i64]),
     "ndmps_ttsvd": (ci, [vp, vp, ci, ci, p_i64, f64, ci, i64, ci, p_vp, p_i64, p_i64, p_f64, i64]),
     "ndmps_compress_bond": (ci, [vp, vp, vp, ci, i64, i64, i64, f64, ci, i64, ci, vp, vp, p_i64, p_f64]),

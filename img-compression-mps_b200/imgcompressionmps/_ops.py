@@ -35,10 +35,10 @@ def plan_for(shape) -> N.Plan:
 
 
 # ---- K1 ---------------------------------------------------------------------------
-def encode(volume, scale: float = 1.0):
+def encode(volume, scale: float = 1.0, plan=None):
     """volume (original shape, device) -> dense array shaped by the site dims."""
     torch = _torch()
-    plan = plan_for(tuple(volume.shape))
+    plan = plan or plan_for(tuple(volume.shape))
     _dev(volume, "volume")
     out = torch.empty(plan.site_dims, dtype=volume.dtype, device=volume.device)
     N.check(N.load_library().ndmps_encode(N.handle(), plan.handle, N.ptr(volume), N.ptr(out),
@@ -46,9 +46,9 @@ def encode(volume, scale: float = 1.0):
     return out
 
 
-def decode(dense, shape):
+def decode(dense, shape, plan=None):
     torch = _torch()
-    plan = plan_for(tuple(shape))
+    plan = plan or plan_for(tuple(shape))
     _dev(dense, "dense")
     if dense.numel() != plan.total:
         raise ValueError("dense array does not match the volume shape")
@@ -215,6 +215,78 @@ def ttsvd(dense, dims, cutoff=1e-10, cutoff_mode="rsum2", max_bond=None, renorm=
         n = int(np.prod(shp, dtype=np.int64))
         cores.append(bufs[i][:n].view(shp) if n == caps[i] else bufs[i][:n].clone().view(shp))
     return cores, ranks, [svals[i, :ranks[i]].copy() for i in range(L - 1)]
+
+
+class _DevicePointer:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def ttsvd_sharded(dense_local, dims_local, world: int, allreduce=None, stop_bytes: int = 8 << 20, cutoff=1e-10,
+                  cutoff_mode="rsum2", max_bond=None, renorm=None):
+    """Sharded phase of the sweep on this rank's column block (``ndmps_ttsvd_sharded``).
+
+    ``allreduce(tensor)`` must sum the float64 device tensor in place over the ranks (e.g.
+    ``torch.distributed.all_reduce``); it is called once per Gram pass on the current stream.
+    Returns (cores of the finished sites, their ranks, singular values, remainder[rows, cols])."""
+    torch = _torch()
+    _dev(dense_local, "dense_local")
+    dims = [int(d) for d in dims_local]
+    L = len(dims)
+    mode = N.CUTOFF_MODES[cutoff_mode]
+    if renorm is None:
+        renorm = {N.CUT_RSUM2: 2, N.CUT_SUM2: 2, N.CUT_RSUM1: 1, N.CUT_SUM1: 1}.get(mode, 0)
+    gdims = dims[:-1] + [dims[-1] * int(world)]
+    bounds = bond_bounds(gdims, max_bond)
+    caps = [int(np.prod(core_shape(i, L, gdims, bounds), dtype=np.int64)) for i in range(L)]
+    bufs = [torch.empty(c, dtype=dense_local.dtype, device=dense_local.device) for c in caps]
+    ranks = (C.c_int64 * max(L - 1, 1))()
+    stride = max(bounds) if bounds else 1
+    svals = np.zeros((max(L - 1, 1), stride), dtype=np.float64)
+    remainder = torch.empty(dense_local.numel(), dtype=dense_local.dtype, device=dense_local.device)
+    sites_done = C.c_int(0)
+    rshape = (C.c_int64 * 2)()
+    failure = []
+
+    def hook(_user, buf, count, _stream):
+        try:
+            allreduce(torch.as_tensor(_DevicePointer(buf, count), device=dense_local.device))
+            return 0
+        except Exception as exc:                     # never let an exception cross the C frame
+            failure.append(exc)
+            return 1
+
+    cb = N.ALLREDUCE_FN(hook) if (world > 1 and allreduce is not None) else C.cast(None, N.ALLREDUCE_FN)
+    if world > 1 and allreduce is None:
+        raise ValueError("ttsvd_sharded: world > 1 needs an allreduce callable")
+    rc = N.load_library().ndmps_ttsvd_sharded(
+        N.handle(), N.ptr(dense_local), N.dtype_code(dense_local.dtype), L, N.i64_array(dims), int(world), cb, None,
+        int(stop_bytes), float(cutoff), mode, int(max_bond or 0), int(renorm), N.ptr_array(bufs), N.i64_array(caps), ranks,
+        svals.ctypes.data_as(N.p_f64), stride, C.byref(sites_done), N.ptr(remainder), remainder.numel(), rshape)
+    if failure:
+        raise failure[0]
+    N.check(rc, "ndmps_ttsvd_sharded")
+    done = sites_done.value
+    rk = [int(r) for r in ranks][:done]
+    cores = []
+    for i in range(done):                              # done < L - 1: never the last core
+        shp = (gdims[0], rk[0]) if i == 0 else (rk[i - 1], gdims[i], rk[i])
+        n = int(np.prod(shp, dtype=np.int64))
+        cores.append(bufs[i][:n].clone().view(shp))
+    rows, cols = int(rshape[0]), int(rshape[1])
+    return cores, rk, [svals[i, :rk[i]].copy() for i in range(done)], remainder[:rows * cols].view(rows, cols)
+
+
+def interleave_shards(gathered, world: int, rows: int, cmid: int, dl: int):
+    """gathered[g][r][c][t] (rank-major, as all-gathered) -> out[r][c][g][t] (site order)."""
+    torch = _torch()
+    _dev(gathered, "gathered")
+    out = torch.empty(rows * cmid * world * dl, dtype=gathered.dtype, device=gathered.device)
+    N.check(N.load_library().ndmps_interleave_shards(N.handle(), N.ptr(gathered), N.dtype_code(gathered.dtype), int(world),
+                                                     int(rows), int(cmid), int(dl), N.ptr(out)), "ndmps_interleave_shards")
+    return out.view(rows, cmid * world * dl)
 
 
 def compress_bond(t1, t2, cutoff, cutoff_mode="rel", max_bond=None, renorm=0):

@@ -6,11 +6,21 @@ item ``i`` goes to rank ``i % world`` and every rank runs the whole single-GPU p
 communication is a gather of the per-item scalars (metrics, bond dimensions) at the end.
 
 ``process_group`` may be NCCL (GPU ranks) or gloo (the CPU tests of the host logic, where the
-``compress_fn`` is a stand-in).  Nothing in here touches the device itself.
+``compress_fn`` is a stand-in).
+
+ONE very large tensor shards too: rank g keeps the voxels whose
+last-level digits select block g of the LAST site index -- a sub-lattice of the volume, cut at load
+time (``shard_volume``) -- which is a column block of every unfolding of the sweep.  The left
+factor of a step depends only on ``G = M M^T``, a sum over column blocks, so each step is: local
+Gram, allreduce of the bond-sized Gram matrix (``ShardedNDMPS``; NCCL through
+``torch.distributed`` on the compute stream), the same small eigenproblem on every rank, local
+projection.  Once the remainder is a few MB it is all-gathered and the sweep finishes replicated.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Sequence
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
@@ -52,3 +62,166 @@ def compress_and_score(index: int, volume, max_bond=None, cutoff: float = 1e-10,
     if 2 <= len(obj.shape) <= 4 and min(obj.shape[:3]) >= 3:
         out["ssim"] = float(compute_ssim_by_dim(rec, volume))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# one tensor over several ranks: column-sharded sweep
+# ---------------------------------------------------------------------------------------------
+def last_level_split(factors: np.ndarray, world: int) -> List[int]:
+    """How ``world`` ranks divide the last site index: per-axis counts ``w`` with prod(w) == world.
+
+    The last site index is the mixed-radix number of the axes' last-level digits, axis 0 most
+    significant (``utils/core.py:6-35``).  Consecutive blocks of it are products of per-axis digit
+    ranges only if the leading axes are split completely before the next one is touched."""
+    last = [int(f) for f in np.asarray(factors)[-1]]
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    split, left = [], int(world)
+    for f in last:
+        if left == 1:
+            split.append(1)
+        elif left % f == 0:
+            split.append(f)
+            left //= f
+        elif f % left == 0:
+            split.append(left)
+            left = 1
+        else:
+            raise ValueError(f"{world} ranks do not divide the last-level factors {last} block-wise")
+    if left != 1:
+        raise ValueError(f"{world} ranks exceed the last site dimension {int(np.prod(last))}")
+    return split
+
+
+def _digit_ranges(factors: np.ndarray, rank: int, world: int) -> List[Tuple[int, int]]:
+    split = last_level_split(factors, world)
+    if not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    last = [int(f) for f in np.asarray(factors)[-1]]
+    coords, g = [], int(rank)
+    for w in reversed(split):                       # rank = mixed radix over the split, axis 0 most significant
+        coords.append(g % w)
+        g //= w
+    coords.reverse()
+    return [(c * (f // w), (c + 1) * (f // w)) for c, f, w in zip(coords, last, split)]
+
+
+def local_factors(factors: np.ndarray, world: int) -> np.ndarray:
+    """Factor table of a rank's sub-lattice: the last level divided by the split."""
+    out = np.array(factors, dtype=np.int64, copy=True)
+    out[-1] //= np.asarray(last_level_split(factors, world), dtype=np.int64)
+    return out
+
+
+def _lattice_view(array, factors: np.ndarray):
+    """View with every axis a split into (n_a / f_a, f_a), f_a the last-level factor."""
+    last = [int(f) for f in np.asarray(factors)[-1]]
+    shape = []
+    for n, f in zip(array.shape, last):
+        shape += [int(n) // f, f]
+    return array.reshape(shape)
+
+
+def shard_volume(volume, factors: np.ndarray, rank: int, world: int):
+    """This rank's sub-lattice of ``volume`` (numpy array or torch tensor, any device): the voxels
+    whose last-level digits fall in the rank's block of the last site index.  Copy, C-contiguous."""
+    ranges = _digit_ranges(factors, rank, world)
+    view = _lattice_view(volume, factors)
+    index = []
+    for lo, hi in ranges:
+        index += [slice(None), slice(lo, hi)]
+    part = view[tuple(index)]
+    shape = [part.shape[2 * a] * part.shape[2 * a + 1] for a in range(len(ranges))]
+    return part.reshape(shape)
+
+
+def place_shard(full, part, factors: np.ndarray, rank: int, world: int):
+    """Inverse of ``shard_volume``: write a rank's sub-lattice back into the full array (in place)."""
+    ranges = _digit_ranges(factors, rank, world)
+    view = _lattice_view(full, factors)
+    index, pshape = [], []
+    for a, (lo, hi) in enumerate(ranges):
+        index += [slice(None), slice(lo, hi)]
+        pshape += [view.shape[2 * a], hi - lo]
+    view[tuple(index)] = part.reshape(pshape)
+    return full
+
+
+class ShardedNDMPS:
+    """MPS of ONE tensor whose voxels are spread over the ranks of a process group.
+
+    ``from_local`` runs the sweep of ``NDMPS.from_tensor`` (``core/ndmps.py:36-78``, Std mode) on this
+    rank's sub-lattice; the cores come out identical on every rank (and equal to what a single GPU
+    computes on the whole tensor, up to the summation order of the Gram allreduce).
+    ``to_local_tensor_device`` reconstructs this rank's sub-lattice (``core/ndmps.py:131-153``)."""
+
+    def __init__(self, cores, site_dims, shape, factors, rank, world, singular_values):
+        self.cores, self.site_dims, self.shape = cores, [int(d) for d in site_dims], tuple(shape)
+        self.factors, self.rank, self.world = factors, int(rank), int(world)
+        self.singular_values = singular_values
+
+    def bond_sizes(self) -> List[int]:
+        return [int(c.shape[-1]) for c in self.cores[:-1]]
+
+    @classmethod
+    def from_local(cls, local_volume, shape: Sequence[int], rank: Optional[int] = None, world: Optional[int] = None,
+                   process_group=None, max_bond=None, cutoff: float = 1e-10, stop_bytes: int = 8 << 20) -> "ShardedNDMPS":
+        import torch
+        import torch.distributed as dist
+        from . import _native, _ops
+        from .utils.core import get_factorlist
+        if rank is None or world is None:
+            rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        shape = tuple(int(s) for s in shape)
+        factors, _ = get_factorlist(shape)
+        site_dims = [int(d) for d in np.prod(factors, axis=1)]
+        lf = local_factors(factors, world)
+        lshape = tuple(int(n) // w for n, w in zip(shape, last_level_split(factors, world)))
+        if tuple(local_volume.shape) != lshape:
+            raise ValueError(f"rank {rank}: local volume has shape {tuple(local_volume.shape)}, expected {lshape}")
+        plan = _native.Plan(lshape, lf)
+        dense = _ops.encode(local_volume.contiguous(), 1.0, plan=plan)
+        ldims = [int(d) for d in plan.site_dims]
+        L = len(ldims)
+
+        def allreduce(t):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group)
+
+        cores, ranks, svals, rem = _ops.ttsvd_sharded(dense, ldims, world, allreduce if world > 1 else None,
+                                                      stop_bytes=stop_bytes, cutoff=cutoff, max_bond=max_bond)
+        del dense
+        done = len(cores)
+        rows, cols = int(rem.shape[0]), int(rem.shape[1])
+        if world > 1:                                   # remainders of all ranks, back in site order
+            gathered = torch.empty((world,) + tuple(rem.shape), dtype=rem.dtype, device=rem.device)
+            if dist.get_backend(process_group) == "nccl":
+                dist.all_gather_into_tensor(gathered, rem.contiguous(), group=process_group)
+            else:                                       # gloo (tests): list form
+                parts = [torch.empty_like(rem) for _ in range(world)]
+                dist.all_gather(parts, rem.contiguous(), group=process_group)
+                for g, part in enumerate(parts):
+                    gathered[g].copy_(part)
+            dl = ldims[-1]
+            rem = _ops.interleave_shards(gathered, world, rows, cols // dl, dl)
+        # replicated tail: the remainder as a dense array whose first site carries the incoming bond
+        tail_dims = [rows * site_dims[done]] + site_dims[done + 1:]
+        tcores, tranks, tsv = _ops.ttsvd(rem.reshape(-1), tail_dims, cutoff=cutoff, max_bond=max_bond)
+        if len(tail_dims) == 1:
+            tcores = [tcores[0].view(rows, site_dims[done])]
+        else:
+            first = tcores[0].view(rows, site_dims[done], tranks[0]) if done > 0 else tcores[0]
+            tcores = [first] + list(tcores[1:])
+        return cls(cores + tcores, site_dims, shape, factors, rank, world, list(svals) + list(tsv))
+
+    def to_local_tensor_device(self):
+        """This rank's sub-lattice of the reconstruction (device tensor)."""
+        from . import _native, _ops
+        lf = local_factors(self.factors, self.world)
+        split = last_level_split(self.factors, self.world)
+        lshape = tuple(int(n) // w for n, w in zip(self.shape, split))
+        plan = _native.Plan(lshape, lf)
+        dl = int(plan.site_dims[-1])
+        last = self.cores[-1]
+        block = last[..., self.rank * dl:(self.rank + 1) * dl].contiguous()
+        dense = _ops.contract_dense(list(self.cores[:-1]) + [block])
+        return _ops.decode(dense.reshape(-1), lshape, plan=plan)

@@ -146,6 +146,30 @@ int ndmps_ttsvd(ndmps_ctx_t* ctx, const void* dense, int dtype, int levels, cons
                 void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out_host,
                 double* svals_out_host, int64_t svals_stride);
 
+/* ---- column-sharded sweep over several GPUs (one process per GPU) -------------
+ * The same from_dense sweep (core/ndmps.py:74) when ONE tensor is spread over `world` ranks: rank g
+ * holds the slice of the dense site array whose LAST site index lies in block g
+ * (dims_local = dims with the last entry divided by world), i.e. a column block of every unfolding.
+ * Per step: local Gram, `allreduce` (sum, float64, in place, `count` doubles at buf_dev, enqueued on
+ * `stream`; return 0 on success - the binding calls ncclAllReduce / torch.distributed.all_reduce),
+ * the same bond eigenproblem on every rank, local projection.  The sharded phase stops before the
+ * step at which the GLOBAL remainder is <= stop_bytes (or the local block stops being wide): cores
+ * 0 .. *sites_done_host-1 (identical on every rank) are written, and the local remainder
+ * (remainder_shape_host[0] x remainder_shape_host[1], row-major) is copied to remainder_out.  The
+ * caller gathers the remainders, restores site order with ndmps_interleave_shards and finishes with
+ * ndmps_ttsvd on dims (rows * d_s, d_{s+1}, ...). */
+typedef int (*ndmps_allreduce_fn)(void* user, double* buf_dev, int64_t count, void* stream);
+int ndmps_ttsvd_sharded(ndmps_ctx_t* ctx, const void* dense_local, int dtype, int levels, const int64_t* dims_local,
+                        int world, ndmps_allreduce_fn allreduce, void* user, int64_t stop_bytes,
+                        double cutoff, int cutoff_mode, int64_t max_bond, int renorm,
+                        void* const* cores_out, const int64_t* core_cap, int64_t* ranks_out_host,
+                        double* svals_out_host, int64_t svals_stride,
+                        int* sites_done_host, void* remainder_out, int64_t remainder_cap, int64_t* remainder_shape_host);
+/* out[r][c][g][t] = gathered[g][r][c][t]  (g < world, r < rows, c < cmid, t < dl): column blocks of
+ * the ranks (as all-gathered, rank-major) back into the site order of the unsharded remainder. */
+int ndmps_interleave_shards(ndmps_ctx_t* ctx, const void* gathered, int dtype, int world, int64_t rows, int64_t cmid, int64_t dl,
+                            void* out);
+
 /* ---- K6: pairwise bond truncation -----------------------------------------
  * qtn.tensor_compress_bond(T1, T2, cutoff, cutoff_mode="rel") at
  * core/ndmps.py:104-106 (absorb="both", no renorm).  t1: a x r, t2: r x b
