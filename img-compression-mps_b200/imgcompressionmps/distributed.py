@@ -18,6 +18,7 @@ projection.  Once the remainder is a few MB it is all-gathered and the sweep fin
 """
 from __future__ import annotations
 
+from functools import lru_cache
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -91,6 +92,20 @@ def last_level_split(factors: np.ndarray, world: int) -> List[int]:
     if left != 1:
         raise ValueError(f"{world} ranks exceed the last site dimension {int(np.prod(last))}")
     return split
+
+
+@lru_cache(maxsize=32)
+def _plan_cached(shape: Tuple[int, ...], factor_bytes: bytes, levels: int):
+    from . import _native
+    return _native.Plan(shape, np.frombuffer(factor_bytes, dtype=np.int64).reshape(levels, len(shape)).copy())
+
+
+def local_plan(shape: Sequence[int], factors: np.ndarray, world: int):
+    """(plan, local shape) of a rank's sub-lattice; plans are cached (building the tile tables and
+    uploading them is milliseconds of host work and a synchronising copy)."""
+    lf = np.ascontiguousarray(local_factors(factors, world), dtype=np.int64)
+    lshape = tuple(int(n) // w for n, w in zip(shape, last_level_split(factors, world)))
+    return _plan_cached(lshape, lf.tobytes(), int(lf.shape[0])), lshape
 
 
 def _digit_ranges(factors: np.ndarray, rank: int, world: int) -> List[Tuple[int, int]]:
@@ -175,11 +190,9 @@ class ShardedNDMPS:
         shape = tuple(int(s) for s in shape)
         factors, _ = get_factorlist(shape)
         site_dims = [int(d) for d in np.prod(factors, axis=1)]
-        lf = local_factors(factors, world)
-        lshape = tuple(int(n) // w for n, w in zip(shape, last_level_split(factors, world)))
+        plan, lshape = local_plan(shape, factors, world)
         if tuple(local_volume.shape) != lshape:
             raise ValueError(f"rank {rank}: local volume has shape {tuple(local_volume.shape)}, expected {lshape}")
-        plan = _native.Plan(lshape, lf)
         dense = _ops.encode(local_volume.contiguous(), 1.0, plan=plan)
         ldims = [int(d) for d in plan.site_dims]
         L = len(ldims)
@@ -215,11 +228,8 @@ class ShardedNDMPS:
 
     def to_local_tensor_device(self):
         """This rank's sub-lattice of the reconstruction (device tensor)."""
-        from . import _native, _ops
-        lf = local_factors(self.factors, self.world)
-        split = last_level_split(self.factors, self.world)
-        lshape = tuple(int(n) // w for n, w in zip(self.shape, split))
-        plan = _native.Plan(lshape, lf)
+        from . import _ops
+        plan, lshape = local_plan(self.shape, self.factors, self.world)
         dl = int(plan.site_dims[-1])
         last = self.cores[-1]
         block = last[..., self.rank * dl:(self.rank + 1) * dl].contiguous()
