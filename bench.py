@@ -343,6 +343,8 @@ def run_ours(args):
         m = json.loads(pk.read_text())
         peaks = {"hbm_gbs": m["hbm_gbs"], "bf16_tflops": m.get("bf16_tflops_sustained", m["bf16_tflops"]), "source": "measured"}
     FP64_PEAK_TFLOPS = 34.2          # measured on this pool, tools/microbench/fp64_rate.cu (profiles/r01_summary.md)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture profiles/r01c_kernels_raw.csv (256^3 only)
+    ncu_traffic = {"permute": 67.15e6 + 17.35e6, "gram": 67.13e6 + 6.24e6} if args.workload == "cfg2" else {}
     work = algorithmic_work(dims, ranks)
     per_step = {k: (v[0] / args.steps, v[1] / max(args.steps, 1)) for k, v in stages.items()}
     step_ms = total_ms / args.steps
@@ -354,7 +356,7 @@ def run_ours(args):
         rooflines["gram"] = {
             "kernel": "gram_dmma_kernel (FP64 tensor pipe, mma.sync m8n8k4, exact float64 accumulation)", "bound": "tensor",
             "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            "frac_of_fp64_peak": ach / FP64_PEAK_TFLOPS, "fp64_peak": FP64_PEAK_TFLOPS, "traffic": None,
+            "frac_of_fp64_peak": ach / FP64_PEAK_TFLOPS, "fp64_peak": FP64_PEAK_TFLOPS, "traffic": ncu_traffic.get("gram"),
             "ms_per_step": gram_ms, "calls_per_step": gram_calls,
             "flops_per_step": work["gram_flops_executed"],
             "note": "flops of the Gram passes actually run (front-merged group + later steps); tcgen05 has no float64 "
@@ -364,8 +366,11 @@ def run_ours(args):
         ach = (work["encode_bytes"] + work["decode_bytes"]) / (perm_ms * 1e-3) / 1e9
         rooflines["permute"] = {
             "kernel": "permute_tiled_kernel<float,4> (encode + decode)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_step": perm_ms, "calls_per_step": perm_calls,
-            "bytes_per_step": work["encode_bytes"] + work["decode_bytes"]}
+            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic.get("permute"), "ms_per_step": perm_ms,
+            "calls_per_step": perm_calls, "bytes_per_step": work["encode_bytes"] + work["decode_bytes"],
+            "note": "achieved = algorithmic 8 B/voxel x 2 launches / event-timed stage (event overhead included; the kernel alone "
+                    "is 40 us = 3.36 TB/s under ncu); traffic = DRAM bytes of ONE launch: below the algorithmic 134 MB because most "
+                    "of the 64 MB output is still in the 126 MB L2 when the kernel ends"}
     eig_ms, eig_calls = per_step["eig"]
     eig_flops = ctx_eig_flops / args.steps
     if eig_calls:
