@@ -1,6 +1,11 @@
 // Context, workspace arena and error plumbing of libndmps_sm100.so.
 #include <stdarg.h>
 
+#include <chrono>
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace ndmps {
@@ -87,6 +92,70 @@ int profile_collect(ndmps_ctx* ctx) {
         cudaEventDestroy(p.end);
     }
     ctx->pending.clear();
+    return NDMPS_OK;
+}
+
+
+// ---- gate for concurrent cooperative launches (see common.cuh) ---------------------------------
+namespace {
+struct CoopTicket { cudaEvent_t done; int sms; };
+struct CoopGate {
+    std::mutex m;
+    int in_use = 0;                        // SMs booked by cooperative kernels in flight
+    std::vector<CoopTicket> inflight;
+    std::vector<cudaEvent_t> pool;
+    void reap() {                          // give back what has finished (called with m held)
+        for (size_t i = 0; i < inflight.size();) {
+            if (cudaEventQuery(inflight[i].done) != cudaErrorNotReady) {
+                in_use -= inflight[i].sms;
+                pool.push_back(inflight[i].done);
+                inflight[i] = inflight.back();
+                inflight.pop_back();
+            } else {
+                i++;
+            }
+        }
+    }
+};
+CoopGate g_gate;
+}  // namespace
+
+int coop_launch(ndmps_ctx* ctx, const void* fn, dim3 grid, dim3 block, void** args, size_t smem) {
+    int per_sm = 0;
+    NDMPS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (int)(block.x * block.y * block.z), smem));
+    if (per_sm < 1) per_sm = 1;
+    const int ctas = (int)(grid.x * grid.y * grid.z);
+    int sms = (ctas + per_sm - 1) / per_sm;
+    const int budget = ctx->sm_count;
+    if (sms > budget) sms = budget;
+    cudaEvent_t ev = nullptr;
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> lock(g_gate.m);
+            g_gate.reap();
+            if (g_gate.in_use == 0 || g_gate.in_use + sms <= budget) {
+                g_gate.in_use += sms;
+                if (!g_gate.pool.empty()) { ev = g_gate.pool.back(); g_gate.pool.pop_back(); }
+                break;
+            }
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    cudaError_t e = cudaSuccess;
+    if (!ev) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(fn, grid, block, args, smem, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->stream);
+    {
+        std::lock_guard<std::mutex> lock(g_gate.m);
+        if (e == cudaSuccess) g_gate.inflight.push_back({ev, sms});
+        else g_gate.in_use -= sms;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s:%d: cooperative launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+        return NDMPS_ERR_CUDA;
+    }
+    ctx->launches++;
     return NDMPS_OK;
 }
 

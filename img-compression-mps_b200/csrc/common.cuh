@@ -202,6 +202,11 @@ int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* ev
 int eigh_small_async(ndmps_ctx* ctx, double* a_dev, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev);
 // leading k eigenpairs (eig_topk.cu); out_dev: k Ritz values, trace(G), rank-loss count
 int eigh_topk(ndmps_ctx* ctx, const double* g_dev, int64_t n, int64_t k, double* out_dev, double* evecs_dev, int64_t ldu, bool* done);
+// Cooperative (grid-barrier) kernels of several contexts may be in flight at once (batch.py).  Their
+// CTAs spin at barriers, so the sum of what is launched must fit the machine: a launch books the SMs
+// its grid needs (grid / resident CTAs per SM) in a process-wide gate and gives them back from a
+// stream callback when the kernel has finished; a launch that does not fit waits on the host.
+int coop_launch(ndmps_ctx* ctx, const void* fn, dim3 grid, dim3 block, void** args, size_t smem);
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);
 
 #ifdef __CUDACC__

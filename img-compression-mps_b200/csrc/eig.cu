@@ -1076,9 +1076,7 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, in
     NDMPS_TRY(ctx->ws.get<unsigned>((size_t)nb * nb + nb, &stamps));
     NDMPS_CUDA_TRY(cudaMemsetAsync(stamps, 0, ((size_t)nb * nb + nb) * sizeof(unsigned), ctx->stream));
     void* args[] = {&A, &n, &ncols, &b, &nb, &max_sweeps, &ctrl, &tol2, &floor2, &stamps, &quad_stop2};
-    NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem,
-                                               ctx->stream));
-    ctx->launches++;
+    NDMPS_TRY(coop_launch(ctx, (const void*)jacobi_persistent_kernel<NR>, dim3(nb / 2), dim3(32 * b), args, smem));
     return NDMPS_OK;
 }
 
@@ -1227,8 +1225,7 @@ static int pivoted_cholesky_blocked(ndmps_ctx* ctx, const double* G, int n, doub
     NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 4 * sizeof(unsigned), ctx->stream));
     double stop_rel = 2.220446049250313e-16;
     void* args[] = {&G, &n, &rows_per, &Lcol, &diag_g, &rows_g, &ctrl, &stop_rel};
-    NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)pivoted_cholesky_blocked_kernel, dim3(ncta), dim3(256), args, smem, ctx->stream));
-    ctx->launches++;
+    NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_blocked_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1267,8 +1264,7 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 4 * sizeof(unsigned), ctx->stream));
     double stop_rel = 2.220446049250313e-16;
     void* args[] = {&G, &n, &rows_per, &Lcol, &cand_rows, &cand, &ctrl, &stop_rel};
-    NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)pivoted_cholesky_kernel, dim3(ncta), dim3(256), args, smem, ctx->stream));
-    ctx->launches++;
+    NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

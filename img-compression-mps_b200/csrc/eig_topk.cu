@@ -704,8 +704,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
         void* fn = (n <= 256 && TDT <= 256) ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
-        NDMPS_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(C), dim3(TDT), args, 0, ctx->stream));
-        ctx->launches++;
+        NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
 #ifdef NDMPS_TOPK_PROF
         {
             unsigned long long h[8];
