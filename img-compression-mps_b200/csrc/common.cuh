@@ -140,7 +140,7 @@ struct ndmps_ctx {
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_gemm_path = 0;      // 0: FP64 tensor pipe for large row-major products, 2: SIMT only
     int64_t opt_permute_path = 0;   // 0: ld/st tiles through shared memory; 3: bulk-copy (TMA-class) tiles; 2: gather kernel
-    int64_t opt_permute_ctas = 0;   // persistent CTAs per SM of the tiled kernel (0: 6)
+    int64_t opt_permute_ctas = 0;   // grid cap of the tiled kernel in CTAs per SM (0: 64)
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;
     int64_t opt_chol_blocked = 1;         // 8 pivots per pair of grid barriers

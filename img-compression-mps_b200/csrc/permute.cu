@@ -495,7 +495,9 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
         }
     }
     int64_t grid = tp.n_tiles;
-    int64_t cap = (int64_t)ctx->sm_count * (ctx->opt_permute_ctas > 0 ? ctx->opt_permute_ctas : 6);
+    // measured: the fewer tiles a CTA walks the better (the hardware scheduler balances the tail); 64 CTAs
+    // per SM in the grid means one tile per CTA up to 512^3 and a grid-stride loop beyond
+    int64_t cap = (int64_t)ctx->sm_count * (ctx->opt_permute_ctas > 0 ? ctx->opt_permute_ctas : 64);
     if (grid > cap) grid = cap;
     // 16-byte accesses when every run and every run offset is a multiple of 4 elements (float32 only)
     bool vec4 = sizeof(T) == 4 && (tp.pa % 4 == 0) && (tp.pb % 4 == 0) &&
