@@ -22,7 +22,7 @@ __device__ __forceinline__ void mma_f64(double& d0, double& d1, double a, double
 }
 
 template <int BM, class TA, class TB, class TC>
-__global__ void __launch_bounds__(BM * 4)
+__global__ void __launch_bounds__(BM * 4, BM == 64 ? 2 : 1)
 gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, const TA* __restrict__ A, int64_t lda, const TB* __restrict__ B, int64_t ldb,
                  TC* __restrict__ C, int64_t ldc, double alpha, int64_t tiles_n) {
     constexpr int THREADS = BM * 4;                     // one warp per 32 x 32 sub-tile

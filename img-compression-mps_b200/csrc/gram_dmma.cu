@@ -153,7 +153,8 @@ int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64
     const int m = (int)rows;
     const int nt = (m + TM - 1) / TM;
     const int ntiles = nt * (nt + 1) / 2;
-    int64_t splits = (2 * (int64_t)ctx->sm_count + ntiles - 1) / ntiles;
+    // one CTA per SM is resident (111 registers x 512 threads): fill whole waves, 2 x sm_count CTAs at most
+    int64_t splits = (2 * (int64_t)ctx->sm_count) / ntiles;
     const int64_t max_splits = (cols + 4 * BK - 1) / (4 * BK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
