@@ -92,7 +92,7 @@ def algorithmic_work(dims, ranks):
         recon_flops += 2.0 * p * r[k] * dims[k] * r[k + 1]
         p *= dims[k]
     # Gram passes actually executed: sites are front-merged while the fused row count stays <= 512
-    executed = 0.0
+    executed = issued = 0.0
     cols, i, rprev = n, 0, 1
     while i < L - 1:
         rows = rprev * dims[i]
@@ -104,10 +104,12 @@ def algorithmic_work(dims, ranks):
             k += 1
         side = min(rows, cols)
         executed += 2.0 * side * side * max(rows, cols)
+        nt = -(-side // 128)                                  # gram_dmma computes the upper-triangle 128 x 128 tiles only
+        issued += 2.0 * side * side * max(rows, cols) * ((nt + 1) / (2.0 * nt) if side >= 48 else 1.0)
         rprev = r[i + k]
         i += k
     return {"encode_bytes": 8.0 * n, "decode_bytes": 8.0 * n, "sweep_bytes": sweep_bytes, "gram_flops": gram_flops,
-            "gram_flops_executed": executed,
+            "gram_flops_executed": executed, "gram_flops_issued": issued,
             "project_flops": proj_flops, "recon_bytes": recon_bytes, "recon_flops": recon_flops}
 
 
@@ -356,11 +358,14 @@ def run_ours(args):
         rooflines["gram"] = {
             "kernel": "gram_dmma_kernel (FP64 tensor pipe, mma.sync m8n8k4, exact float64 accumulation)", "bound": "tensor",
             "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            "frac_of_fp64_peak": ach / FP64_PEAK_TFLOPS, "fp64_peak": FP64_PEAK_TFLOPS, "traffic": ncu_traffic.get("gram"),
+            "frac_of_fp64_peak": ach * work["gram_flops_issued"] / work["gram_flops_executed"] / FP64_PEAK_TFLOPS,
+            "issued_tflops_fp64": ach * work["gram_flops_issued"] / work["gram_flops_executed"],
+            "fp64_peak": FP64_PEAK_TFLOPS, "traffic": ncu_traffic.get("gram"),
             "ms_per_step": gram_ms, "calls_per_step": gram_calls,
             "flops_per_step": work["gram_flops_executed"],
-            "note": "flops of the Gram passes actually run (front-merged group + later steps); tcgen05 has no float64 "
-                    "kind, so the bf16 peak is the wrong denominator for this exact contraction - see frac_of_fp64_peak"}
+            "note": "achieved = 2 m^2 C of the Gram passes actually run (front-merged group + later steps) / time; the kernel "
+                    "issues only the upper-triangle tiles (issued_tflops_fp64).  tcgen05 has no float64 kind, so the bf16 peak is "
+                    "the wrong denominator for this exact contraction - see frac_of_fp64_peak (issued / measured FP64 rate)"}
     perm_ms, perm_calls = per_step["permute"]
     if perm_calls:
         ach = (work["encode_bytes"] + work["decode_bytes"]) / (perm_ms * 1e-3) / 1e9
