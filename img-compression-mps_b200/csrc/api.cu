@@ -68,7 +68,7 @@ int Arena::alloc(size_t bytes, void** out) {
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
     if (ctx->pinned_doubles >= doubles) return NDMPS_OK;
     if (ctx->pinned) {
-        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NDMPS_CUDA_TRY(stream_wait(ctx));
         cudaFreeHost(ctx->pinned);
         ctx->pinned = nullptr;
         ctx->pinned_doubles = 0;
@@ -81,7 +81,7 @@ int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
 
 int profile_collect(ndmps_ctx* ctx) {
     if (ctx->pending.empty()) return NDMPS_OK;
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     for (auto& p : ctx->pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.beg, p.end) == cudaSuccess) {
@@ -95,6 +95,17 @@ int profile_collect(ndmps_ctx* ctx) {
     return NDMPS_OK;
 }
 
+
+cudaError_t stream_wait(ndmps_ctx* ctx) {
+    if (!ctx->opt_blocking_sync) return cudaStreamSynchronize(ctx->stream);
+    if (!ctx->sync_event) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sync_event);
+}
 
 // ---- gate for concurrent cooperative launches (see common.cuh) ---------------------------------
 namespace {
@@ -190,8 +201,9 @@ int ndmps_ctx_create(ndmps_ctx_t** out) {
 
 int ndmps_ctx_destroy(ndmps_ctx_t* ctx) {
     if (!ctx) return NDMPS_OK;
-    cudaStreamSynchronize(ctx->stream);
+    stream_wait(ctx);
     ctx->ws.release();
+    if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
     return NDMPS_OK;
@@ -205,7 +217,7 @@ int ndmps_ctx_set_stream(ndmps_ctx_t* ctx, void* cuda_stream) {
 
 int ndmps_ctx_sync(ndmps_ctx_t* ctx) {
     NDMPS_REQUIRE(ctx != nullptr, "ndmps_ctx_sync: ctx is NULL");
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     return NDMPS_OK;
 }
 
@@ -264,6 +276,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "eig_topk")) ctx->opt_eig_topk = value;
     else if (!strcmp(name, "topk_passes")) ctx->opt_topk_passes = value;
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;
+    else if (!strcmp(name, "blocking_sync")) ctx->opt_blocking_sync = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
     else {
         set_error("ndmps_ctx_set_option: unknown option '%s'", name);

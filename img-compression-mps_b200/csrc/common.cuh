@@ -151,7 +151,9 @@ struct ndmps_ctx {
     int64_t opt_eig_topk = 1;             // bond cap set: leading-eigenpair solver (eig_topk.cu) instead of the full one
     int64_t opt_topk_passes = 0;          // bisection passes (0: 8, each divides the bracket by 129)
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
+    int64_t opt_blocking_sync = 0;        // host waits sleep on a blocking event instead of spinning (many host threads per core)
     int64_t opt_verbose = 0;
+    cudaEvent_t sync_event = nullptr;     // created on first blocking wait
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;
     double eig_flops = 0.0;        // 7 n per rotation x pairs x sweeps (+ n r^2 for the Cholesky), accumulated
@@ -167,6 +169,8 @@ struct ndmps_ctx {
 namespace ndmps {
 
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
+// wait for everything enqueued on the context's stream (spinning cudaStreamSynchronize, or a blocking event)
+cudaError_t stream_wait(ndmps_ctx* ctx);
 
 // RAII stage marker: records an event pair around a leaf stage when profiling is on
 struct StageScope {

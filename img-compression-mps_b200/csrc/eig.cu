@@ -1128,7 +1128,7 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
             default: NDMPS_TRY(run_persistent<0>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
         }
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] <= 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, cols = %d, b = %d)", max_sweeps, n, ncols, b);
             return NDMPS_ERR_NOCONV;
@@ -1144,7 +1144,7 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
         *sweeps_used = s + 1;
         if (s >= 3) {
             NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            NDMPS_CUDA_TRY(stream_wait(ctx));
             converged = host_flag[0] == 0;
         }
     }
@@ -1196,7 +1196,7 @@ static int pivoted_cholesky_cluster(ndmps_ctx* ctx, const double* G, int n, doub
     ctx->launches++;
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, rank_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     *done = true;
     return NDMPS_OK;
@@ -1228,7 +1228,7 @@ static int pivoted_cholesky_blocked(ndmps_ctx* ctx, const double* G, int n, doub
     NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_blocked_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     *done = true;
     return NDMPS_OK;
@@ -1267,7 +1267,7 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     return NDMPS_OK;
 }
@@ -1320,7 +1320,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         NDMPS_TRY(eigh_small_async(ctx, a_in, n, evals_dev, evecs_dev, tol_override > 0.0 ? 1e-14f : 0.f, &info));
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] < 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, single-CTA solver)", max_sweeps, n);
             return NDMPS_ERR_NOCONV;
@@ -1359,7 +1359,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         NDMPS_TRY(run_single<4>(ctx, cols, n, warps, max_sweeps, ctrl, tol2, floor2, (size_t)n * n * sizeof(double)));
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
         NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] <= 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d)", max_sweeps, n);
             return NDMPS_ERR_NOCONV;

@@ -192,7 +192,7 @@ static double renorm_factor(const double* s, int64_t n, int64_t keep, int power)
 static int fetch_svals(ndmps_ctx* ctx, const double* evals_dev, int64_t n, std::vector<double>& sv) {
     NDMPS_TRY(ensure_pinned(ctx, (size_t)n + 64));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, evals_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     sv.resize((size_t)n);
     for (int64_t i = 0; i < n; i++) sv[i] = ctx->pinned[i] > 0.0 ? sqrt(ctx->pinned[i]) : 0.0;
     return NDMPS_OK;
@@ -230,7 +230,7 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     if (!done) return NDMPS_OK;
     NDMPS_TRY(ensure_pinned(ctx, (size_t)k + 64));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     const double* ev = ctx->pinned;
     const double trace = ev[k], rank_loss = ev[k + 1];
     double kept = 0.0;
@@ -618,7 +618,7 @@ int ndmps_ttsvd(ndmps_ctx_t* ctx, const void* dense, int dtype, int levels, cons
     NDMPS_TRY(ctx->ws.reset(ctx->stream));
     TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
     NDMPS_TRY(ttsvd(ctx, dense, dtype, levels, dims, opt, cores_out, core_cap, ranks_out_host, svals_out_host, svals_stride));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     return NDMPS_OK;
 }
 
@@ -647,7 +647,7 @@ int ndmps_ttsvd_sharded(ndmps_ctx_t* ctx, const void* dense_local, int dtype, in
     NDMPS_REQUIRE(count <= remainder_cap, "ndmps_ttsvd_sharded: remainder needs %lld elements, capacity %lld", (long long)count,
                   (long long)remainder_cap);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(remainder_out, sh.remainder, (size_t)count * dtype_size(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     *sites_done_host = sh.sites_done;
     remainder_shape_host[0] = sh.remainder_rows;
     remainder_shape_host[1] = sh.remainder_cols;
@@ -677,7 +677,7 @@ int ndmps_compress_bond(ndmps_ctx_t* ctx, const void* t1, const void* t2, int dt
     NDMPS_TRY(ctx->ws.reset(ctx->stream));
     TrimOpts opt{cutoff, cutoff_mode, max_bond, renorm};
     NDMPS_TRY(compress_bond(ctx, t1, t2, dtype, a, r, b, opt, t1_out, t2_out, new_rank_host, svals_out_host));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     return NDMPS_OK;
 }
 
@@ -702,7 +702,7 @@ int ndmps_overlap(ndmps_ctx_t* ctx, const void* const* cores_a, const int64_t* r
     NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
     NDMPS_TRY(overlap(ctx, cores_a, ranks_a, dtype_a, cores_b, ranks_b, dtype_b, levels, dims, out_dev));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     out_host[0] = ctx->pinned[0];
     return NDMPS_OK;
 }
@@ -748,7 +748,7 @@ int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void*
     NDMPS_TRY(contract_dense(ctx, (const void* const*)cores.data(), dtype, L, plan->site_dims, ranks.data(), dense));
     NDMPS_TRY(permute(ctx, plan, true, dense, vol, dtype, 1.0));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDeviceToHost, ctx->stream));
-    NDMPS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     return NDMPS_OK;
 }
 

@@ -15,6 +15,7 @@ caller would make.
 """
 from __future__ import annotations
 
+import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Iterable, List, Optional, Sequence
@@ -23,7 +24,7 @@ from typing import Callable, Iterable, List, Optional, Sequence
 class VolumePipeline:
     """``workers`` host threads x (CUDA stream + native context) on the current device."""
 
-    def __init__(self, workers: int = 3, device: Optional[int] = None):
+    def __init__(self, workers: int = 3, device: Optional[int] = None, blocking_sync: Optional[bool] = None):
         import torch
         if workers < 1:
             raise ValueError("workers must be >= 1")
@@ -32,6 +33,12 @@ class VolumePipeline:
             raise _native.NativeError("VolumePipeline needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.workers = int(workers)
+        # host threads that wait for the GPU spin by default; with more waiting threads (all ranks of this
+        # node) than cores they would starve each other, so they sleep on blocking events instead
+        if blocking_sync is None:
+            ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            blocking_sync = self.workers * ranks_here > max(1, (os.cpu_count() or 1) - 1)
+        self.blocking_sync = bool(blocking_sync)
         self._tls = threading.local()
         self._ctx_lock = threading.Lock()
         self._contexts = []                             # the workers' native contexts (for launch counts / options)
@@ -44,8 +51,12 @@ class VolumePipeline:
         from . import _native
         torch.cuda.set_device(self.device)
         self._tls.stream = torch.cuda.Stream(device=self.device)
+        self._tls.done = torch.cuda.Event(blocking=self.blocking_sync)
+        ctx = _native.context()
+        if self.blocking_sync:                          # sleep, do not spin, while the GPU works
+            ctx.set_option("blocking_sync", 1)
         with self._ctx_lock:
-            self._contexts.append(_native.context())
+            self._contexts.append(ctx)
 
     def _run(self, fn: Callable, item, ready_event):
         import torch
@@ -54,7 +65,8 @@ class VolumePipeline:
             if ready_event is not None:
                 stream.wait_event(ready_event)          # inputs produced on the submitting stream
             out = fn(item)
-            stream.synchronize()                        # the result is complete when the future resolves
+            self._tls.done.record(stream)
+            self._tls.done.synchronize()                # the result is complete when the future resolves
         return out
 
     # -- caller side ---------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """Throughput of the device-resident round trip with several volumes in flight (VolumePipeline).
 Run on the GPU box:  python tools/batch_probe.py [n] [volumes] [workers ...]"""
+import os
 import sys
 import time
 from pathlib import Path
@@ -23,7 +24,9 @@ def main():
     host = [torch.from_numpy(synthetic_volume((n, n, n), 2026)).pin_memory().numpy() for _ in range(min(nvol, 4))]
     outs = [torch.empty((n, n, n), dtype=torch.float32).pin_memory().numpy() for _ in range(min(nvol, 4))]
     for w in workers:
-        with VolumePipeline(workers=w) as pipe:
+        blocking = {"0": False, "1": True}.get(os.environ.get("PROBE_BLOCKING", ""))
+        with VolumePipeline(workers=w, blocking_sync=blocking) as pipe:
+            print(f"blocking_sync={pipe.blocking_sync}", end=" ")
             pipe.roundtrip(vols[:w], max_bond=64, keep=False)
             pipe.roundtrip(vols[:w], max_bond=64, keep=False)
             torch.cuda.synchronize()
