@@ -624,17 +624,45 @@ backtransform_kernel(const double* __restrict__ V, int ldv, const double* __rest
     }
 }
 
-// out[0..k-1] = Ritz values (descending), out[k] = trace(G), out[k+1] = rank-loss count of the
-// Cholesky-QR steps (0 when healthy)
+// res[t] = | T z_t - theta_t z_t |  for the Ritz pairs (rows of Z): the one check that does not depend on
+// how the vectors were obtained
+__global__ void __launch_bounds__(128)
+ritz_residual_kernel(const double* __restrict__ d, const double* __restrict__ e, const double* __restrict__ Z, const double* __restrict__ theta,
+                     int n, double* __restrict__ res) {
+    __shared__ double scratch[32];
+    const int t = blockIdx.x;
+    const double* z = Z + (size_t)t * n;
+    const double th = theta[t];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 128) {
+        double v = (d[i] - th) * z[i];
+        if (i > 0) v = fma(e[i - 1], z[i - 1], v);
+        if (i < n - 1) v = fma(e[i], z[i + 1], v);
+        acc = fma(v, v, acc);
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) res[t] = sqrt(acc);
+}
+
+// out[0..k-1] = Ritz values (descending), out[k] = trace(G), out[k+1] = health: rank-loss count of the
+// Cholesky-QR steps + 1e3 if a Ritz residual exceeds 1e-11 |T| + 1e6 if the Rayleigh-Ritz solve did not
+// converge (0 when healthy; the caller falls back to the full solver otherwise)
 __global__ void __launch_bounds__(256)
 finish_kernel(const double* __restrict__ G, int n, const double* __restrict__ hev, int k, const int* __restrict__ info,
-              const int* __restrict__ rr_info, double* __restrict__ out) {
+              const int* __restrict__ rr_info, const double* __restrict__ res, const double* __restrict__ bounds,
+              double* __restrict__ out) {
     __shared__ double scratch[32];
     double tr = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) tr += G[(size_t)i * n + i];
     tr = block_sum(tr, scratch);
     for (int i = threadIdx.x; i < k; i += 256) out[i] = hev[i];
-    if (threadIdx.x == 0) { out[k] = tr; out[k + 1] = (double)info[0] + ((rr_info && rr_info[0] < 0) ? 1e6 : 0.0); }
+    if (threadIdx.x == 0) {
+        double worst = 0.0;                               // largest Ritz residual relative to the scale of T
+        for (int i = 0; i < k; i++) worst = fmax(worst, res[i]);
+        const bool bad_res = !(worst <= 1e-11 * bounds[0]);
+        out[k] = tr;
+        out[k + 1] = (double)info[0] + ((rr_info && rr_info[0] < 0) ? 1e6 : 0.0) + (bad_res ? 1e3 : 0.0);
+    }
 }
 
 static int orthonormalise(ndmps_ctx* ctx, const double* Xin, int m, int n, double* S, double* Linv, int* info, double* Xout) {
@@ -723,7 +751,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_LAUNCH_CHECK(ctx);
     // 3. inverse iteration (the LU factors of step 1 are reused), re-orthonormalised between steps;
     //    the last basis is orthonormalised twice
-    const int iters = ctx->opt_topk_iters > 0 ? (int)ctx->opt_topk_iters : 3;
+    const int iters = ctx->opt_topk_iters > 0 ? (int)ctx->opt_topk_iters : 2;   // the Ritz residuals are checked below
     const double* rhs = nullptr;
     for (int it = 0; it < iters; it++) {
         invit_kernel<<<m, 32, smem_iv, ctx->stream>>>(d, e, n, lam, bounds, rhs, Xa, factors, it > 0 ? 1 : 0);
@@ -745,11 +773,15 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     // Zt[c] = sum_r W[r][c] Q[r]
     combine_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8)), 128, 0, ctx->stream>>>(W, 1, m, Xa, m, n, Xb);
     NDMPS_LAUNCH_CHECK(ctx);
+    double* res = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)m, &res));
+    ritz_residual_kernel<<<m, 128, 0, ctx->stream>>>(d, e, Xb, hev, n, res);
+    NDMPS_LAUNCH_CHECK(ctx);
     // 5. back-transform
     if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
     else backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
     NDMPS_LAUNCH_CHECK(ctx);
-    finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, rr_info, out_dev);
+    finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, rr_info, res, bounds, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
     if (ctx->opt_verbose) fprintf(stderr, "[ndmps] eigh_topk n = %d, k = %d: %d CTAs\n", n, m, C);
     ctx->eig_calls++;

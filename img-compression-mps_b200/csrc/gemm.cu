@@ -159,9 +159,9 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     NDMPS_REQUIRE(tiles < (int64_t(1) << 31), "gemm: %lld x %lld output too large for one launch", (long long)m, (long long)n);
     int64_t target = 2 * (int64_t)ctx->sm_count;
     int64_t splits = 1;
-    if (tiles < target && k > 512) {
+    if (tiles < target && k >= 128) {                        // few output tiles: spread K over CTAs (bond-sized products)
         splits = (target + tiles - 1) / tiles;
-        int64_t max_splits = (k + 255) / 256;
+        int64_t max_splits = (k + 63) / 64;
         if (splits > max_splits) splits = max_splits;
         if (splits > 2048) splits = 2048;
         // keep the float64 partial buffer modest
