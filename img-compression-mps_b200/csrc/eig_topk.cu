@@ -31,7 +31,7 @@ namespace ndmps {
 namespace topk {
 
 constexpr int TDT = 256;   // threads per CTA of the tridiagonalisation
-constexpr int NMAX = 1024; // largest matrix of this path (32 columns per lane)
+constexpr int NMAX = 4096; // largest matrix of this path (registers up to 1024, L2-resident working copy beyond)
 constexpr int BIS = 128;   // shifts per pass and eigenvalue in the bisection
 
 __device__ __forceinline__ double rcp_fast(double x) {      // MUFU seed + 2 Newton steps, normal range
@@ -230,6 +230,164 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         epoch++;
         grid_barrier(ctrl, epoch * C);
         PROF_MARK(6);
+        double* t = u; u = un; un = t;
+        tau = taun;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1c. n > 1024 (bond x wide site, e.g. 64 x 40 rows): the matrix no longer fits the register files,
+// so the working copy stays in global memory (L2-resident up to ~3500^2) and the fused pass streams
+// the live part of every row through the SMs once per column: same algorithm, same one barrier per
+// column, rows dealt cyclically to the warps of a grid of one CTA per SM.  The three n-vectors
+// live in dynamic shared memory.  Traffic 16 n^3 / 3 bytes through L2 in total.
+// ---------------------------------------------------------------------------------------------
+constexpr int KMAX_BIG = 16;    // vector elements per thread -> n <= 4096
+
+__global__ void __launch_bounds__(TDT)
+tridiag_big_kernel(double* __restrict__ A, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
+                   double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
+    extern __shared__ double sm[];
+    double* ub0 = sm;
+    double* ub1 = sm + n;
+    double* wv = sm + 2 * (size_t)n;
+    __shared__ double red0[TDT / 32], red1[TDT / 32];
+    __shared__ double s_alpha;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
+    const int gw = warp * C + cta, nw = (TDT / 32) * C;  // this warp owns rows gw, gw + nw, ...
+    for (int c = tid; c < n; c += TDT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
+    double* u = ub0;
+    double* un = ub1;
+    double tau = 0.0;
+    unsigned epoch = 0;
+    __syncthreads();
+    for (int jn = 0; jn <= n - 2; jn++) {
+        const int par = jn & 1;
+        double r[KMAX_BIG];
+        if (jn == 0) {
+#pragma unroll
+            for (int m = 0; m < KMAX_BIG; m++) {
+                const int k = tid + m * TDT;
+                r[m] = k < n ? A[k] : 0.0;
+            }
+        } else {
+            const double* pb = pbuf + (size_t)(par ^ 1) * n;
+            const double* rb = rowbuf + (size_t)(par ^ 1) * n;
+            double pf[KMAX_BIG];
+#pragma unroll
+            for (int m = 0; m < KMAX_BIG; m++) {
+                const int k = tid + m * TDT;
+                const bool on = k >= jn && k < n;
+                pf[m] = on ? __ldcg(pb + k) : 0.0;
+                r[m] = on ? __ldcg(rb + k) : 0.0;
+            }
+            const double pj = __ldcg(pb + jn);
+            double part = 0.0;
+#pragma unroll
+            for (int m = 0; m < KMAX_BIG; m++) {
+                const int k = tid + m * TDT;
+                if (k < n) part = fma(pf[m], u[k], part);
+            }
+            const double s = block_sum_all(part, red0);
+            const double K = -0.5 * tau * tau * s;
+            const double wj = fma(tau, pj, K);
+#pragma unroll
+            for (int m = 0; m < KMAX_BIG; m++) {
+                const int k = tid + m * TDT;
+                if (k >= jn && k < n) {
+                    const double uk = u[k];
+                    const double wk = fma(tau, pf[m], K * uk);
+                    wv[k] = wk;
+                    r[m] = r[m] - wk - wj * uk;
+                } else {
+                    r[m] = 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < KMAX_BIG; m++) {
+            const int k = tid + m * TDT;
+            if (k == jn && cta == 0) d_g[jn] = r[m];
+            if (k == jn + 1) s_alpha = r[m];
+        }
+        if (jn == n - 2) {
+            __syncthreads();
+            if (cta == 0 && tid == 0) { e_g[jn] = s_alpha; tau_g[jn] = 0.0; }
+            if ((n - 1) % nw == gw && lane == 0)
+                d_g[n - 1] = __ldcg(A + (size_t)(n - 1) * n + (n - 1)) - (jn > 0 ? 2.0 * u[n - 1] * wv[n - 1] : 0.0);
+            break;
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int m = 0; m < KMAX_BIG; m++) {
+            const int k = tid + m * TDT;
+            if (k >= jn + 2 && k < n) part = fma(r[m], r[m], part);
+        }
+        const double sigma = block_sum_all(part, red1);
+        const double alpha = s_alpha;
+        double beta = alpha, taun = 0.0, scal = 0.0;
+        if (sigma > 1e-280) {
+            const double h2 = fma(alpha, alpha, sigma);
+            beta = -copysign(h2 * rsqrt_fast(h2), alpha);
+            taun = (beta - alpha) * rcp_fast(beta);
+            scal = rcp_fast(alpha - beta);
+        }
+#pragma unroll
+        for (int m = 0; m < KMAX_BIG; m++) {
+            const int k = tid + m * TDT;
+            if (k < n) {
+                const double v = k == jn + 1 ? 1.0 : (k >= jn + 2 ? r[m] * scal : 0.0);
+                un[k] = v;
+                if (cta == jn % C) V[(size_t)jn * ldv + k] = v;
+            }
+        }
+        if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
+        __syncthreads();
+        // fused rank-2 update (reflector jn-1) + product with reflector jn over this warp's live rows
+        double* pw = pbuf + (size_t)par * n;
+        double* rw = rowbuf + (size_t)par * n;
+        const int kbase = (jn + 1) & ~31;
+        int first = gw;
+        if (first < jn + 1) first += ((jn + 1 - first + nw - 1) / nw) * nw;
+        for (int gi = first; gi < n; gi += nw) {
+            double* Ar = A + (size_t)gi * n;
+            const bool pub = gi == jn + 1;
+            const double ui = u[gi], wi = wv[gi];          // zero while jn == 0
+            double acc0 = 0.0, acc1 = 0.0;
+            int k = kbase + lane;
+            for (; k + 96 < n; k += 128) {                  // four independent 256-byte row segments in flight
+                double a0 = __ldcg(Ar + k), a1 = __ldcg(Ar + k + 32), a2 = __ldcg(Ar + k + 64), a3 = __ldcg(Ar + k + 96);
+                if (k >= jn + 1) {
+                    a0 = fma(-wi, u[k], fma(-ui, wv[k], a0));
+                    __stcg(Ar + k, a0);
+                    acc0 = fma(a0, un[k], acc0);
+                    if (pub) __stcg(rw + k, a0);
+                }
+                a1 = fma(-wi, u[k + 32], fma(-ui, wv[k + 32], a1));
+                a2 = fma(-wi, u[k + 64], fma(-ui, wv[k + 64], a2));
+                a3 = fma(-wi, u[k + 96], fma(-ui, wv[k + 96], a3));
+                __stcg(Ar + k + 32, a1);
+                __stcg(Ar + k + 64, a2);
+                __stcg(Ar + k + 96, a3);
+                acc1 = fma(a1, un[k + 32], acc1);
+                acc0 = fma(a2, un[k + 64], acc0);
+                acc1 = fma(a3, un[k + 96], acc1);
+                if (pub) { __stcg(rw + k + 32, a1); __stcg(rw + k + 64, a2); __stcg(rw + k + 96, a3); }
+            }
+            for (; k < n; k += 32) {
+                if (k >= jn + 1) {
+                    double a0 = __ldcg(Ar + k);
+                    a0 = fma(-wi, u[k], fma(-ui, wv[k], a0));
+                    __stcg(Ar + k, a0);
+                    acc0 = fma(a0, un[k], acc0);
+                    if (pub) __stcg(rw + k, a0);
+                }
+            }
+            const double p = warp_sum(acc0 + acc1);
+            if (lane == 0) __stcg(pw + gi, p);
+        }
+        epoch++;
+        grid_barrier(ctrl, epoch * C);
         double* t = u; u = un; un = t;
         tau = taun;
     }
@@ -624,6 +782,41 @@ backtransform_kernel(const double* __restrict__ V, int ldv, const double* __rest
     }
 }
 
+// Back-transformation for n > 1024: one CTA per Ritz vector, KMAX_BIG elements per thread.
+__global__ void __launch_bounds__(TDT)
+backtransform_big_kernel(const double* __restrict__ V, int ldv, const double* __restrict__ tau_g, int n, const double* __restrict__ Zt,
+                         double* __restrict__ U, int64_t ldu) {
+    __shared__ double red[2][TDT / 32];
+    const int tid = threadIdx.x, t = blockIdx.x;
+    double z[KMAX_BIG];
+#pragma unroll
+    for (int m = 0; m < KMAX_BIG; m++) {
+        const int k = tid + m * TDT;
+        z[m] = k < n ? Zt[(size_t)t * n + k] : 0.0;
+    }
+    for (int j = n - 3; j >= 0; j--) {
+        const double tau = tau_g[j];
+        if (tau == 0.0) continue;                        // uniform
+        const double* v = V + (size_t)j * ldv;
+        double vv[KMAX_BIG];
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < KMAX_BIG; m++) {
+            const int k = tid + m * TDT;
+            vv[m] = (k > j && k < n) ? __ldg(v + k) : 0.0;
+            dot = fma(vv[m], z[m], dot);
+        }
+        dot = block_sum_all(dot, red[j & 1]) * tau;
+#pragma unroll
+        for (int m = 0; m < KMAX_BIG; m++) z[m] = fma(-dot, vv[m], z[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < KMAX_BIG; m++) {
+        const int k = tid + m * TDT;
+        if (k < n) U[(size_t)k * ldu + t] = z[m];
+    }
+}
+
 // res[t] = | T z_t - theta_t z_t |  for the Ritz pairs (rows of Z): the one check that does not depend on
 // how the vectors were obtained
 __global__ void __launch_bounds__(128)
@@ -686,7 +879,8 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     *done = false;
     if (n64 < 96 || n64 > NMAX || k64 < 1 || k64 > 128 || 2 * k64 > n64) return NDMPS_OK;
     const int n = (int)n64, m = (int)k64;
-    const int C = (n + TDT / 32 - 1) / (TDT / 32);       // one row per warp
+    const bool big = n > 1024;
+    const int C = big ? ctx->sm_count : (n + TDT / 32 - 1) / (TDT / 32);   // one row per warp, or one CTA per SM
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
@@ -728,7 +922,23 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned), ctx->stream));
 
     // 1. tridiagonalise
-    {
+    if (big) {
+        double* Awork = nullptr;                         // the reduction overwrites its matrix; G stays intact
+        NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &Awork));
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(Awork, G, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        const size_t smem_big = (size_t)3 * n * sizeof(double);
+        static std::once_flag once_big;
+        static cudaError_t rc_big = cudaSuccess;
+        std::call_once(once_big, [&]() {
+            rc_big = cudaFuncSetAttribute(tridiag_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * NMAX * sizeof(double)));
+            if (rc_big == cudaSuccess)
+                rc_big = cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NMAX * sizeof(double)));
+        });
+        NDMPS_CUDA_TRY(rc_big);
+        int n_arg = n, ldv_arg = ldv;
+        void* args[] = {&Awork, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
+        NDMPS_TRY(coop_launch(ctx, (const void*)tridiag_big_kernel, dim3(C), dim3(TDT), args, smem_big));
+    } else {
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
         void* fn = (n <= 256 && TDT <= 256) ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
@@ -779,7 +989,8 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_LAUNCH_CHECK(ctx);
     // 5. back-transform
     if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
-    else backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
+    else if (n <= 1024) backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
+    else backtransform_big_kernel<<<m, TDT, 0, ctx->stream>>>(V, ldv, tau, n, Xb, U, ldu);
     NDMPS_LAUNCH_CHECK(ctx);
     finish_kernel<<<1, 256, 0, ctx->stream>>>(G, n, hev, m, info, rr_info, res, bounds, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
@@ -803,7 +1014,7 @@ int ndmps_eigh_topk(ndmps_ctx_t* ctx, const double* a_dev, int64_t n, int64_t k,
     bool done = false;
     NDMPS_TRY(eigh_topk(ctx, a_dev, n, k, evals_dev, evecs_dev, k, &done));
     if (!done) {
-        set_error("ndmps_eigh_topk: shape n = %lld, k = %lld is outside the leading-eigenpair path (96 <= n <= 1024, 2k <= n, k <= 128)",
+        set_error("ndmps_eigh_topk: shape n = %lld, k = %lld is outside the leading-eigenpair path (96 <= n <= 4096, 2k <= n, k <= ~100)",
                   (long long)n, (long long)k);
         return NDMPS_ERR_INVALID;
     }

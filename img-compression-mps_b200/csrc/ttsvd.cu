@@ -249,7 +249,8 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     for (int64_t i = 0; i < k; i++) sv[(size_t)i] = sqrt(ev[i]);
     *n_out = k;
     *f_out = opt.renorm == 2 ? sqrt(trace / kept) : 1.0;
-    (void)evals_dev;
+    // the kept eigenvalues also on the device, where the column-side branch scales by them
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(evals_dev, out, (size_t)k * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     *capped = true;
     return NDMPS_OK;
 }
@@ -397,10 +398,17 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             { StageScope sc(ctx, ST_GRAM); NDMPS_TRY(gram(ctx, M, D, C, C, dtype, 1, G)); }
             NDMPS_TRY(ctx->ws.get<double>((size_t)C, &evals));
             NDMPS_TRY(ctx->ws.get<double>((size_t)(C * C), &V));
-            { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, G, C, evals, V, eig_tol)); }
-            NDMPS_TRY(fetch_svals(ctx, evals, C, sv));
-            int64_t n = n_keep(sv.data(), C, opt.cutoff, opt.mode, opt.max_bond);
-            double f = renorm_factor(sv.data(), C, n, opt.renorm);
+            int64_t n = 0;
+            double f = 1.0;
+            bool capped = false;
+            NDMPS_CUDA_TRY(cudaMemsetAsync(evals, 0, (size_t)C * sizeof(double), ctx->stream));
+            if (!sh) NDMPS_TRY(capped_eigh(ctx, G, C, C < D ? C : D, opt, evals, V, sv, &n, &f, &capped));
+            if (!capped) {
+                { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh(ctx, G, C, evals, V, eig_tol)); }
+                NDMPS_TRY(fetch_svals(ctx, evals, C, sv));
+                n = n_keep(sv.data(), C, opt.cutoff, opt.mode, opt.max_bond);
+                f = renorm_factor(sv.data(), C, n, opt.renorm);
+            }
             ranks_out[site] = n;
             if (svals_out)
                 for (int64_t t = 0; t < n && t < svals_stride; t++) svals_out[(int64_t)site * svals_stride + t] = sv[t] * f;

@@ -124,7 +124,7 @@ int ndmps_eigh(ndmps_ctx_t* ctx, double* a_dev, int64_t n, double* evals_dev, do
  * quimb's max_bond at core/ndmps.py:74,104-106 keeps the k largest singular triplets and only the
  * total weight of the rest).  a_dev (n x n) is NOT modified.  evals_dev: k + 2 values = k
  * eigenvalues descending, trace(a), and a health flag (0 = ok).  evecs_dev: n x k row-major,
- * column j is the j-th eigenvector.  Supported: 96 <= n <= 1024, 2k <= n, k <= ~100;
+ * column j is the j-th eigenvector.  Supported: 96 <= n <= 4096, 2k <= n, k <= ~100;
  * other shapes return NDMPS_ERR_INVALID (use ndmps_eigh). */
 int ndmps_eigh_topk(ndmps_ctx_t* ctx, const double* a_dev, int64_t n, int64_t k, double* evals_dev, double* evecs_dev);
 /* C (m x n, ldc) = alpha * A(m x k) * B(k x n) with arbitrary element strides, float64 accumulation. */

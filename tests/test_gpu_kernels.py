@@ -162,7 +162,7 @@ def _topk_check(ops, g, k, res_tol=1e-12):
     return evals, evecs
 
 
-@pytest.mark.parametrize("n,k", [(96, 16), (200, 64), (256, 64), (357, 64), (512, 64), (512, 100), (1000, 64)])
+@pytest.mark.parametrize("n,k", [(96, 16), (200, 64), (256, 64), (357, 64), (512, 64), (512, 100), (1000, 64), (1025, 64), (1536, 64), (2560, 64)])
 def test_eigh_topk_random_gram(ops, n, k):
     rng = np.random.default_rng(7 * n + k)
     a = rng.standard_normal((n, 2 * n + 3))

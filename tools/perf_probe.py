@@ -48,7 +48,7 @@ def main(which):
         from bench import synthetic_volume
         vol = torch.from_numpy(synthetic_volume((128, 128, 128), 7)).cuda().double()
         cases = []
-        for n in (256, 360, 512, 1024):
+        for n in (256, 360, 512, 1024, 1536, 2560):
             a = torch.randn(n, 4 * n, dtype=torch.float64, device="cuda", generator=g)
             cases.append((f"random n={n}", a @ a.T))
             m = vol.reshape(-1)[: (vol.numel() // n) * n].reshape(n, -1)
@@ -102,6 +102,27 @@ def main(which):
             print(f"ssim {shape}: {ms:.3f} ms ({a.numel() * 16 / ms / 1e6:.0f} GB/s algorithmic)", flush=True)
             ms = timeit(lambda: _ops.psnr_terms(a, b), reps=3, warm=1)
             print(f"psnr {shape}: {ms:.3f} ms ({a.numel() * 8 / ms / 1e6:.0f} GB/s)", flush=True)
+    if "configs" in which:
+        from imgcompressionmps.core.ndmps import NDMPS
+        from imgcompressionmps.utils.metrics import compute_psnr, compute_ssim_by_dim
+        cases = [("cfg4 fMRI subject (64,64,32,400) Std", (64, 64, 32, 400), "Std"),
+                 ("cfg5-B video chunk (1920,1080,64) DCT", (1920, 1080, 64), "DCT"),
+                 ("cfg1 image (256,256) Std chi=32", (256, 256), "Std")]
+        for name, shape, mode in cases:
+            x = torch.rand(shape, dtype=torch.float32, device="cuda", generator=g)
+            x = x * 0.1 + torch.linspace(0, 1, shape[-1], device="cuda").expand(shape)
+            chi = 32 if len(shape) == 2 else 64
+            run = lambda: NDMPS.from_tensor(x, mode=mode, max_bond=chi).to_tensor_device()
+            run(); run()
+            ctx.profile(True); ctx.stage_times(reset=True)
+            ms = timeit(run, reps=3, warm=1)
+            st = {k: round(v[0] / 4, 3) for k, v in ctx.stage_times().items() if v[1]}
+            ctx.profile(False)
+            rec = run()
+            t_ssim = timeit(lambda: compute_ssim_by_dim(rec, x), reps=3, warm=1) if len(shape) <= 4 else float("nan")
+            t_psnr = timeit(lambda: compute_psnr(rec, x), reps=3, warm=1)
+            print(f"{name}: encode+sweep+reconstruct {ms:.2f} ms ({x.numel() / ms / 1e6:.2f} Gvoxel/s) stages {st}; "
+                  f"SSIM {t_ssim:.2f} ms, PSNR {t_psnr:.2f} ms", flush=True)
     if "stages" in which:
         from imgcompressionmps.core.ndmps import NDMPS
         from bench import synthetic_volume
