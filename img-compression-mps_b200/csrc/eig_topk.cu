@@ -355,24 +355,20 @@ tridiag_big_kernel(double* __restrict__ A, int n, int ldv, double* __restrict__ 
             const double ui = u[gi], wi = wv[gi];          // zero while jn == 0
             double acc0 = 0.0, acc1 = 0.0;
             int k = kbase + lane;
-            for (; k + 96 < n; k += 128) {                  // four independent 256-byte row segments in flight
-                double a0 = __ldcg(Ar + k), a1 = __ldcg(Ar + k + 32), a2 = __ldcg(Ar + k + 64), a3 = __ldcg(Ar + k + 96);
-                if (k >= jn + 1) {
-                    a0 = fma(-wi, u[k], fma(-ui, wv[k], a0));
-                    __stcg(Ar + k, a0);
-                    acc0 = fma(a0, un[k], acc0);
-                    if (pub) __stcg(rw + k, a0);
+            for (; k + 224 < n; k += 256) {                 // eight independent 256-byte row segments in flight per warp
+                double a[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) a[q] = __ldcg(Ar + k + 32 * q);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int kk = k + 32 * q;
+                    if (q > 0 || kk >= jn + 1) {            // only the first segment can straddle the pivot column
+                        const double v = fma(-wi, u[kk], fma(-ui, wv[kk], a[q]));
+                        __stcg(Ar + kk, v);
+                        if (q & 1) acc1 = fma(v, un[kk], acc1); else acc0 = fma(v, un[kk], acc0);
+                        if (pub) __stcg(rw + kk, v);
+                    }
                 }
-                a1 = fma(-wi, u[k + 32], fma(-ui, wv[k + 32], a1));
-                a2 = fma(-wi, u[k + 64], fma(-ui, wv[k + 64], a2));
-                a3 = fma(-wi, u[k + 96], fma(-ui, wv[k + 96], a3));
-                __stcg(Ar + k + 32, a1);
-                __stcg(Ar + k + 64, a2);
-                __stcg(Ar + k + 96, a3);
-                acc1 = fma(a1, un[k + 32], acc1);
-                acc0 = fma(a2, un[k + 64], acc0);
-                acc1 = fma(a3, un[k + 96], acc1);
-                if (pub) { __stcg(rw + k + 32, a1); __stcg(rw + k + 64, a2); __stcg(rw + k + 96, a3); }
             }
             for (; k < n; k += 32) {
                 if (k >= jn + 1) {
@@ -936,8 +932,13 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
         });
         NDMPS_CUDA_TRY(rc_big);
         int n_arg = n, ldv_arg = ldv;
+        // the fused pass is bound by L2 latency per warp: as many resident warps as fit (up to 3 CTAs per SM)
+        int per_sm = 1;
+        NDMPS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_big_kernel, TDT, smem_big));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+        if (ctx->opt_topk_big_ctas > 0) per_sm = (int)ctx->opt_topk_big_ctas;
         void* args[] = {&Awork, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
-        NDMPS_TRY(coop_launch(ctx, (const void*)tridiag_big_kernel, dim3(C), dim3(TDT), args, smem_big));
+        NDMPS_TRY(coop_launch(ctx, (const void*)tridiag_big_kernel, dim3(C * per_sm), dim3(TDT), args, smem_big));
     } else {
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
