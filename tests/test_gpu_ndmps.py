@@ -108,7 +108,13 @@ def test_appendix_a4_probe_parity(NDMPS, rng):
 
 
 CASES = [((64, 64), 16, "Std"), ((256, 256), 32, "Std"), ((32, 32, 32), 16, "Std"), ((64, 64, 64), 32, "Std"),
-         ((48, 40, 36), 12, "Std"), ((16, 16, 8, 20), 8, "Std"), ((64, 64, 64), 32, "DCT"), ((30, 40, 50), 10, "DCT")]
+         ((48, 40, 36), 12, "Std"), ((16, 16, 8, 20), 8, "Std"), ((64, 64, 64), 32, "DCT"), ((30, 40, 50), 10, "DCT"),
+         # site dims [80, 40, 32, 32]: a 1280 x 1024 unfolding -> capped column-side step on a 1024 x 1024 Gram
+         ((32, 32, 16, 200), 32, "Std"),
+         # site dims [80, 40, 64, 32]: a 1280 x 2048 unfolding -> 1280 x 1280 row Gram on the L2-streamed route
+         ((64, 32, 16, 200), 32, "Std"),
+         # 128^3 at chi = 32: 256 x 256 Gram matrices on the register-resident route, column-side capped step at the end
+         ((128, 128, 128), 32, "Std")]
 
 
 @pytest.mark.parametrize("shape,chi,mode", CASES, ids=lambda v: str(v).replace(" ", ""))
