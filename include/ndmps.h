@@ -72,7 +72,15 @@ int ndmps_ctx_stage_times(ndmps_ctx_t* ctx, double* ms_out, int64_t* calls_out, 
 /* counters: "eig_flops" (rotation + factorisation flops of the bond eigensolves), "eig_calls",
  * "workspace_bytes" (arena high-water mark). */
 int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, int reset);
-/* tuning knobs, e.g. "gram_path" 0=auto 2=force SIMT, "jacobi_block" */
+/* knobs (defaults in parentheses):
+ *   "eig_topk" (1)       bond cap set: leading-eigenpair solver instead of the full one when the cap provably binds
+ *   "topk_iters" (2), "topk_passes" (8), "topk_big_ctas" (occupancy)   inverse-iteration steps, bisection passes, CTAs/SM of the n > 1024 reduction
+ *   "merge_cap" (512)    largest fused row count of a front-merged group of sites
+ *   "eig_cholesky" (1), "eig_small" (1), "chol_blocked" (1), "chol_cluster" (0), "chol_rows", "jacobi_block", "jacobi_max_sweeps" (40)
+ *   "gram_path", "gemm_path" (0 = FP64 tensor pipe when the shape allows, 2 = SIMT only), "permute_path" (0 tiles, 3 bulk copies, 2 gather), "permute_ctas" (64)
+ *   "blocking_sync" (0)  host waits sleep on a blocking event instead of spinning (more waiting host threads than cores)
+ *   "verbose" (0)
+ * A context belongs to one host thread; several contexts (one per thread, each with its own stream) may run concurrently. */
 int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value);
 
 /* ---- K1: N-D volume <-> interleaved MPS site order ----------------------
