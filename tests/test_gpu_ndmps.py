@@ -319,3 +319,26 @@ def test_volume_pipeline_matches_sequential(NDMPS):
     for (bonds, rec), dst, (_, ranks) in zip(seq, host_dst, res):
         assert ranks == bonds
         assert np.array_equal(dst, rec.cpu().numpy())
+
+
+def test_volume_pipeline_blocking_waits_and_errors(NDMPS):
+    """Sleeping waits (oversubscribed hosts) give the same bits; an exception in one item surfaces in the
+    caller and does not wedge the workers."""
+    from imgcompressionmps.batch import VolumePipeline
+    vols = [torch.from_numpy(phantom((64, 64, 64), seed=60 + i, background=0.01).astype(np.float32)).cuda() for i in range(4)]
+    ref = [NDMPS.from_tensor(v, max_bond=16).to_tensor_device().clone() for v in vols]
+    with VolumePipeline(workers=2, blocking_sync=True) as pipe:
+        assert pipe.blocking_sync
+        out = pipe.roundtrip(vols, max_bond=16)
+        for (obj, got), want in zip(out, ref):
+            assert torch.equal(got, want)
+
+        def boom(v):
+            if v is vols[1]:
+                raise RuntimeError("item failed")
+            return float(v.sum())
+
+        with pytest.raises(RuntimeError, match="item failed"):
+            pipe.map(boom, vols)
+        again = pipe.map(lambda v: float(v.sum()), vols)          # the pool still works
+        assert again == [float(v.sum()) for v in vols]
