@@ -727,7 +727,7 @@ int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void*
     void *vol = nullptr, *dense = nullptr;
     NDMPS_TRY(ctx->ws.alloc((size_t)N * esz, &vol));
     NDMPS_TRY(ctx->ws.alloc((size_t)N * esz, &dense));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(vol, src_host, (size_t)N * esz, cudaMemcpyHostToDevice, ctx->stream));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(vol, src_host, (size_t)N * esz, cudaMemcpyDefault, ctx->stream));
     NDMPS_TRY(permute(ctx, plan, false, vol, dense, dtype, 1.0));
     // core capacities from the bond bounds min(max_bond, prod left, prod right)
     std::vector<int64_t> bound((size_t)(L > 1 ? L - 1 : 0)), cap((size_t)L), ranks((size_t)(L > 1 ? L - 1 : 1));
@@ -755,7 +755,7 @@ int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void*
         for (int i = 0; i < L - 1; i++) ranks_out_host[i] = ranks[(size_t)i];
     NDMPS_TRY(contract_dense(ctx, (const void* const*)cores.data(), dtype, L, plan->site_dims, ranks.data(), dense));
     NDMPS_TRY(permute(ctx, plan, true, dense, vol, dtype, 1.0));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDefault, ctx->stream));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     return NDMPS_OK;
 }
