@@ -212,6 +212,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* g_dev, int64_t n, int64_t k, double*
 // its grid needs (grid / resident CTAs per SM) in a process-wide gate and gives them back from a
 // stream callback when the kernel has finished; a launch that does not fit waits on the host.
 int coop_launch(ndmps_ctx* ctx, const void* fn, dim3 grid, dim3 block, void** args, size_t smem);
+int minmax_device(ndmps_ctx* ctx, const void* x, int64_t n, int dtype, double* out_dev2);
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);
 
 #ifdef __CUDACC__

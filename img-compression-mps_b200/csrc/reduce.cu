@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const Q* __restrict__ q
     }
 }
 
+// {min, max} of one device array into out_dev2 (device), for callers inside the library
+int minmax_device(ndmps_ctx* ctx, const void* x, int64_t n, int dtype, double* out_dev2) {
+    return reduce_dispatch<1>(ctx, x, nullptr, n, dtype, out_dev2);
+}
+
 }  // namespace ndmps
 
 using namespace ndmps;

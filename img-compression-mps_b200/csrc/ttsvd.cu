@@ -716,7 +716,8 @@ int ndmps_overlap(ndmps_ctx_t* ctx, const void* const* cores_a, const int64_t* r
 }
 
 int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void* src_host, void* dst_host, int dtype,
-                         double cutoff, int cutoff_mode, int64_t max_bond, int renorm, int64_t* ranks_out_host) {
+                         double cutoff, int cutoff_mode, int64_t max_bond, int renorm, int64_t* ranks_out_host,
+                         double* norm_out_host, double* boundaries_out_host) {
     NDMPS_REQUIRE(ctx && plan && src_host && dst_host, "ndmps_roundtrip_host: NULL argument");
     NDMPS_REQUIRE(dtype_ok(dtype), "ndmps_roundtrip_host: bad dtype");
     NDMPS_REQUIRE(cutoff_mode >= NDMPS_CUT_ABS && cutoff_mode <= NDMPS_CUT_RSUM1, "ndmps_roundtrip_host: bad cutoff_mode %d", cutoff_mode);
@@ -753,10 +754,27 @@ int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void*
     NDMPS_TRY(ttsvd(ctx, dense, dtype, L, plan->site_dims, opt, cores.data(), cap.data(), ranks.data(), nullptr, 0));
     if (ranks_out_host)
         for (int i = 0; i < L - 1; i++) ranks_out_host[i] = ranks[(size_t)i];
+    // boundary list and norm of the MPS, as from_tensor keeps them (core/ndmps.py:75-76, 80-86)
+    double* extras = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>(2 * (size_t)L + 2, &extras));
+    {
+        StageScope sc(ctx, ST_GLUE);
+        for (int i = 0; i < L; i++) {
+            const int64_t l = i == 0 ? 1 : ranks[(size_t)i - 1], r = i == L - 1 ? 1 : ranks[(size_t)i];
+            NDMPS_TRY(minmax_device(ctx, cores[(size_t)i], l * plan->site_dims[i] * r, dtype, extras + 2 * i));
+        }
+        NDMPS_TRY(overlap(ctx, (const void* const*)cores.data(), ranks.data(), dtype, (const void* const*)cores.data(), ranks.data(),
+                          dtype, L, plan->site_dims, extras + 2 * L));
+    }
     NDMPS_TRY(contract_dense(ctx, (const void* const*)cores.data(), dtype, L, plan->site_dims, ranks.data(), dense));
     NDMPS_TRY(permute(ctx, plan, true, dense, vol, dtype, 1.0));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDefault, ctx->stream));
+    NDMPS_TRY(ensure_pinned(ctx, 2 * (size_t)L + 2));
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, extras, (2 * (size_t)L + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NDMPS_CUDA_TRY(stream_wait(ctx));
+    if (boundaries_out_host)
+        for (int i = 0; i < 2 * L; i++) boundaries_out_host[i] = ctx->pinned[i];
+    if (norm_out_host) *norm_out_host = ctx->pinned[2 * L] > 0.0 ? sqrt(ctx->pinned[2 * L]) : 0.0;
     return NDMPS_OK;
 }
 

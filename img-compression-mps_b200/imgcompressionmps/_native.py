@@ -70,7 +70,7 @@ PROTOTYPES = {
     "ndmps_dequantize": (ci, [vp, vp, i64, ci, f64, f64, ci, vp]),
     "ndmps_ssim": (ci, [vp, vp, vp, ci, ci, p_i64, p_f64]),
     "ndmps_ssim_slices": (ci, [vp, vp, vp, ci, p_i64, ci, p_f64]),
-    "ndmps_roundtrip_host": (ci, [vp, vp, vp, vp, ci, f64, ci, i64, ci, p_i64]),
+    "ndmps_roundtrip_host": (ci, [vp, vp, vp, vp, ci, f64, ci, i64, ci, p_i64, p_f64, p_f64]),
 }
 
 

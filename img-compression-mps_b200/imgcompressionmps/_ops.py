@@ -385,9 +385,10 @@ def ssim_slices(a, b, axis: int) -> np.ndarray:
 
 
 # ---- host-buffer end-to-end entry ---------------------------------------------------
-def roundtrip_host(src: np.ndarray, max_bond=None, cutoff=1e-10, cutoff_mode="rsum2", renorm=None, out=None):
+def roundtrip_host(src: np.ndarray, max_bond=None, cutoff=1e-10, cutoff_mode="rsum2", renorm=None, out=None, extras=None):
     """NDMPS.from_tensor(src, max_bond=...).to_tensor() in ONE C-ABI call on host buffers
-    (H2D, encode, sweep, contract, decode, D2H).  Returns (reconstruction, ranks)."""
+    (H2D, encode, sweep, boundary list + norm, contract, decode, D2H).  Returns (reconstruction, ranks);
+    a dict passed as ``extras`` receives ``norm`` and ``boundary_list``."""
     if src.dtype not in (np.float32, np.float64):
         raise ValueError("roundtrip_host expects a float32 or float64 array")
     src = np.ascontiguousarray(src)
@@ -399,7 +400,13 @@ def roundtrip_host(src: np.ndarray, max_bond=None, cutoff=1e-10, cutoff_mode="rs
         out = np.empty_like(src)
     ranks = (C.c_int64 * max(plan.levels - 1, 1))()
     code = N.F32 if src.dtype == np.float32 else N.F64
+    norm = C.c_double(0.0)
+    bounds = np.zeros((plan.levels, 2), dtype=np.float64)
     N.check(N.load_library().ndmps_roundtrip_host(N.handle(), plan.handle, src.ctypes.data_as(C.c_void_p),
                                                   out.ctypes.data_as(C.c_void_p), code, float(cutoff), mode,
-                                                  int(max_bond or 0), int(renorm), ranks), "ndmps_roundtrip_host")
+                                                  int(max_bond or 0), int(renorm), ranks, C.byref(norm),
+                                                  bounds.ctypes.data_as(N.p_f64)), "ndmps_roundtrip_host")
+    if extras is not None:
+        extras["norm"] = norm.value
+        extras["boundary_list"] = bounds
     return out, [int(r) for r in ranks][:plan.levels - 1]

@@ -221,10 +221,13 @@ int ndmps_ssim_slices(ndmps_ctx_t* ctx, const void* a, const void* b, int dtype,
                       double* scores_out_host);
 
 /* ---- whole path on HOST buffers (the e2e measurement entry) --------------------
- * NDMPS.from_tensor(x).to_tensor() with the max_bond / cutoff extension:
- * H2D copy, encode, sweep, contract, decode, D2H copy.  ranks_out_host: L-1. */
+ * NDMPS.from_tensor(x).to_tensor() with the max_bond / cutoff extension (core/ndmps.py:36-78, 131-153):
+ * H2D copy, encode, sweep, boundary list + norm of the MPS (core/ndmps.py:75-76), contract, decode,
+ * D2H copy.  ranks_out_host: L-1 values.  Optional: norm_out_host (1 value, sqrt(<mps|mps>)),
+ * boundaries_out_host (2 L values: min, max of every core).  src / dst may also be device pointers. */
 int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void* src_host, void* dst_host, int dtype,
-                         double cutoff, int cutoff_mode, int64_t max_bond, int renorm, int64_t* ranks_out_host);
+                         double cutoff, int cutoff_mode, int64_t max_bond, int renorm, int64_t* ranks_out_host,
+                         double* norm_out_host, double* boundaries_out_host);
 
 #ifdef __cplusplus
 }

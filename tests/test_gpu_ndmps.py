@@ -234,9 +234,13 @@ def test_api_surface(NDMPS):
 def test_roundtrip_host_entry():
     from imgcompressionmps import _ops
     x = phantom((64, 64, 64), seed=5).astype(np.float32)
-    rec, ranks = _ops.roundtrip_host(x, max_bond=16)
+    extras = {}
+    rec, ranks = _ops.roundtrip_host(x, max_bond=16, extras=extras)
     o = OracleNDMPS.from_tensor(x, max_bond=16)
     assert ranks == o.bond_sizes()
+    assert extras["norm"] == pytest.approx(o.norm_value, rel=1e-5)
+    assert extras["boundary_list"].shape == (len(o.bond_sizes()) + 1, 2)
+    assert np.all(extras["boundary_list"][:, 0] <= extras["boundary_list"][:, 1])
     ro = o.to_tensor()
     assert np.linalg.norm(rec - ro) / np.linalg.norm(ro) < 1e-5
 
