@@ -189,3 +189,30 @@ def _sharded_sweep_worker(rank, world, port, out_dir):
 def test_two_rank_gloo_sharded_sweep(tmp_path):
     mp.spawn(_sharded_sweep_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert np.array_equal(np.load(tmp_path / "bonds0.npy"), np.load(tmp_path / "bonds1.npy"))
+
+
+def test_shard_partition_random_shapes():
+    """Every voxel lands in exactly one rank's sub-lattice, for every world size the last level admits."""
+    from imgcompressionmps.distributed import last_level_split, place_shard, shard_volume
+    from imgcompressionmps.utils.core import get_factorlist
+    rng = np.random.default_rng(11)
+    primes = [2, 2, 2, 3, 5]
+    for _ in range(12):
+        ndim = int(rng.integers(1, 5))
+        shape = tuple(int(np.prod(rng.choice(primes, size=int(rng.integers(1, 4))))) for _ in range(ndim))
+        factors, _ = get_factorlist(shape)
+        d_last = int(np.prod(factors[-1]))
+        x = rng.random(shape)
+        for world in range(1, d_last + 1):
+            try:
+                last_level_split(factors, world)
+            except ValueError:
+                continue
+            seen = np.zeros(shape, dtype=np.int64)
+            full = np.zeros(shape)
+            for r in range(world):
+                place_shard(seen, shard_volume(np.ones(shape, dtype=np.int64), factors, r, world) + shard_volume(seen, factors, r, world),
+                            factors, r, world)
+                place_shard(full, shard_volume(x, factors, r, world), factors, r, world)
+            assert np.array_equal(seen, np.ones(shape, dtype=np.int64)), (shape, world)
+            assert np.array_equal(full, x)
