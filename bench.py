@@ -46,7 +46,7 @@ for _p in (str(ROOT), str(ROOT / "img-compression-mps_b200")):
 METRIC = "ndmps_encode_truncate_reconstruct_voxels_per_s"
 UNIT = "voxels/s"
 WORKLOADS = {
-    "cfg2": {"shape": (256, 256, 256), "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume", "in_flight": 8},
+    "cfg2": {"shape": (256, 256, 256), "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume", "in_flight": 12},
     "cfg3": {"shape": (512, 512, 512), "name": "configs[2]: 512x512x512 fp32 synthetic volume (north-star target)", "in_flight": 4},
 }
 CPU_SAMPLE_SHAPE = (128, 128, 128)
