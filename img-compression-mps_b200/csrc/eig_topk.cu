@@ -98,7 +98,7 @@ __device__ unsigned long long g_prof[8];
 // V row j = reflector j (unit at j+1, zero before), H_j = I - tau_j v_j v_j^T.
 // ---------------------------------------------------------------------------------------------
 template <int NEQ>
-__global__ void __launch_bounds__(TDT, 2)
+__global__ void __launch_bounds__(TDT)
 tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
                double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
     __shared__ double ub0[32 * NEQ], ub1[32 * NEQ], wv[32 * NEQ];
