@@ -636,6 +636,31 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
         for (int e = tid; e < m * m; e += 128) Linv[e] = (e / m == e % m) ? 1.0 : 0.0;
         return;
     }
+    const int big = __syncthreads_or(dev > 1e-5 ? 1 : 0);
+    if (!big) {
+        // nearly orthonormal (the usual case: well separated eigenvalues): symmetric orthogonalisation by the
+        // series S^-1/2 = I - E/2 + 3/8 E^2 - 5/16 E^3 + O(E^4), E = S - I, |E| <= 1e-5 -> error ~1e-20.
+        // No sequential factorisation; any orthonormal basis of the span serves the Rayleigh-Ritz step.
+        for (int e = tid; e < m * m; e += 128) {
+            const int r = e / m, c = e - r * m;
+            if (r == c) Lm[r * ld + c] -= 1.0;           // Lm = E
+        }
+        __syncthreads();
+        for (int e = tid; e < m * m; e += 128) {          // Y = E^2
+            const int r = e / m, c = e - r * m;
+            double acc = 0.0;
+            for (int q = 0; q < m; q++) acc = fma(Lm[r * ld + q], Lm[q * ld + c], acc);
+            Y[r * ld + c] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < m * m; e += 128) {          // Linv = I - E/2 + 3/8 E^2 - 5/16 E E^2
+            const int r = e / m, c = e - r * m;
+            double acc = 0.0;
+            for (int q = 0; q < m; q++) acc = fma(Lm[r * ld + q], Y[q * ld + c], acc);
+            Linv[e] = (r == c ? 1.0 : 0.0) - 0.5 * Lm[r * ld + c] + 0.375 * Y[r * ld + c] - 0.3125 * acc;
+        }
+        return;
+    }
     for (int j = tid; j < m; j += 128) diag0[j] = fabs(Lm[j * ld + j]);
     __syncthreads();
     const int r = tid;
