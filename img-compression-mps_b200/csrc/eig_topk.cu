@@ -97,7 +97,7 @@ __device__ unsigned long long g_prof[8];
 // pivot row, and meets the others at the barrier.  One barrier per column.
 // V row j = reflector j (unit at j+1, zero before), H_j = I - tau_j v_j v_j^T.
 // ---------------------------------------------------------------------------------------------
-template <int NEQ>
+template <int NEQ, int RPW>
 __global__ void __launch_bounds__(TDT)
 tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
                double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
@@ -106,12 +106,18 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
     __shared__ double s_alpha;
     constexpr int KM = (32 * NEQ) / TDT > 0 ? (32 * NEQ) / TDT : 1;                 // vector elements per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
-    const int gi = warp * C + cta;                       // this warp's row, held in registers: lane l has columns l + 32 q
-    double a[NEQ];
+    // this warp's RPW rows, held in registers: lane l has columns l + 32 q.  Row t of the warp is row
+    // (t * warps + warp) * C + cta of the matrix (cyclic over CTAs first, so live rows stay spread to the end)
+    int gi[RPW];
+    double a[RPW][NEQ];
 #pragma unroll
-    for (int q = 0; q < NEQ; q++) {
-        const int k = lane + 32 * q;
-        a[q] = (gi < n && k < n) ? G[(size_t)gi * n + k] : 0.0;
+    for (int t = 0; t < RPW; t++) {
+        gi[t] = (t * (TDT / 32) + warp) * C + cta;
+#pragma unroll
+        for (int q = 0; q < NEQ; q++) {
+            const int k = lane + 32 * q;
+            a[t][q] = (gi[t] < n && k < n) ? G[(size_t)gi[t] * n + k] : 0.0;
+        }
     }
     for (int c = tid; c < 32 * NEQ; c += TDT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
     double* u = ub0;
@@ -172,10 +178,13 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         if (jn == n - 2) {                               // last 2 x 2 block: no reflector left
             __syncthreads();
             if (cta == 0 && tid == 0) { e_g[jn] = s_alpha; tau_g[jn] = 0.0; }
-            if (gi == n - 1) {
 #pragma unroll
-                for (int q = 0; q < NEQ; q++)
-                    if (lane + 32 * q == n - 1) d_g[n - 1] = a[q] - (jn > 0 ? 2.0 * u[n - 1] * wv[n - 1] : 0.0);
+            for (int t = 0; t < RPW; t++) {
+                if (gi[t] == n - 1) {
+#pragma unroll
+                    for (int q = 0; q < NEQ; q++)
+                        if (lane + 32 * q == n - 1) d_g[n - 1] = a[t][q] - (jn > 0 ? 2.0 * u[n - 1] * wv[n - 1] : 0.0);
+                }
             }
             break;
         }
@@ -206,28 +215,43 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
         __syncthreads();
         PROF_MARK(4);
-        // fused rank-2 update (reflector jn-1) + product with reflector jn, this warp's row, columns >= jn+1
-        if (gi >= jn + 1 && gi < n) {
+        // fused rank-2 update (reflector jn-1) + product with reflector jn, this warp's rows, columns >= jn+1
+        {
             double* pw = pbuf + (size_t)par * n;
             double* rw = rowbuf + (size_t)par * n;
-            const bool pub = gi == jn + 1;
-            const double ui = u[gi], wi = wv[gi];        // zero while jn == 0
             const int q0 = (jn + 1) >> 5;
-            double acc0 = 0.0, acc1 = 0.0;
+            double acc[RPW];
+            bool live[RPW];
 #pragma unroll
-            for (int q = 0; q < NEQ; q++) {
-                const int k = lane + 32 * q;
-                if (q >= q0 && k >= jn + 1 && k < n) {
-                    double v = a[q];
-                    v = fma(-ui, wv[k], v);
-                    v = fma(-wi, u[k], v);
-                    a[q] = v;
-                    if (q & 1) acc1 = fma(v, un[k], acc1); else acc0 = fma(v, un[k], acc0);
-                    if (pub) __stcg(rw + k, v);
+            for (int t = 0; t < RPW; t++) {
+                live[t] = gi[t] >= jn + 1 && gi[t] < n;
+                acc[t] = 0.0;
+                if (live[t]) {
+                    const bool pub = gi[t] == jn + 1;
+                    const double ui = u[gi[t]], wi = wv[gi[t]];   // zero while jn == 0
+                    double acc1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NEQ; q++) {
+                        const int k = lane + 32 * q;
+                        if (q >= q0 && k >= jn + 1 && k < n) {
+                            double v = a[t][q];
+                            v = fma(-ui, wv[k], v);
+                            v = fma(-wi, u[k], v);
+                            a[t][q] = v;
+                            if (q & 1) acc1 = fma(v, un[k], acc1); else acc[t] = fma(v, un[k], acc[t]);
+                            if (pub) __stcg(rw + k, v);
+                        }
+                    }
+                    acc[t] += acc1;
                 }
             }
-            const double p = warp_sum(acc0 + acc1);
-            if (lane == 0) __stcg(pw + gi, p);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)              // the RPW reductions interleaved
+#pragma unroll
+                for (int t = 0; t < RPW; t++) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+#pragma unroll
+            for (int t = 0; t < RPW; t++)
+                if (live[t] && lane == 0) __stcg(pw + gi[t], acc[t]);
         }
         PROF_MARK(5);
         epoch++;
@@ -904,7 +928,10 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     if (n64 < 96 || n64 > NMAX || k64 < 1 || k64 > 128 || 2 * k64 > n64) return NDMPS_OK;
     const int n = (int)n64, m = (int)k64;
     const bool big = n > 1024;
-    const int C = big ? ctx->sm_count : (n + TDT / 32 - 1) / (TDT / 32);   // one row per warp, or one CTA per SM
+    // register route: RPW rows per warp.  Two rows per warp up to n = 512 (the row pair still fits the register
+    // file) halve the SMs a reduction sits on, which is what the other volumes in flight need
+    const int rpw = (n <= 512 && !ctx->opt_topk_one_row) ? 2 : 1;
+    const int C = big ? ctx->sm_count : (n + rpw * (TDT / 32) - 1) / (rpw * (TDT / 32));
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
@@ -970,7 +997,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     } else {
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
-        void* fn = (n <= 256 && TDT <= 256) ? (void*)tridiag_kernel<8> : (n <= 512 ? (void*)tridiag_kernel<16> : (void*)tridiag_kernel<32>);
+        void* fn = n <= 512 ? (rpw == 2 ? (void*)tridiag_kernel<16, 2> : (void*)tridiag_kernel<16, 1>) : (void*)tridiag_kernel<32, 1>;
         NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
 #ifdef NDMPS_TOPK_PROF
         {
