@@ -88,9 +88,11 @@ __device__ unsigned long long g_prof[8];
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// 1. Householder tridiagonalisation.  Rows are dealt cyclically to the warps of the grid (row i
-// lives in warp i / C of CTA i mod C, in REGISTERS, full rows: the symmetric half is not
-// exploited, the 2x flops are free next to the barrier).  Per column jn every CTA redundantly derives, from the partial
+// 1. Householder tridiagonalisation.  Rows are dealt cyclically to the CTAs and then to their warps,
+// RPW rows per warp, in REGISTERS (full rows: the symmetric half is not exploited, the 2x flops are
+// free next to the barrier).  RPW = 2 up to n = 512: 16 CTAs x 512 threads x 128 registers, so a
+// reduction owns its SMs outright and leaves all the others to the kernels of the volumes running
+// beside it (see profiles/r01_summary.md, "Interference between volumes in flight").  Per column jn every CTA redundantly derives, from the partial
 // products p = A u and the pivot row that were published before the barrier, the vector w of
 // the rank-2 update of the PREVIOUS reflector and the NEXT reflector u'; then one fused pass
 // over its rows applies A -= u w^T + w u^T and accumulates p' = A u', publishes p' and the next
