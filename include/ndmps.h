@@ -75,6 +75,7 @@ int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, in
 /* knobs (defaults in parentheses):
  *   "eig_topk" (1)       bond cap set: leading-eigenpair solver instead of the full one when the cap provably binds
  *   "topk_iters" (2), "topk_passes" (8), "topk_big_ctas" (occupancy)   inverse-iteration steps, bisection passes, CTAs/SM of the n > 1024 reduction
+ *   "topk_one_row" (0)   one matrix row per warp in the register-resident reduction (faster alone, worse beside other volumes)
  *   "merge_cap" (512)    largest fused row count of a front-merged group of sites
  *   "eig_cholesky" (1), "eig_small" (1), "chol_blocked" (1), "chol_cluster" (0), "chol_rows", "jacobi_block", "jacobi_max_sweeps" (40)
  *   "gram_path", "gemm_path" (0 = FP64 tensor pipe when the shape allows, 2 = SIMT only), "permute_path" (0 tiles, 3 bulk copies, 2 gather), "permute_ctas" (64)
