@@ -1,0 +1,120 @@
+"""The reference's cutoff sweep on device-resident data.
+
+Mirrors the three functions of ``evaluation/benchmark.py`` that sit directly on the NDMPS path --
+``compress_list`` (:103-118), ``benchmark_metric`` (:121-146) and ``run_benchmark`` (:149-194) --
+with the same names, arguments, result keys and post-processing, so the reference's callers
+(``run_full_benchmark``, the notebook) can import them unchanged.  What differs is how the work
+is issued: the original tensors are put on the device once, every (tensor, cutoff) pair is
+reconstructed ONCE and that reconstruction serves both SSIM and PSNR (the reference calls
+``to_tensor()`` per metric), nothing but scalars comes back to the host, and the tensors of a
+list are independent, so they run several at a time (``batch.VolumePipeline``).  File loading,
+plotting and result files stay out."""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from ..utils.metrics import compute_overlap, compute_psnr, compute_ssim_by_dim
+
+_METRICS = ("ssim", "compression_ratio", "bond_dims", "psnr", "fidelity", "storage", "gzip_bytes", "gzip_ratio")
+
+
+def compress_list(mps_list, compression_factors):
+    """``mps.compress(compression_factors)`` for every item, in place (``benchmark.py:103-118``)."""
+    if compression_factors is None:
+        raise ValueError("compression_factors must not be None")
+    for mps in mps_list:
+        mps.compress(compression_factors)
+
+
+def _one_metric(mps, ref, metric: str, dtype, rec=None):
+    if metric == "compression_ratio":
+        return mps.compression_ratio()
+    if metric == "storage":
+        return mps.get_storage_space(dtype)
+    if metric == "gzip_bytes":
+        return mps.get_bytesize_on_disk(dtype=dtype)
+    if metric == "gzip_ratio":
+        return mps.compression_ratio_on_disk(dtype=dtype, replace=True)       # replace=True as the reference does
+    if metric == "ssim":
+        return compute_ssim_by_dim(mps.to_tensor_device() if rec is None else rec, ref)
+    if metric == "psnr":
+        return compute_psnr(mps.to_tensor_device() if rec is None else rec, ref)
+    if metric == "bond_dims":
+        return mps.bond_sizes()
+    if metric == "shape":
+        return ref.shape
+    if metric == "fidelity":
+        return compute_overlap(mps, ref)
+    raise ValueError(f"Unsupported metric: {metric}")
+
+
+def benchmark_metric(mps_list, reference_list=None, metric: str = "compression_ratio", dtype=np.uint16):
+    """One metric for every item of ``mps_list`` (``benchmark.py:121-146``)."""
+    if metric not in _METRICS + ("shape",):
+        raise ValueError(f"Unsupported metric: {metric}")
+    if reference_list and len(reference_list) != len(mps_list):
+        raise IndexError("Length mismatch: reference_list and mps_list must have the same length.")
+    return [_one_metric(mps, reference_list[i] if reference_list else None, metric, dtype) for i, mps in enumerate(mps_list)]
+
+
+def _to_device(x):
+    import torch
+    if isinstance(x, torch.Tensor):
+        return x if x.is_cuda else x.cuda()
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _level(item, dtype):
+    """All metrics of one tensor at the current compression level; one reconstruction shared by SSIM and PSNR."""
+    mps, original, reference_mps = item
+    rec = mps.to_tensor_device()
+    out = {"ssim": float(compute_ssim_by_dim(rec, original)), "psnr": float(compute_psnr(rec, original))}
+    del rec
+    for name in ("compression_ratio", "bond_dims", "fidelity", "storage", "gzip_bytes", "gzip_ratio"):   # the reference's order
+        out[name] = _one_metric(mps, reference_mps if name == "fidelity" else None, name, dtype)
+    return out
+
+
+def run_benchmark(mps_list, original_tensors_list, cutoff_list, *, workers: Optional[int] = None, dtype=np.uint16) -> Dict:
+    """Metrics of every tensor before compression and after each cutoff of ``cutoff_list`` (cumulative, in place),
+    in the reference's result layout (``benchmark.py:149-194``): per metric an array ``[tensor][level]``
+    (``bond_dims`` stays ``[level][tensor]``)."""
+    if len(original_tensors_list) != len(mps_list):
+        raise IndexError("Length mismatch: reference_list and mps_list must have the same length.")
+    originals = [_to_device(t) for t in original_tensors_list]
+    original_mps_list = deepcopy(mps_list)
+    results: Dict[str, List] = {name: [] for name in _METRICS}
+    pipe = None
+    if workers is None:
+        workers = min(4, len(mps_list))
+    if workers > 1:
+        from ..batch import VolumePipeline
+        pipe = VolumePipeline(workers=workers)
+    try:
+        items = list(zip(mps_list, originals, original_mps_list))
+
+        def measure():
+            rows = pipe.map(lambda it: _level(it, dtype), items) if pipe else [_level(it, dtype) for it in items]
+            for name in _METRICS:
+                results[name].append([row[name] for row in rows])
+
+        measure()
+        for i, cutoff in enumerate(cutoff_list):
+            print(f"Status: {100 * (i + 1) / len(cutoff_list):.2f}% - Cutoff: {cutoff}")
+            if pipe:
+                pipe.map(lambda mps: mps.compress(cutoff), mps_list)
+            else:
+                compress_list(mps_list, cutoff)
+            measure()
+    finally:
+        if pipe:
+            pipe.close()
+    for key in results:
+        if not results[key] or not results[key][0]:
+            results[key] = []
+        elif key != "bond_dims" and isinstance(results[key][0], (list, np.ndarray)) and np.ndim(results[key][0]) > 0:
+            results[key] = np.array(results[key]).T
+    return results

@@ -346,3 +346,49 @@ def test_volume_pipeline_blocking_waits_and_errors(NDMPS):
             pipe.map(boom, vols)
         again = pipe.map(lambda v: float(v.sum()), vols)          # the pool still works
         assert again == [float(v.sum()) for v in vols]
+
+
+# ---- the reference's cutoff sweep (evaluation/benchmark.py:149-194) on the device -----------------------
+def test_run_benchmark_matches_the_oracle_loop(NDMPS, capsys):
+    from imgcompressionmps.evaluation.benchmark import benchmark_metric, run_benchmark
+    vols = [phantom((32, 32, 32), seed=70 + i, background=0.01) for i in range(3)]
+    cutoffs = [0.02, 0.1]
+    res = run_benchmark([NDMPS.from_tensor(v) for v in vols], vols, cutoffs, workers=2)
+    assert "Cutoff: 0.1" in capsys.readouterr().out
+    # the same loop on the oracle
+    want = {k: [] for k in ("ssim", "compression_ratio", "bond_dims", "psnr", "fidelity", "storage")}
+    objs = [OracleNDMPS.from_tensor(v) for v in vols]
+    refs = copy.deepcopy(objs)
+    for level in [None] + cutoffs:
+        if level is not None:
+            for o in objs:
+                o.compress(level)
+        recs = [o.to_tensor() for o in objs]
+        want["ssim"].append([OM.compute_ssim_by_dim(r, v) for r, v in zip(recs, vols)])
+        want["psnr"].append([OM.compute_psnr(r, v) for r, v in zip(recs, vols)])
+        want["compression_ratio"].append([o.compression_ratio() for o in objs])
+        want["bond_dims"].append([o.bond_sizes() for o in objs])
+        want["fidelity"].append([OM.compute_overlap(o.cores, o.norm_value, r.cores, r.norm_value) for o, r in zip(objs, refs)])
+        want["storage"].append([o.get_storage_space(np.uint16) for o in objs])
+        for o in objs:                                   # the reference's gzip_ratio metric quantises the cores IN PLACE
+            o.compression_ratio_on_disk(np.uint16, replace=True)
+    assert res["bond_dims"] == want["bond_dims"]
+    assert res["ssim"].shape == (3, 3) and res["gzip_ratio"].shape == (3, 3)
+    assert np.array_equal(res["compression_ratio"], np.array(want["compression_ratio"]).T)
+    assert np.array_equal(res["storage"], np.array(want["storage"]).T)
+    # levels 0 and 1 see at most one in-place uint16 quantisation of cores that are still close to lossless: 1e-4.
+    # From level 2 on the cores were quantised in the library's gauge (core values differ from the oracle's by the usual
+    # sign / rotation freedom, so the 1.5e-5 quantisation noise differs) and then truncated hard: agreement ~1e-3
+    # ("tolerance depends on gauge").
+    for key in ("ssim", "fidelity"):
+        got, ref = res[key], np.array(want[key]).T
+        assert np.allclose(got[:, :2], ref[:, :2], rtol=0, atol=1e-4), key
+        assert np.allclose(got[:, 2:], ref[:, 2:], rtol=0, atol=3e-3), key
+    got, ref = res["psnr"], np.array(want["psnr"]).T                               # dB
+    assert np.all(got[:, 0] > 120) and np.all(ref[:, 0] > 120)                         # lossless level: rounding noise only
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=0, atol=1e-2) and np.allclose(got[:, 2:], ref[:, 2:], rtol=0, atol=5e-2)
+    assert np.all(res["gzip_bytes"] > 0) and np.all(np.diff(res["compression_ratio"], axis=1) <= 0)
+    with pytest.raises(ValueError):
+        benchmark_metric([], metric="nope")
+    with pytest.raises(IndexError):
+        run_benchmark([NDMPS.from_tensor(vols[0])], vols, cutoffs)
