@@ -24,111 +24,13 @@ struct SliceFamily {
     int win;          // window (odd)
 };
 
-constexpr int TILE_W = 32, TILE_H = 16, MAXWIN = 7;
+constexpr int TILE_W = 32, TILE_H = 32, MAXWIN = 7;
 constexpr int PATCH_W = TILE_W + MAXWIN - 1, PATCH_H = TILE_H + MAXWIN - 1;
 
 __device__ __forceinline__ int64_t slice_base(const SliceFamily& f, int64_t s) {
     int64_t i = s / f.nT, t = s - i * f.nT;
     return i * f.s_axis + t * f.s_t;
 }
-
-// one CTA per slice: R = max(max a, max clip(b)) - min(min a, min clip(b))   (metrics.py:23-24)
-template <class T>
-__global__ void __launch_bounds__(256) ssim_range_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
-                                                          double* __restrict__ range) {
-    __shared__ double scratch[32];
-    const int64_t s = blockIdx.x;
-    const int64_t base = slice_base(f, s);
-    double lo = INFINITY, hi = -INFINITY;
-    const int64_t total = f.H * f.W;
-    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
-        int64_t h = e / f.W, w = e - h * f.W;
-        int64_t off = base + h * f.sh + w * f.sw;
-        double x = (double)a[off];
-        double y = fmax((double)b[off], 0.0);
-        lo = fmin(lo, fmin(x, y));
-        hi = fmax(hi, fmax(x, y));
-    }
-    lo = block_min(lo, scratch);
-    hi = block_max(hi, scratch);
-    if (threadIdx.x == 0) range[s] = hi - lo;
-}
-
-template <class T>
-__global__ void __launch_bounds__(256)
-ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
-                 int tiles_y, int tiles_x, double* __restrict__ partial) {
-    __shared__ T pa[PATCH_H][PATCH_W + 1];
-    __shared__ T pb[PATCH_H][PATCH_W + 1];
-    __shared__ double hs[5][PATCH_H][TILE_W];
-    __shared__ double scratch[32];
-    const int win = f.win, pad = (win - 1) / 2;
-    int64_t bid = blockIdx.x;
-    const int tx = (int)(bid % tiles_x); bid /= tiles_x;
-    const int ty = (int)(bid % tiles_y); bid /= tiles_y;
-    const int64_t s = bid;
-    const int64_t base = slice_base(f, s);
-    const int64_t oy = (int64_t)ty * TILE_H, ox = (int64_t)tx * TILE_W;   // interior coordinates
-    const int ph = TILE_H + win - 1, pw = TILE_W + win - 1;
-    for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
-        int r = e / pw, c = e - r * pw;
-        int64_t h = oy + r, w = ox + c;
-        T va = (T)0, vb = (T)0;
-        if (h < f.H && w < f.W) {
-            int64_t off = base + h * f.sh + w * f.sw;
-            va = a[off];
-            vb = b[off];
-            vb = vb > (T)0 ? vb : (T)0;
-        }
-        pa[r][c] = va;
-        pb[r][c] = vb;
-    }
-    __syncthreads();
-    // horizontal box sums
-    for (int e = threadIdx.x; e < ph * TILE_W; e += blockDim.x) {
-        int r = e / TILE_W, c = e - r * TILE_W;
-        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
-        for (int j = 0; j < win; j++) {
-            double x = (double)pa[r][c + j], y = (double)pb[r][c + j];
-            sx += x; sy += y;
-            sxx = fma(x, x, sxx); syy = fma(y, y, syy); sxy = fma(x, y, sxy);
-        }
-        hs[0][r][c] = sx; hs[1][r][c] = sy; hs[2][r][c] = sxx; hs[3][r][c] = syy; hs[4][r][c] = sxy;
-    }
-    __syncthreads();
-    const double R = range[s];
-    const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
-    const double np = (double)(win * win);
-    const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
-    const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;   // interior extent
-    double acc = 0.0;
-    for (int e = threadIdx.x; e < TILE_H * TILE_W; e += blockDim.x) {
-        int y = e / TILE_W, x = e - y * TILE_W;
-        if (oy + y >= ih || ox + x >= iw) continue;
-        double v[5];
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-            double t = 0.0;
-            for (int i = 0; i < win; i++) t += hs[q][y + i][x];
-            v[q] = t * inv_np;
-        }
-        double ux = v[0], uy = v[1];
-        double vx = cov_norm * (v[2] - ux * ux), vy = cov_norm * (v[3] - uy * uy), vxy = cov_norm * (v[4] - ux * uy);
-        double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
-        double den = (ux * ux + uy * uy + c1) * (vx + vy + c2);
-        acc += num / den;
-    }
-    acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Slice-batched variants for families whose SLICE INDEX is the contiguous memory dimension
-// (3-D: slices along the last axis; 4-D: every family, the frame index runs fastest).  A CTA
-// takes 32 consecutive slices, lane = slice: every global load is a coalesced 128-byte line
-// and the shared-memory patch [position][slice] is bank-conflict free.
-// ---------------------------------------------------------------------------------------------
-constexpr int BT_H = 8, BT_W = 8, BT_SLICES = 32;
 
 // order-preserving map double -> uint64 so that min / max can be done with integer atomics
 __device__ __forceinline__ unsigned long long dkey(double x) {
@@ -140,9 +42,152 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-constexpr int RANGE_CHUNK = 2048;   // slice positions per CTA
+constexpr int RANGE_ROWS = 32;     // slice rows per CTA of the range pass
 
-// keys[2s] = min key, keys[2s+1] = max key (initialised to all-ones / zero by the host)
+// R = max(max a, max clip(b)) - min(min a, min clip(b)) per slice (metrics.py:23-24).  Grid (slices, row
+// chunks): a warp walks whole rows (lane = column, no index division), the CTA folds its result into the
+// slice's {min key, max key} with integer atomics.  keys start at all-ones / zero.
+template <class T>
+__global__ void __launch_bounds__(256) ssim_range_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
+                                                          unsigned long long* __restrict__ keys) {
+    __shared__ double scratch[32];
+    const int64_t s = blockIdx.x;
+    const int64_t base = slice_base(f, s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t h0 = (int64_t)blockIdx.y * RANGE_ROWS;
+    const int64_t h1 = h0 + RANGE_ROWS < f.H ? h0 + RANGE_ROWS : f.H;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t h = h0 + warp; h < h1; h += 8) {
+        const int64_t row = base + h * f.sh;
+        for (int64_t w = lane; w < f.W; w += 32) {
+            const double x = (double)a[row + w * f.sw];
+            const double y = fmax((double)b[row + w * f.sw], 0.0);
+            lo = fmin(lo, fmin(x, y));
+            hi = fmax(hi, fmax(x, y));
+        }
+    }
+    lo = block_min(lo, scratch);
+    hi = block_max(hi, scratch);
+    if (threadIdx.x == 0 && lo <= hi) {
+        atomicMin(keys + 2 * s, dkey(lo));
+        atomicMax(keys + 2 * s + 1, dkey(hi));
+    }
+}
+
+// Horizontal pass: direct win-tap sums.  Vertical pass: a warp owns a strip of TILE_H / 8 output rows
+// (lane = column) and slides the window down with one add and one subtract per quantity instead of
+// `win` adds (for float32 inputs every intermediate is exact in float64).
+template <class T>
+__global__ void __launch_bounds__(256)
+ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
+                 int tiles_y, int tiles_x, double* __restrict__ partial) {
+    extern __shared__ unsigned char tile_smem[];
+    constexpr int HS_LD = TILE_W + 1;                                   // row stride of the horizontal sums (bank spread)
+    double* hs = reinterpret_cast<double*>(tile_smem);                  // [5][PATCH_H][HS_LD]
+    T* pa = reinterpret_cast<T*>(hs + 5 * PATCH_H * HS_LD);             // [PATCH_H][PATCH_W + 1]
+    T* pb = pa + PATCH_H * (PATCH_W + 1);
+    __shared__ double scratch[32];
+    const int win = f.win, pad = (win - 1) / 2;
+    int64_t bid = blockIdx.x;
+    const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+    const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+    const int64_t s = bid;
+    const int64_t base = slice_base(f, s);
+    const int64_t oy = (int64_t)ty * TILE_H, ox = (int64_t)tx * TILE_W;   // interior coordinates
+    const int ph = TILE_H + win - 1, pw = TILE_W + win - 1;
+    for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
+        const int r = e / pw, c = e - r * pw;
+        const int64_t h = oy + r, w = ox + c;
+        T va = (T)0, vb = (T)0;
+        if (h < f.H && w < f.W) {
+            const int64_t off = base + h * f.sh + w * f.sw;
+            va = a[off];
+            vb = b[off];
+            vb = vb > (T)0 ? vb : (T)0;
+        }
+        pa[r * (PATCH_W + 1) + c] = va;
+        pb[r * (PATCH_W + 1) + c] = vb;
+    }
+    __syncthreads();
+    // horizontal box sums: direct win-tap sums, every thread busy (a sliding sum along the row was measured
+    // slower here: its dependent add chain serialises what this form does with pure instruction-level parallelism)
+    for (int e = threadIdx.x; e < ph * TILE_W; e += blockDim.x) {
+        const int r = e / TILE_W, c = e - r * TILE_W;
+        const T* xa = pa + r * (PATCH_W + 1) + c;
+        const T* xb = pb + r * (PATCH_W + 1) + c;
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        for (int j = 0; j < win; j++) {
+            const double x = (double)xa[j], y = (double)xb[j];
+            sx += x; sy += y;
+            sxx = fma(x, x, sxx); syy = fma(y, y, syy); sxy = fma(x, y, sxy);
+        }
+        hs[(0 * PATCH_H + r) * HS_LD + c] = sx; hs[(1 * PATCH_H + r) * HS_LD + c] = sy; hs[(2 * PATCH_H + r) * HS_LD + c] = sxx;
+        hs[(3 * PATCH_H + r) * HS_LD + c] = syy; hs[(4 * PATCH_H + r) * HS_LD + c] = sxy;
+    }
+    __syncthreads();
+    const double R = range[s];
+    const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
+    const double np = (double)(win * win);
+    const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+    const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;   // interior extent
+    double acc = 0.0;
+    {
+        constexpr int STRIP = TILE_H / 8;
+        const int x = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * STRIP;
+        double v[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            double t = 0.0;
+            for (int i = 0; i < win; i++) t += hs[(q * PATCH_H + y0 + i) * HS_LD + x];
+            v[q] = t;
+        }
+#pragma unroll
+        for (int dy = 0; dy < STRIP; dy++) {
+            const int y = y0 + dy;
+            if (dy > 0) {
+#pragma unroll
+                for (int q = 0; q < 5; q++)
+                    v[q] += hs[(q * PATCH_H + y + win - 1) * HS_LD + x] - hs[(q * PATCH_H + y - 1) * HS_LD + x];
+            }
+            if (oy + y < ih && ox + x < iw) {
+                const double ux = v[0] * inv_np, uy = v[1] * inv_np;
+                const double vx = cov_norm * (v[2] * inv_np - ux * ux), vy = cov_norm * (v[3] * inv_np - uy * uy);
+                const double vxy = cov_norm * (v[4] * inv_np - ux * uy);
+                const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
+                const double den = (ux * ux + uy * uy + c1) * (vx + vy + c2);
+                acc += num / den;
+            }
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+template <class T>
+static int launch_ssim_tile(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
+                            int64_t nt, double* partial) {
+    const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(double) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    ssim_tile_kernel<T><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slice-batched variants for families whose SLICE INDEX is the contiguous memory dimension
+// (3-D: slices along the last axis; 4-D: every family, the frame index runs fastest).  A CTA
+// takes 32 consecutive slices, lane = slice: every global load is a coalesced 128-byte line
+// and the shared-memory patch [position][slice] is bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+constexpr int BT_H = 8, BT_W = 8, BT_SLICES = 32;
+
+
+// keys[2s] = min key, keys[2s+1] = max key (initialised to all-ones / zero by the host).  lane = slice
+// (32 consecutive slices are 32 consecutive addresses), a warp walks whole slice rows.
 template <class T>
 __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f,
                                                                   unsigned long long* __restrict__ keys) {
@@ -152,16 +197,17 @@ __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __rest
     double lo = INFINITY, hi = -INFINITY;
     if (s < f.S) {
         const int64_t base = slice_base(f, s);
-        const int64_t total = f.H * f.W;
-        const int64_t e0 = (int64_t)blockIdx.y * RANGE_CHUNK;
-        const int64_t e1 = e0 + RANGE_CHUNK < total ? e0 + RANGE_CHUNK : total;
-        for (int64_t e = e0 + warp; e < e1; e += 8) {
-            int64_t h = e / f.W, w = e - h * f.W;
-            int64_t off = base + h * f.sh + w * f.sw;
-            double x = (double)a[off];
-            double y = fmax((double)b[off], 0.0);
-            lo = fmin(lo, fmin(x, y));
-            hi = fmax(hi, fmax(x, y));
+        const int64_t h0 = (int64_t)blockIdx.y * RANGE_ROWS;
+        const int64_t h1 = h0 + RANGE_ROWS < f.H ? h0 + RANGE_ROWS : f.H;
+        for (int64_t h = h0 + warp; h < h1; h += 8) {
+            const int64_t row = base + h * f.sh;
+#pragma unroll 4
+            for (int64_t w = 0; w < f.W; w++) {
+                const double x = (double)a[row + w * f.sw];
+                const double y = fmax((double)b[row + w * f.sw], 0.0);
+                lo = fmin(lo, fmin(x, y));
+                hi = fmax(hi, fmax(x, y));
+            }
         }
     }
     s_lo[warp][lane] = lo;
@@ -281,6 +327,28 @@ __global__ void __launch_bounds__(128) ssim_slice_kernel(const double* __restric
     if (threadIdx.x == 0) scores[blockIdx.x] = acc * scale;
 }
 
+// per-slice data range of a family into range[0..S): keys initialised, range pass, finalize
+template <class T>
+static int slice_ranges(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, bool batched, double* range) {
+    unsigned long long* keys = nullptr;
+    NDMPS_TRY(ctx->ws.get<unsigned long long>((size_t)(2 * f.S), &keys));
+    // min keys start at all-ones, max keys at zero: 0xFF.. / 0x00.. interleaved per slice
+    NDMPS_CUDA_TRY(cudaMemset2DAsync(keys, 16, 0xFF, 8, (size_t)f.S, ctx->stream));
+    NDMPS_CUDA_TRY(cudaMemset2DAsync(keys + 1, 16, 0x00, 8, (size_t)f.S, ctx->stream));
+    const unsigned chunks = (unsigned)((f.H + RANGE_ROWS - 1) / RANGE_ROWS);
+    if (batched) {
+        dim3 rgrid((unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), chunks);
+        ssim_range_batched_kernel<T><<<rgrid, 256, 0, ctx->stream>>>(a, b, f, keys);
+    } else {
+        dim3 rgrid((unsigned)f.S, chunks);
+        ssim_range_kernel<T><<<rgrid, 256, 0, ctx->stream>>>(a, b, f, keys);
+    }
+    NDMPS_LAUNCH_CHECK(ctx);
+    ssim_range_finalize_kernel<<<(unsigned)((f.S + 255) / 256), 256, 0, ctx->stream>>>(keys, f.S, range);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
 template <class T>
 static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, double* scores_host) {
     NDMPS_TRY(ensure_pinned(ctx, (size_t)f.S + 64));
@@ -293,10 +361,9 @@ static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const Slice
     NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &range));
     NDMPS_TRY(ctx->ws.get<double>((size_t)nt, &partial));
     NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &scores));
-    ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range);
-    NDMPS_LAUNCH_CHECK(ctx);
-    ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range, ty, tx, partial);
-    NDMPS_LAUNCH_CHECK(ctx);
+    NDMPS_REQUIRE(f.S < 65536 * 32, "ssim: too many slices");
+    NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, false, range));
+    NDMPS_TRY(launch_ssim_tile<T>(ctx, a, b, f, range, ty, tx, nt, partial));
     ssim_slice_kernel<<<(unsigned)f.S, 128, 0, ctx->stream>>>(partial, ty * tx, 1.0 / ((double)ih * (double)iw), scores);
     NDMPS_LAUNCH_CHECK(ctx);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, scores, (size_t)f.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -350,25 +417,13 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
                 NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                 attr_set = true;
             }
-            unsigned long long* keys = nullptr;
-            NDMPS_TRY(ctx->ws.get<unsigned long long>((size_t)(2 * f.S), &keys));
-            // min keys start at all-ones, max keys at zero: 0xFF.. / 0x00.. interleaved per slice
-            NDMPS_CUDA_TRY(cudaMemset2DAsync(keys, 16, 0xFF, 8, (size_t)f.S, ctx->stream));
-            NDMPS_CUDA_TRY(cudaMemset2DAsync(keys + 1, 16, 0x00, 8, (size_t)f.S, ctx->stream));
-            dim3 rgrid((unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), (unsigned)((f.H * f.W + RANGE_CHUNK - 1) / RANGE_CHUNK));
-            ssim_range_batched_kernel<T><<<rgrid, 256, 0, ctx->stream>>>(a, b, f, keys);
-            NDMPS_LAUNCH_CHECK(ctx);
-            ssim_range_finalize_kernel<<<(unsigned)((f.S + 255) / 256), 256, 0, ctx->stream>>>(keys, f.S, range + slice_off);
-            NDMPS_LAUNCH_CHECK(ctx);
+            NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, true, range + slice_off));
             ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
                                                                                  partial + bounds_h[k]);
             NDMPS_LAUNCH_CHECK(ctx);
         } else {
-            ssim_range_kernel<T><<<(unsigned)f.S, 256, 0, ctx->stream>>>(a, b, f, range + slice_off);
-            NDMPS_LAUNCH_CHECK(ctx);
-            ssim_tile_kernel<T><<<(unsigned)nt, 256, 0, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
-                                                                      partial + bounds_h[k]);
-            NDMPS_LAUNCH_CHECK(ctx);
+            NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, false, range + slice_off));
+            NDMPS_TRY(launch_ssim_tile<T>(ctx, a, b, f, range + slice_off, tiles_y[k], tiles_x[k], nt, partial + bounds_h[k]));
         }
         slice_off += f.S;
     }
