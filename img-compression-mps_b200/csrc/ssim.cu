@@ -184,6 +184,7 @@ static int launch_ssim_tile(ndmps_ctx* ctx, const T* a, const T* b, const SliceF
 // and the shared-memory patch [position][slice] is bank-conflict free.
 // ---------------------------------------------------------------------------------------------
 constexpr int BT_H = 8, BT_W = 8, BT_SLICES = 32;
+constexpr int BT_RANGE_ROWS = 8;   // one slice row per warp in the batched range pass (few slice groups: many row chunks)
 
 
 // keys[2s] = min key, keys[2s+1] = max key (initialised to all-ones / zero by the host).  lane = slice
@@ -197,11 +198,11 @@ __global__ void __launch_bounds__(256) ssim_range_batched_kernel(const T* __rest
     double lo = INFINITY, hi = -INFINITY;
     if (s < f.S) {
         const int64_t base = slice_base(f, s);
-        const int64_t h0 = (int64_t)blockIdx.y * RANGE_ROWS;
-        const int64_t h1 = h0 + RANGE_ROWS < f.H ? h0 + RANGE_ROWS : f.H;
+        const int64_t h0 = (int64_t)blockIdx.y * BT_RANGE_ROWS;
+        const int64_t h1 = h0 + BT_RANGE_ROWS < f.H ? h0 + BT_RANGE_ROWS : f.H;
         for (int64_t h = h0 + warp; h < h1; h += 8) {
             const int64_t row = base + h * f.sh;
-#pragma unroll 4
+#pragma unroll 8
             for (int64_t w = 0; w < f.W; w++) {
                 const double x = (double)a[row + w * f.sw];
                 const double y = fmax((double)b[row + w * f.sw], 0.0);
@@ -337,7 +338,7 @@ static int slice_ranges(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamil
     NDMPS_CUDA_TRY(cudaMemset2DAsync(keys + 1, 16, 0x00, 8, (size_t)f.S, ctx->stream));
     const unsigned chunks = (unsigned)((f.H + RANGE_ROWS - 1) / RANGE_ROWS);
     if (batched) {
-        dim3 rgrid((unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), chunks);
+        dim3 rgrid((unsigned)((f.S + BT_SLICES - 1) / BT_SLICES), (unsigned)((f.H + BT_RANGE_ROWS - 1) / BT_RANGE_ROWS));
         ssim_range_batched_kernel<T><<<rgrid, 256, 0, ctx->stream>>>(a, b, f, keys);
     } else {
         dim3 rgrid((unsigned)f.S, chunks);
