@@ -24,7 +24,48 @@ __global__ void __launch_bounds__(256) reduce_stage1(const T* __restrict__ a, co
     double acc0 = MODE == 1 ? INFINITY : 0.0;
     double acc1 = -INFINITY;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t done = 0;
+    if (sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (MODE != 2 || (reinterpret_cast<uintptr_t>(b) & 15) == 0)) {
+        // float32: 16-byte loads, two of them in flight per array and thread; sums in two independent float64 chains
+        const int64_t n4 = n >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        double accb = 0.0;
+        auto take = [&](const float4& va, const float4& vb, double& sum) {
+            const float xs[4] = {va.x, va.y, va.z, va.w}, ys[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double x = (double)xs[q];
+                if (MODE == 0) {
+                    sum = fma(x, x, sum);
+                } else if (MODE == 1) {
+                    acc0 = fmin(acc0, x);
+                    acc1 = fmax(acc1, x);
+                } else {
+                    const double d = x - (double)ys[q];
+                    sum = fma(d, d, sum);
+                    acc1 = fmax(acc1, x);
+                }
+            }
+        };
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + stride < n4; i += 2 * stride) {
+            const float4 va0 = __ldcs(a4 + i), va1 = __ldcs(a4 + i + stride);
+            float4 vb0 = va0, vb1 = va1;
+            if (MODE == 2) { vb0 = __ldcs(b4 + i); vb1 = __ldcs(b4 + i + stride); }
+            if (MODE == 1) { take(va0, vb0, accb); take(va1, vb1, accb); }
+            else { take(va0, vb0, acc0); take(va1, vb1, accb); }
+        }
+        for (; i < n4; i += stride) {
+            const float4 va0 = __ldcs(a4 + i);
+            float4 vb0 = va0;
+            if (MODE == 2) vb0 = __ldcs(b4 + i);
+            if (MODE == 1) take(va0, vb0, accb); else take(va0, vb0, acc0);
+        }
+        if (MODE != 1) acc0 += accb;
+        done = n4 << 2;
+    }
+    for (int64_t i = done + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double x = (double)a[i];
         if (MODE == 0) {
             acc0 += x * x;
