@@ -8,7 +8,9 @@
 
 namespace ndmps {
 
-__global__ void __launch_bounds__(256) dct_matrix_kernel(double* __restrict__ C, int64_t n) {
+// C (row-major, C[k][i]) when transposed == 0, C^T (Ct[i][k]) otherwise: both products of the transform then read
+// their small operand along its rows, which is what the FP64 tensor-pipe GEMM wants
+__global__ void __launch_bounds__(256) dct_matrix_kernel(double* __restrict__ C, int64_t n, int transposed) {
     int64_t total = n * n, stride = (int64_t)gridDim.x * blockDim.x;
     const double scale = sqrt(2.0 / (double)n);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -17,7 +19,7 @@ __global__ void __launch_bounds__(256) dct_matrix_kernel(double* __restrict__ C,
         int64_t q = ((2 * i + 1) * k) % (4 * n);
         double v = scale * cospi((double)q / (double)(2 * n));
         if (k == 0) v *= 0.70710678118654752440;
-        C[e] = v;
+        C[transposed ? i * n + k : e] = v;
     }
 }
 
@@ -36,10 +38,10 @@ int ndmps_dct_last_axis(ndmps_ctx_t* ctx, const void* src, void* dst, int64_t li
     double* C = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)(n * n), &C));
     int64_t want = (n * n + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
-    dct_matrix_kernel<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>(C, n);
+    dct_matrix_kernel<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>(C, n, inverse ? 0 : 1);
     NDMPS_LAUNCH_CHECK(ctx);
-    if (!inverse)   // y[l, k] = sum_i x[l, i] C[k, i]
-        return gemm(ctx, lines, n, n, 1.0, src, dtype, n, 1, C, NDMPS_F64, 1, n, dst, dtype, n);
+    if (!inverse)   // y[l, k] = sum_i x[l, i] C[k, i] = sum_i x[l, i] Ct[i, k]
+        return gemm(ctx, lines, n, n, 1.0, src, dtype, n, 1, C, NDMPS_F64, n, 1, dst, dtype, n);
     // x[l, i] = sum_k y[l, k] C[k, i]
     return gemm(ctx, lines, n, n, 1.0, src, dtype, n, 1, C, NDMPS_F64, n, 1, dst, dtype, n);
 }

@@ -139,7 +139,7 @@ int gemm_dmma(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, con
               bool* done) {
     *done = false;
     if (ctx->opt_gemm_path == 2) return NDMPS_OK;
-    if (a_cs != 1 || b_cs != 1 || m < 48 || n < 96 || k < 4) return NDMPS_OK;
+    if (a_cs != 1 || b_cs != 1 || m < 48 || n < 64 || k < 4) return NDMPS_OK;   // n = 64: half of the 128-wide tile idles, still ahead of SIMT
     const int64_t tiles64 = ((m + 63) / 64) * ((n + gdm::BN - 1) / gdm::BN);
     if (tiles64 < ctx->sm_count) return NDMPS_OK;          // would need split-K: SIMT path has it
     if (tiles64 >= (int64_t(1) << 31)) return NDMPS_OK;
