@@ -236,7 +236,7 @@ def _pair(shape, seed, dtype):
     return a.astype(dtype), b.astype(dtype)
 
 
-@pytest.mark.parametrize("shape", [(16, 16), (40, 70), (7, 9), (5, 30), (6, 31), (256, 256)])
+@pytest.mark.parametrize("shape", [(16, 16), (40, 70), (7, 9), (5, 30), (6, 31), (256, 256), (33, 65), (70, 100), (39, 38)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_ssim_2d(ops, shape, dtype):
     a, b = _pair(shape, 1, dtype)
@@ -245,7 +245,7 @@ def test_ssim_2d(ops, shape, dtype):
     assert got == pytest.approx(want, abs=1e-10)            # north-star tolerance is 1e-4
 
 
-@pytest.mark.parametrize("shape", [(9, 10, 11), (32, 48, 40), (64, 64, 64)])
+@pytest.mark.parametrize("shape", [(9, 10, 11), (32, 48, 40), (64, 64, 64), (37, 45, 50), (40, 71, 33)])
 def test_ssim_3d(ops, shape):
     a, b = _pair(shape, 2, np.float32)
     a64, b64 = a.astype(np.float64), b.astype(np.float64)
@@ -255,8 +255,9 @@ def test_ssim_3d(ops, shape):
         assert np.allclose(got, OM.ssim_3d_axis(a64, b64, ax), atol=1e-10)
 
 
-def test_ssim_4d(ops):
-    a, b = _pair((16, 12, 10, 5), 3, np.float32)
+@pytest.mark.parametrize("shape", [(16, 12, 10, 5), (12, 10, 9, 40), (40, 39, 8, 33)])
+def test_ssim_4d(ops, shape):
+    a, b = _pair(shape, 3, np.float32)
     want = OM.avg_ssim_4d(a.astype(np.float64), b.astype(np.float64))
     assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=1e-10)
 
