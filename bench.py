@@ -346,8 +346,8 @@ def run_ours(args):
         m = json.loads(pk.read_text())
         peaks = {"hbm_gbs": m["hbm_gbs"], "bf16_tflops": m.get("bf16_tflops_sustained", m["bf16_tflops"]), "source": "measured"}
     FP64_PEAK_TFLOPS = 34.2          # measured on this pool, tools/microbench/fp64_rate.cu (profiles/r01_summary.md)
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture profiles/r01c_kernels_raw.csv (256^3 only)
-    ncu_traffic = {"permute": 67.15e6 + 17.35e6, "gram": 67.13e6 + 6.24e6} if args.workload == "cfg2" else {}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture profiles/r01f_kernels_raw.csv (256^3 only)
+    ncu_traffic = {"permute": 67.15e6 + 18.72e6, "gram": 67.13e6 + 5.30e6} if args.workload == "cfg2" else {}
     work = algorithmic_work(dims, ranks)
     per_step = {k: (v[0] / args.steps, v[1] / max(args.steps, 1)) for k, v in stages.items()}
     step_ms = total_ms / args.steps
@@ -375,7 +375,7 @@ def run_ours(args):
             "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic.get("permute"), "ms_per_step": perm_ms,
             "calls_per_step": perm_calls, "bytes_per_step": work["encode_bytes"] + work["decode_bytes"],
             "note": "achieved = algorithmic 8 B/voxel x 2 launches / event-timed stage (event overhead included; the kernel alone "
-                    "is 40 us = 3.36 TB/s under ncu); traffic = DRAM bytes of ONE launch: below the algorithmic 134 MB because most "
+                    "is 35 us = 3.8 TB/s under ncu); traffic = DRAM bytes of ONE launch: below the algorithmic 134 MB because most "
                     "of the 64 MB output is still in the 126 MB L2 when the kernel ends"}
     eig_ms, eig_calls = per_step["eig"]
     eig_flops = ctx_eig_flops / args.steps
