@@ -112,9 +112,14 @@ def run_benchmark(mps_list, original_tensors_list, cutoff_list, *, workers: Opti
     finally:
         if pipe:
             pipe.close()
-    for key in results:
-        if not results[key] or not results[key][0]:
-            results[key] = []
-        elif key != "bond_dims" and isinstance(results[key][0], (list, np.ndarray)) and np.ndim(results[key][0]) > 0:
-            results[key] = np.array(results[key]).T
-    return results
+    return {name: _layout(name, levels) for name, levels in results.items()}
+
+
+def _layout(name: str, levels: List[List]):
+    """Result layout of the reference: scalar metrics become an array indexed [tensor][level]; the bond
+    dimensions (ragged lists) stay [level][tensor]; an empty tensor list gives an empty result."""
+    if len(levels) == 0 or len(levels[0]) == 0:
+        return []
+    if name == "bond_dims":
+        return levels
+    return np.asarray(levels).transpose()
