@@ -73,6 +73,65 @@ def synthetic_volume(shape, seed):
     return out
 
 
+def synthetic_image(shape=(256, 256), seed=2025):
+    """configs[0]: smooth + texture grayscale image, clip(sum of 3 Gaussians + 0.05 noise, 0, 1)."""
+    rng = np.random.default_rng(seed)
+    gy, gx = np.meshgrid(np.linspace(-1, 1, shape[0]), np.linspace(-1, 1, shape[1]), indexing="ij")
+    img = np.zeros(shape)
+    for _ in range(3):
+        cy, cx = rng.uniform(-0.5, 0.5, 2)
+        sy, sx = rng.uniform(0.15, 0.5, 2)
+        img += rng.uniform(0.3, 0.6) * np.exp(-(((gy - cy) / sy) ** 2 + ((gx - cx) / sx) ** 2))
+    img += 0.05 * rng.random(shape)
+    return np.clip(img, 0.0, 1.0).astype(np.float32)
+
+
+def synthetic_fmri(shape=(64, 64, 32, 400), seed=3000):
+    """configs[3]: static phantom x (1 + 0.05 low-rank temporal modes (rank 8, sinusoids)) + 0.01 noise."""
+    rng = np.random.default_rng(seed)
+    sx, sy, sz, nt = shape
+    g = np.meshgrid(*[np.linspace(-1, 1, n, dtype=np.float32) for n in (sx, sy, sz)], indexing="ij")
+    base = np.zeros((sx, sy, sz), dtype=np.float32)
+    for k in range(3):
+        c = rng.uniform(-0.2, 0.2, 3)
+        r = rng.uniform(0.45, 0.85, 3) * (1.0 - 0.2 * k)
+        r2 = sum(((gi - ci) / ri) ** 2 for gi, ci, ri in zip(g, c, r))
+        base += (0.3 + 0.15 * k) / (1.0 + np.exp(np.clip((r2 - 1.0) * 10.0, -60, 60)))
+    t = np.arange(nt, dtype=np.float32) / nt
+    out = np.empty(shape, dtype=np.float32)
+    mod = np.ones(shape, dtype=np.float32)
+    for m in range(8):
+        spatial = np.cos((m % 3 + 1) * g[0] + m) * np.cos((m % 2 + 1) * g[1] - m) * np.cos((m % 4) * 0.5 * g[2])
+        temporal = np.sin(2 * np.pi * (m + 1) * t + rng.uniform(0, 6.28))
+        mod += (0.05 / (1 + 0.5 * m)) * spatial[..., None].astype(np.float32) * temporal[None, None, None, :].astype(np.float32)
+    np.multiply(base[..., None], mod, out=out)
+    out += 0.01 * rng.random(shape, dtype=np.float32)
+    return out
+
+
+def synthetic_video(shape=(1920, 1080, 64), seed=4000, channel=0, chunk=0):
+    """configs[4], non-degenerate partition 5-B: one colour channel x one 64-frame chunk of a moving-blob
+    video: 5 Gaussians with linear motion, per-channel gain, 0.02 noise."""
+    rng = np.random.default_rng(seed)
+    blobs = [(rng.uniform(-0.6, 0.6, 2), rng.uniform(-0.4, 0.4, 2), rng.uniform(0.1, 0.35, 2), rng.uniform(0.3, 0.8)) for _ in range(5)]
+    gains = rng.uniform(0.6, 1.0, 3)
+    noise = np.random.default_rng(seed + 17 * channel + 101 * chunk + 1)
+    w, h, nf = shape
+    gx = np.linspace(-1, 1, w, dtype=np.float32)[:, None]
+    gy = np.linspace(-1, 1, h, dtype=np.float32)[None, :]
+    out = np.empty(shape, dtype=np.float32)
+    for f in range(nf):
+        tt = (chunk * nf + f) / 512.0
+        fr = np.zeros((w, h), dtype=np.float32)
+        for p0, vel, sig, amp in blobs:
+            cx, cy = p0[0] + vel[0] * tt, p0[1] + vel[1] * tt
+            fr += np.float32(amp) * (np.exp(-((gx - np.float32(cx)) / np.float32(sig[0])) ** 2) * np.exp(-((gy - np.float32(cy)) / np.float32(sig[1])) ** 2))
+        fr *= np.float32(gains[channel])
+        fr += 0.02 * noise.random((w, h), dtype=np.float32)
+        out[:, :, f] = fr
+    return out
+
+
 def algorithmic_work(dims, ranks):
     """Bytes / flops of the stages per SURVEY section 8(d) for float32 payloads (4 B)."""
     L, n = len(dims), int(np.prod(dims))

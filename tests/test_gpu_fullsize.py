@@ -1,7 +1,8 @@
-"""Full BASELINE sizes on the B200, checked through size-independent properties (the oracle
-cannot run these sizes in seconds): permutation round trip and checksums, norm preservation,
-monotone fidelity in chi, left-canonical cores, reconstruction error == discarded weight,
-batch sharding through run_sharded, DCT mode round trip."""
+"""Full BASELINE sizes on the B200 through size-independent properties: permutation round trip
+and checksums, norm preservation, monotone fidelity in chi, left-canonical cores, reconstruction
+error == discarded weight, batch sharding through run_sharded, DCT mode round trip.  The oracle
+comparison at these sizes (15 s to 2 min of host time per case) lives in
+``test_gpu_baseline_parity.py``."""
 import math
 
 import numpy as np
