@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -62,6 +63,23 @@ int Arena::alloc(size_t bytes, void** out) {
     chunks.push_back({p, cap, bytes});
     cur_total += bytes;
     *out = p;
+    return NDMPS_OK;
+}
+
+int raise_dynamic_smem(const void* kernel, int device, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> raised;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, device);
+    auto it = raised.find(key);
+    if (it != raised.end() && it->second >= bytes) return NDMPS_OK;
+    int cur = -1;
+    NDMPS_CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) NDMPS_CUDA_TRY(cudaSetDevice(device));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (cur != device) cudaSetDevice(cur);
+    NDMPS_CUDA_TRY(e);
+    raised[key] = bytes;
     return NDMPS_OK;
 }
 
@@ -252,6 +270,7 @@ int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, in
     if (!strcmp(name, "eig_flops")) { *value_out = ctx->eig_flops; if (reset) ctx->eig_flops = 0.0; }
     else if (!strcmp(name, "eig_calls")) { *value_out = (double)ctx->eig_calls; if (reset) ctx->eig_calls = 0; }
     else if (!strcmp(name, "workspace_bytes")) { *value_out = (double)ctx->ws.high_water; }
+    else if (!strcmp(name, "tc_launches")) { *value_out = (double)ctx->tc_launches; if (reset) ctx->tc_launches = 0; }
     else {
         set_error("ndmps_ctx_get_stat: unknown statistic '%s'", name);
         return NDMPS_ERR_INVALID;
@@ -280,6 +299,9 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;
     else if (!strcmp(name, "blocking_sync")) ctx->opt_blocking_sync = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
+    else if (!strcmp(name, "tc")) ctx->opt_tc = value;
+    else if (!strcmp(name, "tc_chunk")) ctx->opt_tc_chunk = value;
+    else if (!strcmp(name, "gemm_out_t")) ctx->opt_gemm_out_t = value;
     else {
         set_error("ndmps_ctx_set_option: unknown option '%s'", name);
         return NDMPS_ERR_INVALID;

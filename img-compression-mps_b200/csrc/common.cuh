@@ -42,12 +42,15 @@ struct TilePlan {
     std::vector<uint16_t> rslot;
     int run_pad = 0;
     int gather_conflict = 0;
-    uint16_t* d_rslot = nullptr;
-    // device copies, uploaded on first use
-    int64_t* d_hi_src = nullptr;
-    int64_t* d_hi_dst = nullptr;
-    uint16_t* d_pos = nullptr;
-    int device = -1;
+    // device copies, uploaded on first use PER DEVICE (a plan is shared by host threads that may drive different GPUs)
+    struct DevTables {
+        int device = -1;
+        int64_t* hi_src = nullptr;
+        int64_t* hi_dst = nullptr;
+        uint16_t* pos = nullptr;
+        uint16_t* rslot = nullptr;
+    };
+    std::vector<DevTables> dev;          // guarded by the upload mutex in permute.cu; read through upload_tile_plan only
 };
 
 struct ndmps_plan {
@@ -136,7 +139,12 @@ struct ndmps_ctx {
     double* pinned = nullptr;
     size_t pinned_doubles = 0;
     // options
-    int64_t opt_gram_path = 0;      // 0: auto (FP64 tensor pipe when the shape allows), 2: force the SIMT kernel
+    int64_t opt_gram_path = 0;      // 0: auto (FP64 tensor pipe when the shape allows), 2: force the SIMT kernel, 3: force tcgen05 (tc_gemm.cu)
+    int64_t opt_tc = 1;             // tcgen05 contractions on bf16x3 split planes for float32 payloads of a capped sweep / the reconstruction (0: off)
+    int64_t opt_tc_chunk = 0;       // k-tiles (64 columns each) between drains of the tcgen05 Gram accumulator into float64 (0: 4)
+    int64_t opt_gemm_out_t = 0;     // test hook: ndmps_gemm writes C transposed (n x m) through the tcgen05 epilogue
+    bool tc_gemm = false;           // set around the products that may take the tcgen05 GEMM (projection, final contraction)
+    bool tc_sweep = false;          // set by the sweep while the tcgen05 Gram / projection are admissible (float32, bond cap)
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_gemm_path = 0;      // 0: FP64 tensor pipe for large row-major products, 2: SIMT only
     int64_t opt_permute_path = 0;   // 0: ld/st tiles through shared memory; 3: bulk-copy (TMA-class) tiles; 2: gather kernel
@@ -160,6 +168,7 @@ struct ndmps_ctx {
     int last_eig_sweeps = 0;
     double eig_flops = 0.0;        // 7 n per rotation x pairs x sweeps (+ n r^2 for the Cholesky), accumulated
     int64_t eig_calls = 0;
+    int64_t tc_launches = 0;       // tcgen05 kernels launched (tc_gemm.cu)
     // stage profiler
     bool profile = false;
     struct Pending { int stage; cudaEvent_t beg, end; };
@@ -171,6 +180,9 @@ struct ndmps_ctx {
 namespace ndmps {
 
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it to `bytes` once per
+// (kernel, device), from any host thread (the largest value set so far is remembered under a mutex).
+int raise_dynamic_smem(const void* kernel, int device, int bytes);
 // wait for everything enqueued on the context's stream (spinning cudaStreamSynchronize, or a blocking event)
 cudaError_t stream_wait(ndmps_ctx* ctx);
 
@@ -203,6 +215,10 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
          const void* b, int dtype_b, int64_t b_rs, int64_t b_cs,
          void* c, int dtype_c, int64_t ldc);
 int gram(ndmps_ctx* ctx, const void* m, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev);
+// tcgen05 paths (tc_gemm.cu); *done = false when the shape is not eligible
+int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
+int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,
+            const void* b, int dtype_b, int64_t b_rs, int64_t b_cs, void* c, int dtype_c, int64_t ldc, bool out_t, bool* done);
 // tol_override > 0 loosens the relative off-diagonal threshold (float32 payloads do not need 1e-15)
 int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, double tol_override = 0.0);
 int eigh_small_async(ndmps_ctx* ctx, double* a_dev, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev);

@@ -35,6 +35,7 @@ int ndmps_dct_last_axis(ndmps_ctx_t* ctx, const void* src, void* dst, int64_t li
     NDMPS_REQUIRE(src != dst, "ndmps_dct_last_axis: in-place transform is not supported");
     if (lines == 0) return NDMPS_OK;
     NDMPS_TRY(ctx->ws.reset(ctx->stream));
+    StageScope sc(ctx, ST_DCT);
     double* C = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)(n * n), &C));
     int64_t want = (n * n + 255) / 256, cap = (int64_t)ctx->sm_count * 8;

@@ -28,6 +28,8 @@
 // the once-per-sweep pair coverage and the sweep count explodes.)
 #include <cooperative_groups.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -1056,22 +1058,19 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
 
 template <class K>
 static int raise_smem_minus(K kernel, const ndmps_ctx* ctx, int reserve) {
-    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - reserve));
-    return NDMPS_OK;
+    return raise_dynamic_smem((const void*)kernel, ctx->device, (int)ctx->smem_optin - reserve);
 }
 
 template <class K>
 static int raise_smem(K kernel, const ndmps_ctx* ctx) {
     // leave room for the kernels' few bytes of static shared memory
-    NDMPS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
-    return NDMPS_OK;
+    return raise_dynamic_smem((const void*)kernel, ctx->device, (int)ctx->smem_optin - 1024);
 }
 
 template <int NR>
 static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb, int max_sweeps, unsigned* ctrl,
                           double tol2, const double* floor2, size_t smem, float quad_stop2) {
-    static bool attr_set = false;
-    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx)); attr_set = true; }
+    NDMPS_TRY(raise_smem(jacobi_persistent_kernel<NR>, ctx));
     unsigned* stamps = nullptr;
     NDMPS_TRY(ctx->ws.get<unsigned>((size_t)nb * nb + nb, &stamps));
     NDMPS_CUDA_TRY(cudaMemsetAsync(stamps, 0, ((size_t)nb * nb + nb) * sizeof(unsigned), ctx->stream));
@@ -1083,8 +1082,7 @@ static int run_persistent(ndmps_ctx* ctx, double* A, int n, int ncols, int b, in
 template <int NR>
 static int run_round(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb, int round, unsigned* flag, double tol2,
                      const double* floor2, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx)); attr_set = true; }
+    NDMPS_TRY(raise_smem(jacobi_round_kernel<NR>, ctx));
     jacobi_round_kernel<NR><<<nb / 2, 32 * b, smem, ctx->stream>>>(A, n, ncols, b, nb, round, flag, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
@@ -1093,8 +1091,7 @@ static int run_round(ndmps_ctx* ctx, double* A, int n, int ncols, int b, int nb,
 template <int NR>
 static int run_single(ndmps_ctx* ctx, double* A, int n, int warps, int max_sweeps, unsigned* ctrl, double tol2,
                       const double* floor2, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) { NDMPS_TRY(raise_smem(jacobi_single_kernel<NR>, ctx)); attr_set = true; }
+    NDMPS_TRY(raise_smem(jacobi_single_kernel<NR>, ctx));
     jacobi_single_kernel<NR><<<1, 32 * warps, smem, ctx->stream>>>(A, n, max_sweeps, ctrl, tol2, floor2);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
@@ -1163,13 +1160,13 @@ static int pivoted_cholesky_cluster(ndmps_ctx* ctx, const double* G, int n, doub
     int ncta = (n + rows_per - 1) / rows_per;
     const size_t smem = ((size_t)rows_per * n + n + rows_per) * sizeof(double) + (size_t)rows_per * sizeof(int) + 16;
     if (ncta > 16 || smem > ctx->smem_optin - 4096) return NDMPS_OK;
-    static int usable = -1;      // -1 unknown, 0 the device refused the cluster launch once, 1 fine
-    if (usable == 0) return NDMPS_OK;
-    if (usable < 0) {
-        cudaError_t e = cudaFuncSetAttribute(pivoted_cholesky_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ctx->smem_optin - 4096);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pivoted_cholesky_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) { cudaGetLastError(); usable = 0; return NDMPS_OK; }
+    static std::atomic<int> usable{-1};      // -1 unknown, 0 a device refused the cluster launch once, 1 fine
+    if (usable.load() == 0) return NDMPS_OK;
+    {
+        int rc = raise_smem_minus(pivoted_cholesky_cluster_kernel, ctx, 4096);
+        cudaError_t e = rc == NDMPS_OK ? cudaFuncSetAttribute(pivoted_cholesky_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                                       : cudaErrorUnknown;
+        if (e != cudaSuccess) { cudaGetLastError(); usable.store(0); return NDMPS_OK; }
     }
     int* rank_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<int>(4, &rank_dev));
@@ -1189,10 +1186,10 @@ static int pivoted_cholesky_cluster(ndmps_ctx* ctx, const double* G, int n, doub
     cudaError_t e = cudaLaunchKernelEx(&cfg, pivoted_cholesky_cluster_kernel, G, n, rows_per, Lcol, rank_dev, stop_rel);
     if (e != cudaSuccess) {      // e.g. no GPC with ncta free SMs: fall back to the global-barrier kernel
         cudaGetLastError();
-        if (usable < 0) usable = 0;
+        if (usable.load() < 0) usable.store(0);
         return NDMPS_OK;
     }
-    usable = 1;
+    usable.store(1);
     ctx->launches++;
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
     NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, rank_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1211,12 +1208,7 @@ static int pivoted_cholesky_blocked(ndmps_ctx* ctx, const double* G, int n, doub
     while (ncta > ctx->sm_count) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }
     const size_t smem = ((size_t)rows_per * n + (size_t)n * CHB + (size_t)CHB * n + n) * sizeof(double) + (size_t)n * sizeof(int) + 16;
     if (smem > ctx->smem_optin - 4096) return NDMPS_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ctx->smem_optin - 4096));
-        attr_set = true;
-    }
+    NDMPS_TRY(raise_smem_minus(pivoted_cholesky_blocked_kernel, ctx, 4096));
     double *diag_g = nullptr, *rows_g = nullptr;
     unsigned* ctrl = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)2 * n, &diag_g));
@@ -1248,13 +1240,8 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     while (ncta > ctx->sm_count) { rows_per++; ncta = (n + rows_per - 1) / rows_per; }
     const size_t smem = ((size_t)rows_per * n + n + rows_per) * sizeof(double) + (size_t)rows_per * sizeof(int) + 16;
     NDMPS_REQUIRE(smem <= ctx->smem_optin - 4096, "pivoted_cholesky: n = %d does not fit shared memory", n);
-    static bool attr_set = false;
-    if (!attr_set) {
-        // the kernel also has ~3 KB of static shared memory: static + dynamic must stay within the opt-in limit
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ctx->smem_optin - 4096));
-        attr_set = true;
-    }
+    // the kernel also has ~3 KB of static shared memory: static + dynamic must stay within the opt-in limit
+    NDMPS_TRY(raise_smem_minus(pivoted_cholesky_kernel, ctx, 4096));
     double* cand_rows = nullptr;
     CholCand* cand = nullptr;
     unsigned* ctrl = nullptr;
@@ -1286,8 +1273,7 @@ int eigh_small_async(ndmps_ctx* ctx, double* a_in, int n, double* evals_dev, dou
     const double stop_rel = 2.220446049250313e-16;
 #define NDMPS_SMALL(NRV)                                                                                              \
     do {                                                                                                            \
-        static bool attr_set = false;                                                                               \
-        if (!attr_set) { NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192)); attr_set = true; }        \
+        NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192));                                           \
         eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, quad_stop2, evals_dev, evecs_dev, info); \
     } while (0)
     if (n <= 32) NDMPS_SMALL(4);

@@ -937,16 +937,10 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
-    {   // fixed ceilings, set once: contexts on several host threads share these function attributes
-        static std::once_flag once;
-        static cudaError_t once_rc = cudaSuccess;
+    {   // fixed ceilings, set once per device: contexts on several host threads share these function attributes
         const int ceiling = (int)ctx->smem_optin - 2048;
-        std::call_once(once, [&]() {
-            once_rc = cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
-            if (once_rc == cudaSuccess)
-                once_rc = cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
-        });
-        NDMPS_CUDA_TRY(once_rc);
+        NDMPS_TRY(raise_dynamic_smem((const void*)invit_kernel, ctx->device, ceiling));
+        NDMPS_TRY(raise_dynamic_smem((const void*)chol_inverse_kernel, ctx->device, ceiling));
         if (smem_iv > (size_t)ceiling) return NDMPS_OK;
     }
     double *V, *tau, *d, *e, *pbuf, *rowbuf, *lam, *bounds, *Xa, *Xb, *S, *Linv, *TQ, *H, *hev, *W, *factors;
@@ -980,14 +974,8 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
         NDMPS_TRY(ctx->ws.get<double>((size_t)n * n, &Awork));
         NDMPS_CUDA_TRY(cudaMemcpyAsync(Awork, G, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         const size_t smem_big = (size_t)3 * n * sizeof(double);
-        static std::once_flag once_big;
-        static cudaError_t rc_big = cudaSuccess;
-        std::call_once(once_big, [&]() {
-            rc_big = cudaFuncSetAttribute(tridiag_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * NMAX * sizeof(double)));
-            if (rc_big == cudaSuccess)
-                rc_big = cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NMAX * sizeof(double)));
-        });
-        NDMPS_CUDA_TRY(rc_big);
+        NDMPS_TRY(raise_dynamic_smem((const void*)tridiag_big_kernel, ctx->device, (int)(3 * NMAX * sizeof(double))));
+        NDMPS_TRY(raise_dynamic_smem((const void*)bisect_kernel, ctx->device, (int)(2 * NMAX * sizeof(double))));
         int n_arg = n, ldv_arg = ldv;
         // the fused pass is bound by L2 latency per warp: as many resident warps as fit (up to 3 CTAs per SM)
         int per_sm = 1;

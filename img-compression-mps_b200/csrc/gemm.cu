@@ -5,7 +5,7 @@
 // float64), and all bond-sized glue (r x r, <= a few thousand) runs through it.
 // B200 keeps a full-rate FP64 pipe (about half the FP32 SIMT rate), so this path is
 // not the bottleneck for bond-sized problems; the long-K Gram of the first
-// unfoldings has a tcgen05 split-precision alternative (gram_tc.cu).
+// unfoldings of a capped float32 sweep goes to tcgen05 on split planes (tc_gemm.cu).
 //
 // C (m x n, row-major, ldc) = alpha * A (m x k) * B (k x n); A and B are addressed
 // as a[i*rs + j*cs], so transposes and K-major / MN-major operands need no copies.
@@ -149,6 +149,14 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     NDMPS_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative size");
     NDMPS_REQUIRE(dtype_ok(dtype_a) && dtype_ok(dtype_b) && dtype_ok(dtype_c), "gemm: bad dtype");
     if (m == 0 || n == 0) return NDMPS_OK;
+    if (ctx->opt_gemm_path == 3 || (ctx->opt_gemm_path == 0 && ctx->opt_tc && ctx->tc_gemm)) {
+        // tcgen05 on bf16x3 planes (tc_gemm.cu): float32-class products of the capped sweep and the reconstruction
+        bool done = false;
+        NDMPS_TRY(gemm_tc(ctx, m, n, k, alpha, a, dtype_a, a_rs, a_cs, b, dtype_b, b_rs, b_cs, c, dtype_c, ldc,
+                          ctx->opt_gemm_out_t != 0, &done));
+        if (done) return NDMPS_OK;
+        NDMPS_REQUIRE(ctx->opt_gemm_out_t == 0, "gemm: transposed output needs the tcgen05 path (shape not eligible)");
+    }
     {   // large row-major products go to the FP64 tensor pipe (gemm_dmma.cu)
         bool done = false;
         NDMPS_TRY(gemm_dmma(ctx, m, n, k, alpha, a, dtype_a, a_rs, a_cs, b, dtype_b, b_rs, b_cs, c, dtype_c, ldc, &done));
@@ -196,6 +204,12 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
 int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
 
 int gram(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev) {
+    if (side == 0 && (ctx->opt_gram_path == 3 || (ctx->opt_gram_path == 0 && ctx->opt_tc && ctx->tc_sweep))) {
+        // tcgen05 on bf16x3 planes, float64 drains (tc_gemm.cu): float32 unfoldings of a capped sweep
+        bool done = false;
+        NDMPS_TRY(gram_tc(ctx, mat, rows, cols, ld, dtype, g_dev, &done));
+        if (done) return NDMPS_OK;
+    }
     if (side == 0 && ctx->opt_gram_path != 2) {   // FP64 tensor-pipe path when the shape allows (gram_dmma.cu)
         bool done = false;
         NDMPS_TRY(gram_dmma(ctx, mat, rows, cols, ld, dtype, g_dev, &done));

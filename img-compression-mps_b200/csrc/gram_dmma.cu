@@ -164,11 +164,7 @@ int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64
     double* partial = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)splits * ntiles * TM * TM, &partial));
     const size_t smem = (size_t)2 * STAGES * TM * LDS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    NDMPS_TRY(raise_dynamic_smem((const void*)gram_dmma_kernel, ctx->device, (int)smem));
     dim3 grid((unsigned)ntiles, (unsigned)splits);
     gram_dmma_kernel<<<grid, THREADS, smem, ctx->stream>>>((const float*)mat, m, cols, ld, nt, k_per, partial);
     NDMPS_LAUNCH_CHECK(ctx);

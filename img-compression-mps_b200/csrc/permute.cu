@@ -424,24 +424,31 @@ static void build_tile_plan(const DigitList& dl, TilePlan& tp) {
 
 static std::mutex g_upload_mutex;   // plans are shared between host threads (batch.py); the upload happens once
 
-static int upload_tile_plan(TilePlan& tp, int device) {
+// Returns (a copy of) the table pointers of `device`, uploading them on first use.  The copy is taken under the
+// lock, so host threads driving different GPUs with one shared plan never see each other's pointers.
+static int upload_tile_plan(TilePlan& tp, int device, TilePlan::DevTables* out) {
     std::lock_guard<std::mutex> lock(g_upload_mutex);
-    if (tp.device == device && tp.d_pos) return NDMPS_OK;
-    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_src, tp.hi_src.size() * sizeof(int64_t)));
-    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_hi_dst, tp.hi_dst.size() * sizeof(int64_t)));
-    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_pos, tp.pos.size() * sizeof(uint16_t)));
-    NDMPS_CUDA_TRY(cudaMalloc(&tp.d_rslot, tp.rslot.size() * sizeof(uint16_t)));
-    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_rslot, tp.rslot.data(), tp.rslot.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_hi_src, tp.hi_src.data(), tp.hi_src.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_hi_dst, tp.hi_dst.data(), tp.hi_dst.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-    NDMPS_CUDA_TRY(cudaMemcpy(tp.d_pos, tp.pos.data(), tp.pos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    tp.device = device;
+    for (const auto& d : tp.dev)
+        if (d.device == device) { *out = d; return NDMPS_OK; }
+    TilePlan::DevTables d;
+    d.device = device;
+    NDMPS_CUDA_TRY(cudaMalloc(&d.hi_src, tp.hi_src.size() * sizeof(int64_t)));
+    NDMPS_CUDA_TRY(cudaMalloc(&d.hi_dst, tp.hi_dst.size() * sizeof(int64_t)));
+    NDMPS_CUDA_TRY(cudaMalloc(&d.pos, tp.pos.size() * sizeof(uint16_t)));
+    NDMPS_CUDA_TRY(cudaMalloc(&d.rslot, tp.rslot.size() * sizeof(uint16_t)));
+    NDMPS_CUDA_TRY(cudaMemcpy(d.rslot, tp.rslot.data(), tp.rslot.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    NDMPS_CUDA_TRY(cudaMemcpy(d.hi_src, tp.hi_src.data(), tp.hi_src.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    NDMPS_CUDA_TRY(cudaMemcpy(d.hi_dst, tp.hi_dst.data(), tp.hi_dst.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    NDMPS_CUDA_TRY(cudaMemcpy(d.pos, tp.pos.data(), tp.pos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    tp.dev.push_back(d);
+    *out = d;
     return NDMPS_OK;
 }
 
 template <class T>
 static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, double scale, bool do_scale) {
-    NDMPS_TRY(upload_tile_plan(tp, ctx->device));
+    TilePlan::DevTables dt;
+    NDMPS_TRY(upload_tile_plan(tp, ctx->device, &dt));
     TileArgs ta;
     ta.tile = tp.tile; ta.pa = tp.pa; ta.pb = tp.pb; ta.n_outer = tp.n_outer; ta.n_tiles = tp.n_tiles;
     for (int j = 0; j < tp.n_outer; j++) {
@@ -449,7 +456,7 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
         ta.outer_dst[j] = tp.outer_dst[j];
         ta.outer_src[j] = tp.outer_src[j];
     }
-    ta.hi_src = tp.d_hi_src; ta.hi_dst = tp.d_hi_dst; ta.pos = tp.d_pos;
+    ta.hi_src = dt.hi_src; ta.hi_dst = dt.hi_dst; ta.pos = dt.pos;
     // ---- bulk-copy (TMA-class) variant: every run and offset must be a multiple of 16 bytes ----
     {
         const int q = 16 / (int)sizeof(T);
@@ -468,13 +475,8 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
                 ba.outer_dst[j] = tp.outer_dst[j];
                 ba.outer_src[j] = tp.outer_src[j];
             }
-            ba.hi_src = tp.d_hi_src; ba.hi_dst = tp.d_hi_dst; ba.rslot = tp.d_rslot;
-            static bool attr_set = false;
-            if (!attr_set) {
-                NDMPS_CUDA_TRY(cudaFuncSetAttribute(permute_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)ctx->smem_optin - 2048));
-                attr_set = true;
-            }
+            ba.hi_src = dt.hi_src; ba.hi_dst = dt.hi_dst; ba.rslot = dt.rslot;
+            NDMPS_TRY(raise_dynamic_smem((const void*)permute_bulk_kernel<T>, ctx->device, (int)ctx->smem_optin - 2048));
             int per_sm = (int)((ctx->smem_optin - 2048) / (bsmem + 1024));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 4) per_sm = 4;
@@ -487,12 +489,9 @@ static int permute_tiled(ndmps_ctx* ctx, TilePlan& tp, const T* src, T* dst, dou
     }
     const size_t smem = (size_t)(skew_slot(tp.tile) + 8) * sizeof(T);
     {
-        static bool attr_set2 = false;      // float64 tiles exceed the 48 KB default
-        if (!attr_set2) {
-            NDMPS_CUDA_TRY(cudaFuncSetAttribute(permute_tiled_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            NDMPS_CUDA_TRY(cudaFuncSetAttribute(permute_tiled_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_set2 = true;
-        }
+        // float64 tiles exceed the 48 KB default
+        NDMPS_TRY(raise_dynamic_smem((const void*)permute_tiled_kernel<T, 4>, ctx->device, 96 * 1024));
+        NDMPS_TRY(raise_dynamic_smem((const void*)permute_tiled_kernel<T, 1>, ctx->device, 96 * 1024));
     }
     int64_t grid = tp.n_tiles;
     // measured: the fewer tiles a CTA walks the better (the hardware scheduler balances the tail); 64 CTAs
@@ -614,11 +613,18 @@ int ndmps_plan_create(int ndim, const int64_t* shape, int levels, const int64_t*
 
 int ndmps_plan_destroy(ndmps_plan_t* plan) {
     if (plan) {
+        int cur = -1;
+        cudaGetDevice(&cur);
         for (TilePlan* tp : {&plan->enc_tile, &plan->dec_tile}) {
-            if (tp->d_hi_src) cudaFree(tp->d_hi_src);
-            if (tp->d_hi_dst) cudaFree(tp->d_hi_dst);
-            if (tp->d_pos) cudaFree(tp->d_pos);
-            if (tp->d_rslot) cudaFree(tp->d_rslot);
+            for (auto& d : tp->dev) {
+                if (d.device != cur) cudaSetDevice(d.device);
+                cudaFree(d.hi_src);
+                cudaFree(d.hi_dst);
+                cudaFree(d.pos);
+                cudaFree(d.rslot);
+                if (d.device != cur) cudaSetDevice(cur);
+            }
+            tp->dev.clear();
         }
     }
     delete plan;

@@ -200,7 +200,7 @@ int ndmps_psnr_terms(ndmps_ctx_t* ctx, const void* a, const void* b, int64_t n, 
     NDMPS_TRY(ensure_pinned(ctx, 2));
     double* out_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
-    NDMPS_TRY(reduce_dispatch<2>(ctx, a, b, n, dtype, out_dev));
+    { StageScope sc(ctx, ST_METRIC); NDMPS_TRY(reduce_dispatch<2>(ctx, a, b, n, dtype, out_dev)); }
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     out_host[0] = ctx->pinned[0];

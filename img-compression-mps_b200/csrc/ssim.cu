@@ -167,11 +167,7 @@ template <class T>
 static int launch_ssim_tile(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
                             int64_t nt, double* partial) {
     const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(double) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
-    static bool attr_set = false;
-    if (!attr_set) {
-        NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_kernel<T>, ctx->device, 96 * 1024));
     ssim_tile_kernel<T><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
@@ -413,11 +409,7 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         int64_t nt = bounds_h[k + 1] - bounds_h[k];
         if (batched[k]) {
             const size_t bsm = (size_t)2 * (BT_H + f.win - 1) * (BT_W + f.win - 1) * BT_SLICES * sizeof(T);
-            static bool attr_set = false;
-            if (!attr_set) {
-                NDMPS_CUDA_TRY(cudaFuncSetAttribute(ssim_tile_batched_kernel<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-                attr_set = true;
-            }
+            NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7>, ctx->device, 112 * 1024));
             NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, true, range + slice_off));
             ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
                                                                                  partial + bounds_h[k]);
@@ -475,6 +467,7 @@ int ndmps_ssim(ndmps_ctx_t* ctx, const void* a, const void* b, int dtype, int nd
             return NDMPS_OK;
         }
     }
+    StageScope sc(ctx, ST_METRIC);
     if (dtype == NDMPS_F32) return ssim_typed<float>(ctx, (const float*)a, (const float*)b, nfam, fams, out_host);
     return ssim_typed<double>(ctx, (const double*)a, (const double*)b, nfam, fams, out_host);
 }

@@ -1,0 +1,624 @@
+// K2 / K5 / K7 on the 5th-generation tensor cores: tcgen05.mma on bf16x3 split planes.
+//
+// The capped (max_bond) float32 sweep of `MatrixProductState.from_dense` (core/ndmps.py:74) and
+// the contraction of `to_tensor` (core/ndmps.py:140) need float32-class products with
+// better-than-float32 accumulation; tcgen05 has no float32/float64 kind.  A float32 value splits
+// EXACTLY into three bfloat16 values (8 + 8 + 8 significand bits, round to nearest at every step:
+// x = h + m + l), so
+//
+//     a . b  =  h.h + (h.m + m.h) + (h.l + l.h + m.m)  +  O(2^-26 |a||b|)
+//
+// is six kind::f16 MMAs with float32 accumulation in TMEM.  The operands live in HBM as "split
+// planes" (bf16[3][rows][ld]); tiles arrive in shared memory by TMA (cp.async.bulk.tensor, 128-byte
+// swizzle, out-of-range rows/columns zero-filled), one elected thread issues the MMAs, the
+// accumulators stay in tensor memory and come back with tcgen05.ld.
+//
+//   * gram_tc_kernel : G = M M^T.  K = C is long (2^15 .. 2^18): the TMEM accumulator is drained
+//     every `chunk` k-tiles into float64 registers (ping-pong accumulators, so draining overlaps
+//     the MMAs) - the float32 rounding of an accumulator then acts on short partial sums only.
+//     Upper-triangle tiles, split-K partials reduced in fixed order (deterministic, symmetric).
+//   * gemm_tc_kernel : C = A B for the projection T = P^T M and the final contraction
+//     dense = X W: K is bond-sized, the whole K loop accumulates in TMEM.  Either operand may be
+//     K-major or MN-major (the big unfolding is MN-major for the projection); the output is written
+//     row-major or transposed.
+//
+// Warp roles (one CTA per SM: the stages fill its shared memory): warp 0 TMA producer, warp 1 MMA
+// issuer, warp 2 TMEM allocator, warps 4-11 epilogue (TMEM lane quadrant = warp % 4).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ndmps {
+namespace tc {
+
+constexpr int TILE = 128;                 // MMA M (rows of A per CTA) and the Gram's N
+constexpr int BK = 64;                    // bf16 elements per k-tile: one 128-byte swizzled row
+constexpr int UK = 16;                    // K of one tcgen05.mma.kind::f16
+constexpr int PLANE_TILE = TILE * BK * 2; // bytes of one 128 x 64 bf16 tile
+constexpr int CTRL_THREADS = 128, EPI_THREADS = 256, THREADS = CTRL_THREADS + EPI_THREADS;
+constexpr unsigned long long SPIN_LIMIT = 4000000000ull;   // ~2 s of SM clocks: a protocol bug traps instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if ((unsigned long long)clock64() - t0 > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, float32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on `bar` when every tcgen05 operation this thread issued so far has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive float32 columns: thread t of the warp gets lane (quadrant base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle, descriptor version 1 (sm_100).
+//   K-major  tile (rows x 64 bf16, 128-byte rows, 8-row groups 1024 B apart): lbo = 1 (unused), sbo = 1024 B;
+//            the k-step inside the swizzled row advances the start address by 32 B.
+//   MN-major tile (64 k-rows x 64 bf16 per TMA box, boxes 8192 B apart along MN): lbo = 8192 B, sbo = 1024 B
+//            (8 k-rows); a k-step of 16 rows advances the start address by 2048 B.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16 instruction descriptor: D float32, A and B bfloat16, M x N, majors (0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
+// the six products kept, most significant first: (plane of A, plane of B)
+__device__ __constant__ int8_t TERM_A[6] = {0, 0, 1, 0, 2, 1};
+__device__ __constant__ int8_t TERM_B[6] = {0, 1, 0, 2, 0, 1};
+
+__device__ __forceinline__ void upper_tile(int t, int nt, int& ti, int& tj) {
+    int row = 0, left = t;
+    while (left >= nt - row) { left -= nt - row; row++; }
+    ti = row;
+    tj = row + left;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float32 / float64 -> three bfloat16 planes (x = h + m + l, every step round-to-nearest)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void split3(T x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn((float)x);
+    T r = x - (T)__bfloat162float(h);
+    m = __float2bfloat16_rn((float)r);
+    r = r - (T)__bfloat162float(m);
+    l = __float2bfloat16_rn((float)r);
+}
+
+// src: rows x cols (row stride ld_src, optional transpose: element (r, c) read from src[c * ld_src + r]);
+// dst: bf16[3][rows][ldp], columns cols..ldp-1 zeroed.  Eight elements per thread (16-byte stores).
+template <class T, bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const T* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src, double alpha,
+                    __nv_bfloat16* __restrict__ dst, int64_t ldp, int64_t plane_stride) {
+    const int64_t groups = ldp >> 3, total = rows * groups, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / groups, c0 = (i - r * groups) << 3;
+        __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+        T v[8];
+        if constexpr (!TRANSPOSE) {
+            const T* p = src + r * ld_src + c0;
+            if (sizeof(T) == 4 && c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+                v[0] = (T)a.x; v[1] = (T)a.y; v[2] = (T)a.z; v[3] = (T)a.w; v[4] = (T)b.x; v[5] = (T)b.y; v[6] = (T)b.z; v[7] = (T)b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = c0 + j < cols ? p[j] : (T)0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = c0 + j < cols ? src[(c0 + j) * ld_src + r] : (T)0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) split3<T>(v[j] * (T)alpha, h[j], m[j], l[j]);
+        __nv_bfloat16* o = dst + r * ldp + c0;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<const uint4*>(m);
+        *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram: partial[split][tile] (float64 128 x 128) = sum over this CTA's K range of A_ti . A_tj^T
+// ---------------------------------------------------------------------------------------------
+struct GramSmem {
+    static constexpr int STAGES = 2;
+    static constexpr int STAGE_BYTES = 6 * PLANE_TILE;          // A planes h, m, l + B planes h, m, l
+    static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BARRIER_OFF + 128 + 1024;      // + alignment slack
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64_t k_per, int chunk, double* __restrict__ partial) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GramSmem::BARRIER_OFF);
+    uint64_t* empty = full + GramSmem::STAGES;
+    uint64_t* acc_full = empty + GramSmem::STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int ti, tj;
+    upper_tile(blockIdx.x, nt, ti, tj);
+    const int64_t kbeg = (int64_t)blockIdx.y * k_per;
+    const int64_t kend = kbeg + k_per < K ? kbeg + k_per : K;
+    const int nk = (int)((kend - kbeg + BK - 1) / BK);
+    const int n_chunks = (nk + chunk - 1) / chunk;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map);
+        for (int s = 0; s < GramSmem::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS / 32); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            // ---- TMA producer ----
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % GramSmem::STAGES;
+                mbar_wait(&empty[s], ((kt / GramSmem::STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], GramSmem::STAGE_BYTES);
+                uint8_t* st = smem + s * GramSmem::STAGE_BYTES;
+                const int kc = (int)(kbeg + (int64_t)kt * BK);
+#pragma unroll
+                for (int p = 0; p < 3; p++) {
+                    tma_load_3d(st + p * PLANE_TILE, &map, &full[s], kc, ti * TILE, p);
+                    tma_load_3d(st + (3 + p) * PLANE_TILE, &map, &full[s], kc, tj * TILE, p);
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc = instr_desc(TILE, TILE, 0, 0);
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % GramSmem::STAGES;
+                const int c = kt / chunk, within = kt - c * chunk, buf = c & 1;
+                if (within == 0) {
+                    mbar_wait(&acc_empty[buf], ((c >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], (kt / GramSmem::STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * GramSmem::STAGE_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)buf * TILE;
+#pragma unroll
+                for (int ks = 0; ks < BK / UK; ks++) {
+#pragma unroll
+                    for (int t = 0; t < 6; t++) {
+                        const uint64_t da = smem_desc(st + TERM_A[t] * PLANE_TILE + ks * 32, 16, 1024);
+                        const uint64_t db = smem_desc(st + (3 + TERM_B[t]) * PLANE_TILE + ks * 32, 16, 1024);
+                        umma_bf16(d, da, db, idesc, (within | ks | t) != 0);
+                    }
+                }
+                umma_commit(&empty[s]);                                   // the stage is free once these MMAs have read it
+                if (within == chunk - 1 || kt == nk - 1) umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ---- epilogue: drain the accumulator of every chunk into float64 registers ----
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        double acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; i++) acc[i] = 0.0;
+        for (int c = 0; c < n_chunks; c++) {
+            const int buf = c & 1;
+            mbar_wait(&acc_full[buf], (c >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE + half * 64 + g * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[g * 32 + i] += (double)__uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * TILE + (size_t)(q * 32 + lane) * TILE + half * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) *reinterpret_cast<double2*>(out + i) = make_double2(acc[i], acc[i + 1]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// G[i][j] = G[j][i] = sum over splits, in split order
+__global__ void __launch_bounds__(256)
+gram_tc_reduce_kernel(const double* __restrict__ partial, int m, int nt, int ntiles, int splits, double* __restrict__ G) {
+    int ti, tj;
+    upper_tile(blockIdx.y, nt, ti, tj);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TILE * TILE; e += gridDim.x * blockDim.x) {
+        const int r = e / TILE, c = e - r * TILE;
+        const int gi = ti * TILE + r, gj = tj * TILE + c;
+        if (gi >= m || gj >= m || (ti == tj && gj < gi)) continue;
+        double s = 0.0;
+        for (int z = 0; z < splits; z++) s += partial[((size_t)z * ntiles + blockIdx.y) * TILE * TILE + e];
+        G[(size_t)gi * m + gj] = s;
+        G[(size_t)gj * m + gi] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C (m x n) = A (m x k) . B (k x n), bond-sized k, one CTA per 128 x BN output tile
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = 3 * PLANE_TILE;
+    static constexpr int B_PLANE = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + 3 * B_PLANE;
+    static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BARRIER_OFF + 128 + 1024;
+};
+
+// A_MN / B_MN: operand stored MN-major (planes are [k][mn]) instead of K-major ([mn][k]).
+// OUT_T: write C transposed (C[n][m], lanes = consecutive m: coalesced) instead of row-major (through a
+// per-warp shared-memory transpose so that rows leave in 128-byte lines).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool OUT_T, class TC>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t m, int64_t n,
+               int64_t k, TC* __restrict__ C, int64_t ldc) {
+    using S = GemmSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BARRIER_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TILE, n0 = (int64_t)blockIdx.y * BN;
+    const int nk = (int)((k + BK - 1) / BK);
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % STAGES;
+            mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full[s], S::STAGE_BYTES);
+            uint8_t* st = smem + s * S::STAGE_BYTES;
+            const int k0 = kt * BK;
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                uint8_t* a = st + p * PLANE_TILE;
+                if constexpr (A_MN) {      // two boxes of 64 k-rows x 64 mn-columns
+                    tma_load_3d(a, &map_a, &full[s], (int)m0, k0, p);
+                    tma_load_3d(a + PLANE_TILE / 2, &map_a, &full[s], (int)m0 + 64, k0, p);
+                } else {                   // one box of 128 mn-rows x 64 k-columns
+                    tma_load_3d(a, &map_a, &full[s], k0, (int)m0, p);
+                }
+                uint8_t* b = st + S::A_BYTES + p * S::B_PLANE;
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; h++) tma_load_3d(b + h * 8192, &map_b, &full[s], (int)n0 + 64 * h, k0, p);
+                } else {
+                    tma_load_3d(b, &map_b, &full[s], k0, (int)n0, p);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = instr_desc(TILE, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % STAGES;
+            mbar_wait(&full[s], (kt / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ks++) {
+#pragma unroll
+                for (int t = 0; t < 6; t++) {
+                    const uint32_t a_addr = st + TERM_A[t] * PLANE_TILE + (A_MN ? ks * 2048 : ks * 32);
+                    const uint32_t b_addr = st + S::A_BYTES + TERM_B[t] * S::B_PLANE + (B_MN ? ks * 2048 : ks * 32);
+                    const uint64_t da = A_MN ? smem_desc(a_addr, 8192, 1024) : smem_desc(a_addr, 16, 1024);
+                    const uint64_t db = B_MN ? smem_desc(b_addr, 8192, 1024) : smem_desc(b_addr, 16, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (kt | ks | t) != 0);
+                }
+            }
+            umma_commit(&empty[s]);
+            if (kt == nk - 1) umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        // stage buffers are dead once acc_full has fired: reuse them for the per-warp transpose (33-float rows)
+        float* xpose = reinterpret_cast<float*>(smem) + (warp - 4) * 32 * 33;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        constexpr int CPW = BN / 2;                       // columns per warp (the two halves split N)
+        const int64_t row = m0 + q * 32 + lane;
+#pragma unroll
+        for (int g = 0; g < CPW / 32; g++) {
+            uint32_t v[32];
+            const int col0 = half * CPW + g * 32;
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+            if constexpr (OUT_T) {
+                if (row < m) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const int64_t cn = n0 + col0 + i;
+                        if (cn < n) C[cn * ldc + row] = (TC)__uint_as_float(v[i]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++) xpose[lane * 33 + i] = __uint_as_float(v[i]);
+                __syncwarp();
+                const int64_t cn = n0 + col0 + lane;
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    const int64_t rr = m0 + q * 32 + r;
+                    if (rr < m && cn < n) C[rr * ldc + cn] = (TC)xpose[r * 33 + lane];
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// planes: bf16[3][rows][ldp]; box = 64 columns x box_rows rows x 1 plane, 128-byte swizzle, zero fill outside
+static int make_plane_map(CUtensorMap* map, const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride,
+                          int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tc: cuTensorMapEncodeTiled is not available from the driver"); return NDMPS_ERR_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldp * 2, (cuuint64_t)plane_stride * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled failed (%d) rows %lld cols %lld ld %lld", (int)r, (long long)rows, (long long)cols, (long long)ldp); return NDMPS_ERR_CUDA; }
+    return NDMPS_OK;
+}
+
+static inline int64_t round8(int64_t x) { return (x + 7) & ~int64_t(7); }
+
+}  // namespace tc
+
+// Split `src` (rows x cols, optionally read transposed) into planes in the workspace.
+int tc_split(ndmps_ctx* ctx, const void* src, int dtype, int64_t rows, int64_t cols, int64_t ld_src, bool transpose, double alpha,
+             __nv_bfloat16** planes_out, int64_t* ldp_out, int64_t* plane_stride_out) {
+    using namespace tc;
+    const int64_t ldp = round8(cols), pstride = rows * ldp;
+    __nv_bfloat16* planes = nullptr;
+    NDMPS_TRY(ctx->ws.get<__nv_bfloat16>((size_t)(3 * pstride), &planes));
+    const int64_t total = rows * (ldp >> 3);
+    int64_t want = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    const int g = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+#define NDMPS_SPLIT(T, TR) split_planes_kernel<T, TR><<<g, 256, 0, ctx->stream>>>((const T*)src, rows, cols, ld_src, alpha, planes, ldp, pstride)
+    if (dtype == NDMPS_F32) { if (transpose) NDMPS_SPLIT(float, true); else NDMPS_SPLIT(float, false); }
+    else { if (transpose) NDMPS_SPLIT(double, true); else NDMPS_SPLIT(double, false); }
+#undef NDMPS_SPLIT
+    NDMPS_LAUNCH_CHECK(ctx);
+    *planes_out = planes;
+    *ldp_out = ldp;
+    *plane_stride_out = pstride;
+    return NDMPS_OK;
+}
+
+// G = M M^T from the float32 unfolding `mat` (rows x cols, row stride ld).  *done = false: shape not eligible.
+int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done) {
+    using namespace tc;
+    *done = false;
+    if (dtype != NDMPS_F32 || rows < 64 || rows > 4096 || cols < 2048) return NDMPS_OK;
+    __nv_bfloat16* planes = nullptr;
+    int64_t ldp = 0, pstride = 0;
+    NDMPS_TRY(tc_split(ctx, mat, dtype, rows, cols, ld, false, 1.0, &planes, &ldp, &pstride));
+    CUtensorMap map;
+    NDMPS_TRY(make_plane_map(&map, planes, rows, cols, ldp, pstride, TILE));
+    const int m = (int)rows, nt = (m + TILE - 1) / TILE, ntiles = nt * (nt + 1) / 2;
+    const int chunk = ctx->opt_tc_chunk > 0 ? (int)ctx->opt_tc_chunk : 4;          // k-tiles of 64 between accumulator drains
+    // whole waves of one CTA per SM; a CTA's K range is a multiple of the drain chunk
+    int64_t splits = (int64_t)ctx->sm_count / ntiles;
+    if (splits < 1) splits = 1;
+    const int64_t unit = (int64_t)BK * chunk;
+    int64_t k_per = (cols + splits - 1) / splits;
+    k_per = ((k_per + unit - 1) / unit) * unit;
+    splits = (cols + k_per - 1) / k_per;
+    double* partial = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)splits * ntiles * TILE * TILE, &partial));
+    NDMPS_TRY(raise_dynamic_smem((const void*)gram_tc_kernel, ctx->device, GramSmem::TOTAL));
+    dim3 grid((unsigned)ntiles, (unsigned)splits);
+    gram_tc_kernel<<<grid, THREADS, GramSmem::TOTAL, ctx->stream>>>(map, nt, cols, k_per, chunk, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    ctx->tc_launches++;
+    dim3 rgrid(16, (unsigned)ntiles);
+    gram_tc_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, nt, ntiles, (int)splits, g_dev);
+    NDMPS_LAUNCH_CHECK(ctx);
+    *done = true;
+    return NDMPS_OK;
+}
+
+namespace tc {
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool OUT_T, class TC>
+static int launch_gemm(ndmps_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int64_t m, int64_t n, int64_t k, TC* c, int64_t ldc) {
+    using S = GemmSmem<BN, STAGES>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, OUT_T, TC>;
+    NDMPS_TRY(raise_dynamic_smem((const void*)kern, ctx->device, S::TOTAL));
+    dim3 grid((unsigned)((m + TILE - 1) / TILE), (unsigned)((n + BN - 1) / BN));
+    kern<<<grid, THREADS, S::TOTAL, ctx->stream>>>(ma, mb, m, n, k, c, ldc);
+    NDMPS_LAUNCH_CHECK(ctx);
+    ctx->tc_launches++;
+    return NDMPS_OK;
+}
+
+}  // namespace tc
+
+// C (m x n, row-major ldc; or n x m when out_t) = A . B on the tensor cores.
+//   a: m x k with strides (a_rs, a_cs); b: k x n with strides (b_rs, b_cs); one stride of each must be 1.
+// Operands are split into planes here (the big one costs a pass; bond-sized ones are negligible).
+int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,
+            const void* b, int dtype_b, int64_t b_rs, int64_t b_cs, void* c, int dtype_c, int64_t ldc, bool out_t, bool* done) {
+    using namespace tc;
+    *done = false;
+    if (m < 128 || n < 8 || k < 8 || (a_cs != 1 && a_rs != 1) || (b_cs != 1 && b_rs != 1)) return NDMPS_OK;
+    if (m >= (int64_t(1) << 31) || n >= (int64_t(1) << 31) || k >= (int64_t(1) << 31)) return NDMPS_OK;
+    const bool a_mn = a_cs != 1;                 // a[i * a_rs + j]: K contiguous -> K-major; else M contiguous -> MN-major
+    const bool b_mn = b_cs == 1 && b_rs != 1;    // b[j * b_rs + l]: N contiguous -> MN-major; K contiguous (b_rs == 1) -> K-major
+    // plane matrices as stored: K-major A planes are [m][k]; MN-major A planes are [k][m]; same for B with n
+    __nv_bfloat16 *pa = nullptr, *pb = nullptr;
+    int64_t lda = 0, sa = 0, ldb = 0, sb = 0;
+    if (a_mn) NDMPS_TRY(tc_split(ctx, a, dtype_a, k, m, a_cs, false, alpha, &pa, &lda, &sa));
+    else NDMPS_TRY(tc_split(ctx, a, dtype_a, m, k, a_rs, false, alpha, &pa, &lda, &sa));
+    if (b_mn) NDMPS_TRY(tc_split(ctx, b, dtype_b, k, n, b_rs, false, 1.0, &pb, &ldb, &sb));
+    else NDMPS_TRY(tc_split(ctx, b, dtype_b, n, k, b_cs, false, 1.0, &pb, &ldb, &sb));
+    CUtensorMap ma, mb;
+    if (a_mn) NDMPS_TRY(make_plane_map(&ma, pa, k, m, lda, sa, 64));
+    else NDMPS_TRY(make_plane_map(&ma, pa, m, k, lda, sa, TILE));
+    const int bn = n <= 64 ? 64 : 128;
+    if (b_mn) NDMPS_TRY(make_plane_map(&mb, pb, k, n, ldb, sb, 64));
+    else NDMPS_TRY(make_plane_map(&mb, pb, n, k, ldb, sb, bn));
+#define NDMPS_TC_GO(BN, ST, AMN, BMN)                                                                                          \
+    do {                                                                                                                       \
+        if (dtype_c == NDMPS_F32) {                                                                                            \
+            if (out_t) NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, true, float>(ctx, ma, mb, m, n, k, (float*)c, ldc)));          \
+            else NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, false, float>(ctx, ma, mb, m, n, k, (float*)c, ldc)));               \
+        } else {                                                                                                               \
+            if (out_t) NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, true, double>(ctx, ma, mb, m, n, k, (double*)c, ldc)));        \
+            else NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, false, double>(ctx, ma, mb, m, n, k, (double*)c, ldc)));             \
+        }                                                                                                                      \
+    } while (0)
+    if (bn == 64) {
+        if (a_mn && !b_mn) NDMPS_TC_GO(64, 3, true, false);
+        else if (!a_mn && b_mn) NDMPS_TC_GO(64, 3, false, true);
+        else if (!a_mn && !b_mn) NDMPS_TC_GO(64, 3, false, false);
+        else NDMPS_TC_GO(64, 3, true, true);
+    } else {
+        if (a_mn && !b_mn) NDMPS_TC_GO(128, 2, true, false);
+        else if (!a_mn && b_mn) NDMPS_TC_GO(128, 2, false, true);
+        else if (!a_mn && !b_mn) NDMPS_TC_GO(128, 2, false, false);
+        else NDMPS_TC_GO(128, 2, true, true);
+    }
+#undef NDMPS_TC_GO
+    *done = true;
+    return NDMPS_OK;
+}
+
+}  // namespace ndmps

@@ -16,13 +16,52 @@ caller would make.
 from __future__ import annotations
 
 import os
+import queue
 import threading
-from concurrent.futures import ThreadPoolExecutor
+from concurrent.futures import Future
 from typing import Callable, Iterable, List, Optional, Sequence
 
 
+def _walk_tensors(obj, seen=None):
+    """Every CUDA torch tensor reachable from ``obj`` through tuples / lists / dicts and the MPS
+    containers of this package (``NDMPS.mps.cores``)."""
+    import torch
+    if seen is None:
+        seen = set()
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            yield obj
+        return
+    if isinstance(obj, (list, tuple)):
+        for x in obj:
+            yield from _walk_tensors(x, seen)
+        return
+    if isinstance(obj, dict):
+        for x in obj.values():
+            yield from _walk_tensors(x, seen)
+        return
+    mps = getattr(obj, "mps", None)
+    cores = getattr(mps if mps is not None else obj, "cores", None)
+    if cores is not None and not isinstance(obj, (str, bytes)):
+        yield from _walk_tensors(list(cores), seen)
+
+
 class VolumePipeline:
-    """``workers`` host threads x (CUDA stream + native context) on the current device."""
+    """``workers`` host threads x (CUDA stream + native context) on one device.
+
+    Stream safety (torch's caching allocator recycles a block as soon as the stream that ALLOCATED it
+    is past its last use, and knows nothing of other streams):
+
+    * item ``i`` of every ``map`` call goes to worker ``i % workers``, so an object that is built in one
+      call and transformed in a later one (the cutoff sweep of ``run_benchmark``) stays on ONE stream;
+    * every device tensor reachable from an item is ``record_stream``-ed on the worker's stream (inputs
+      were allocated on the caller's stream), every device tensor reachable from a result on the
+      caller's stream (results were allocated on the worker's);
+    * a worker synchronises its stream before its future resolves.
+    """
 
     def __init__(self, workers: int = 3, device: Optional[int] = None, blocking_sync: Optional[bool] = None):
         import torch
@@ -39,47 +78,84 @@ class VolumePipeline:
             ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
             blocking_sync = self.workers * ranks_here > max(1, (os.cpu_count() or 1) - 1)
         self.blocking_sync = bool(blocking_sync)
-        self._tls = threading.local()
         self._ctx_lock = threading.Lock()
         self._contexts = []                             # the workers' native contexts (for launch counts / options)
-        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="ndmps-worker",
-                                        initializer=self._init_worker)
+        self._queues = [queue.SimpleQueue() for _ in range(self.workers)]
+        self._threads = [threading.Thread(target=self._worker, args=(w,), name=f"ndmps-worker-{w}", daemon=True)
+                         for w in range(self.workers)]
+        self._ready = threading.Barrier(self.workers + 1)
+        for t in self._threads:
+            t.start()
+        self._ready.wait()
+        self._closed = False
 
     # -- worker side ---------------------------------------------------------------------------
-    def _init_worker(self):
+    def _worker(self, index: int):
         import torch
         from . import _native
         torch.cuda.set_device(self.device)
-        self._tls.stream = torch.cuda.Stream(device=self.device)
-        self._tls.done = torch.cuda.Event(blocking=self.blocking_sync)
+        stream = torch.cuda.Stream(device=self.device)
+        done = torch.cuda.Event(blocking=self.blocking_sync)
         ctx = _native.context()
         if self.blocking_sync:                          # sleep, do not spin, while the GPU works
             ctx.set_option("blocking_sync", 1)
         with self._ctx_lock:
             self._contexts.append(ctx)
-
-    def _run(self, fn: Callable, item, ready_event):
-        import torch
-        stream = self._tls.stream
-        with torch.cuda.stream(stream):
-            if ready_event is not None:
-                stream.wait_event(ready_event)          # inputs produced on the submitting stream
-            out = fn(item)
-            self._tls.done.record(stream)
-            self._tls.done.synchronize()                # the result is complete when the future resolves
-        return out
+        self._ready.wait()
+        q = self._queues[index]
+        while True:
+            job = q.get()
+            if job is None:
+                return
+            fn, item, ready_event, caller_stream, fut = job
+            if not fut.set_running_or_notify_cancel():
+                continue
+            try:
+                with torch.cuda.stream(stream):
+                    if ready_event is not None:
+                        stream.wait_event(ready_event)  # inputs produced on the submitting stream
+                    for t in _walk_tensors(item):
+                        t.record_stream(stream)
+                    out = fn(item)
+                    for t in _walk_tensors(out):
+                        t.record_stream(caller_stream)
+                    done.record(stream)
+                    done.synchronize()                  # the result is complete when the future resolves
+                fut.set_result(out)
+            except BaseException as exc:                # noqa: BLE001 - handed to the caller
+                try:
+                    stream.synchronize()
+                except Exception:
+                    pass
+                fut.set_exception(exc)
 
     # -- caller side ---------------------------------------------------------------------------
     def map(self, fn: Callable, items: Iterable) -> List:
         """``[fn(item) for item in items]`` with up to ``workers`` items in flight, in item order.
         ``fn`` runs with the worker's stream current, so everything it launches (native calls
         included) lands there; device inputs must already be materialised on the calling
-        stream, which the workers wait for."""
+        stream, which the workers wait for.  Item ``i`` always runs on worker ``i % workers``."""
         import torch
+        if self._closed:
+            raise RuntimeError("VolumePipeline is closed")
+        caller_stream = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
-        futures = [self._pool.submit(self._run, fn, item, ready) for item in items]
-        return [f.result() for f in futures]
+        ready.record(caller_stream)
+        futures = []
+        for i, item in enumerate(items):
+            fut = Future()
+            self._queues[i % self.workers].put((fn, item, ready, caller_stream, fut))
+            futures.append(fut)
+        results, first_error = [], None
+        for f in futures:                               # wait for ALL items, then raise the first failure
+            try:
+                results.append(f.result())
+            except BaseException as exc:                # noqa: BLE001
+                results.append(None)
+                first_error = first_error or exc
+        if first_error is not None:
+            raise first_error
+        return results
 
     def roundtrip(self, volumes: Sequence, max_bond: Optional[int] = None, cutoff: float = 1e-10, mode: str = "Std",
                   keep: bool = True) -> List:
@@ -112,7 +188,13 @@ class VolumePipeline:
             return sum(c.launch_count() for c in self._contexts)
 
     def close(self):
-        self._pool.shutdown(wait=True)
+        if self._closed:
+            return
+        self._closed = True
+        for q in self._queues:
+            q.put(None)
+        for t in self._threads:
+            t.join()
 
     def __enter__(self):
         return self

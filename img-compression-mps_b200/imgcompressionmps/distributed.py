@@ -170,6 +170,22 @@ class ShardedNDMPS:
     computes on the whole tensor, up to the summation order of the Gram allreduce).
     ``to_local_tensor_device`` reconstructs this rank's sub-lattice (``core/ndmps.py:131-153``)."""
 
+    # data-path collective accounting (read by bench.py): calls, payload bytes and device time of the Gram allreduces
+    _ar = {"calls": 0, "bytes": 0, "events": []}
+
+    @classmethod
+    def allreduce_stats(cls, reset: bool = False) -> Dict:
+        """{calls, bytes, ms} of the Gram allreduces since the last reset (ms from CUDA events on the compute
+        stream; synchronises)."""
+        ms = 0.0
+        for beg, end in cls._ar["events"]:
+            end.synchronize()
+            ms += beg.elapsed_time(end)
+        out = {"calls": cls._ar["calls"], "bytes": cls._ar["bytes"], "ms": ms}
+        if reset:
+            cls._ar = {"calls": 0, "bytes": 0, "events": []}
+        return out
+
     def __init__(self, cores, site_dims, shape, factors, rank, world, singular_values):
         self.cores, self.site_dims, self.shape = cores, [int(d) for d in site_dims], tuple(shape)
         self.factors, self.rank, self.world = factors, int(rank), int(world)
@@ -198,7 +214,17 @@ class ShardedNDMPS:
         L = len(ldims)
 
         def allreduce(t):
+            ar = ShardedNDMPS._ar
+            timed = t.is_cuda and len(ar["events"]) < 4096
+            if timed:
+                beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                beg.record()
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group)
+            if timed:
+                end.record()
+                ar["events"].append((beg, end))
+            ar["calls"] += 1
+            ar["bytes"] += t.numel() * t.element_size()
 
         cores, ranks, svals, rem = _ops.ttsvd_sharded(dense, ldims, world, allreduce if world > 1 else None,
                                                       stop_bytes=stop_bytes, cutoff=cutoff, max_bond=max_bond)
