@@ -111,6 +111,7 @@ struct Arena {
     std::vector<Chunk> chunks;
     size_t high_water = 0;
     size_t cur_total = 0;
+    uint64_t generation = 0;            // bumped by reset(): cached workspace pointers of an older generation are dead
 
     int reset(cudaStream_t stream);
     int alloc(size_t bytes, void** out);
@@ -143,7 +144,9 @@ struct ndmps_ctx {
     int64_t opt_tc = 1;             // tcgen05 contractions on bf16x3 split planes for float32 payloads of a capped sweep / the reconstruction (0: off)
     int64_t opt_tc_chunk = 0;       // k-tiles (64 columns each) between drains of the tcgen05 Gram accumulator into float64 (0: 4)
     int64_t opt_gemm_out_t = 0;     // test hook: ndmps_gemm writes C transposed (n x m) through the tcgen05 epilogue
-    bool tc_gemm = false;           // set around the products that may take the tcgen05 GEMM (projection, final contraction)
+    // planes of the unfolding the tcgen05 Gram split last (workspace memory: valid until the next ws.reset); the
+    // projection of the same sweep step reuses them instead of splitting the unfolding again
+    struct { const void* src = nullptr; int64_t rows = 0, cols = 0, ld = 0; void* planes = nullptr; int64_t ldp = 0, pstride = 0; uint64_t gen = 0; } tc_planes;
     bool tc_sweep = false;          // set by the sweep while the tcgen05 Gram / projection are admissible (float32, bond cap)
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_gemm_path = 0;      // 0: FP64 tensor pipe for large row-major products, 2: SIMT only

@@ -149,7 +149,7 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     NDMPS_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative size");
     NDMPS_REQUIRE(dtype_ok(dtype_a) && dtype_ok(dtype_b) && dtype_ok(dtype_c), "gemm: bad dtype");
     if (m == 0 || n == 0) return NDMPS_OK;
-    if (ctx->opt_gemm_path == 3 || (ctx->opt_gemm_path == 0 && ctx->opt_tc && ctx->tc_gemm)) {
+    if (ctx->opt_gemm_path == 3) {
         // tcgen05 on bf16x3 planes (tc_gemm.cu): float32-class products of the capped sweep and the reconstruction
         bool done = false;
         NDMPS_TRY(gemm_tc(ctx, m, n, k, alpha, a, dtype_a, a_rs, a_cs, b, dtype_b, b_rs, b_cs, c, dtype_c, ldc,

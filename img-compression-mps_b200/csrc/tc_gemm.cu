@@ -13,10 +13,11 @@
 // swizzle, out-of-range rows/columns zero-filled), one elected thread issues the MMAs, the
 // accumulators stay in tensor memory and come back with tcgen05.ld.
 //
-//   * gram_tc_kernel : G = M M^T.  K = C is long (2^15 .. 2^18): the TMEM accumulator is drained
-//     every `chunk` k-tiles into float64 registers (ping-pong accumulators, so draining overlaps
-//     the MMAs) - the float32 rounding of an accumulator then acts on short partial sums only.
-//     Upper-triangle tiles, split-K partials reduced in fixed order (deterministic, symmetric).
+//   * gram_tc_kernel : G = M M^T.  K = C is long (2^15 .. 2^18): the TMEM accumulators are drained
+//     into float64 registers (double-buffered, so draining overlaps the MMAs) - the truncating
+//     float32 accumulation of the tensor core then acts on short chains only (see "Accumulation
+//     discipline" below).  Upper-triangle tiles, split-K partials reduced in fixed order
+//     (deterministic, symmetric).
 //   * gemm_tc_kernel : C = A B for the projection T = P^T M and the final contraction
 //     dense = X W: K is bond-sized, the whole K loop accumulates in TMEM.  Either operand may be
 //     K-major or MN-major (the big unfolding is MN-major for the projection); the output is written
@@ -138,10 +139,6 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, int a_mn, int b_
            ((uint32_t)(m >> 4) << 24);
 }
 
-// the six products kept, most significant first: (plane of A, plane of B)
-__device__ __constant__ int8_t TERM_A[6] = {0, 0, 1, 0, 2, 1};
-__device__ __constant__ int8_t TERM_B[6] = {0, 1, 0, 2, 0, 1};
-
 __device__ __forceinline__ void upper_tile(int t, int nt, int& ti, int& tj) {
     int row = 0, left = t;
     while (left >= nt - row) { left -= nt - row; row++; }
@@ -195,24 +192,42 @@ split_planes_kernel(const T* __restrict__ src, int64_t rows, int64_t cols, int64
 }
 
 // ---------------------------------------------------------------------------------------------
+// Accumulation discipline (measured on B200, tools/tc_probe.py): the tensor core adds into its float32
+// TMEM accumulator with TRUNCATION, a relative bias of about -3e-8 of the accumulator per MMA.  So:
+//   * the leading products h.h (16 significant bits each) go to their OWN accumulator, restarted
+//     every k-tile (4 MMAs of K = 16): 64 products per chain, then the chain is drained by the
+//     epilogue warps and summed on the CUDA cores (round to nearest, unbiased; float64 for the Gram);
+//   * the five correction products (2^-8 and 2^-16 of the result) share a second accumulator with
+//     long chains: the same relative bias there is 2^-8 smaller in the result.
+// Both accumulators are double-buffered so the drains overlap the MMAs of the next k-tile.
+// ---------------------------------------------------------------------------------------------
+// correction products, smallest first: (plane of A, plane of B)
+__device__ __constant__ int8_t REST_A[5] = {1, 2, 0, 1, 0};
+__device__ __constant__ int8_t REST_B[5] = {1, 0, 2, 0, 1};
+
+// ---------------------------------------------------------------------------------------------
 // Gram: partial[split][tile] (float64 128 x 128) = sum over this CTA's K range of A_ti . A_tj^T
 // ---------------------------------------------------------------------------------------------
 struct GramSmem {
     static constexpr int STAGES = 2;
     static constexpr int STAGE_BYTES = 6 * PLANE_TILE;          // A planes h, m, l + B planes h, m, l
     static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BARRIER_OFF + 128 + 1024;      // + alignment slack
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;      // + alignment slack
 };
 
+// TMEM columns: [0, 128) h.h buffer 0, [128, 256) h.h buffer 1, [256, 384) corrections buffer 0, [384, 512) buffer 1.
+// `rest_every`: k-tiles per chain of the correction accumulator.
 __global__ void __launch_bounds__(THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64_t k_per, int chunk, double* __restrict__ partial) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64_t k_per, int rest_every, double* __restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GramSmem::BARRIER_OFF);
     uint64_t* empty = full + GramSmem::STAGES;
-    uint64_t* acc_full = empty + GramSmem::STAGES;     // [2]
-    uint64_t* acc_empty = acc_full + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* hh_full = empty + GramSmem::STAGES;      // [2]
+    uint64_t* hh_empty = hh_full + 2;                  // [2]
+    uint64_t* rest_full = hh_empty + 2;                // [2]
+    uint64_t* rest_empty = rest_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rest_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ti, tj;
@@ -220,15 +235,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64
     const int64_t kbeg = (int64_t)blockIdx.y * k_per;
     const int64_t kend = kbeg + k_per < K ? kbeg + k_per : K;
     const int nk = (int)((kend - kbeg + BK - 1) / BK);
-    const int n_chunks = (nk + chunk - 1) / chunk;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map);
         for (int s = 0; s < GramSmem::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS / 32); }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&hh_full[b], 1); mbar_init(&hh_empty[b], EPI_THREADS / 32);
+            mbar_init(&rest_full[b], 1); mbar_init(&rest_empty[b], EPI_THREADS / 32);
+        }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -255,49 +272,69 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64
             constexpr uint32_t idesc = instr_desc(TILE, TILE, 0, 0);
             for (int kt = 0; kt < nk; kt++) {
                 const int s = kt % GramSmem::STAGES;
-                const int c = kt / chunk, within = kt - c * chunk, buf = c & 1;
-                if (within == 0) {
-                    mbar_wait(&acc_empty[buf], ((c >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                }
+                const int hb = kt & 1;
+                const int rc = kt / rest_every, rwithin = kt - rc * rest_every, rb = rc & 1;
+                mbar_wait(&hh_empty[hb], ((kt >> 1) & 1) ^ 1);
+                if (rwithin == 0) mbar_wait(&rest_empty[rb], ((rc >> 1) & 1) ^ 1);
                 mbar_wait(&full[s], (kt / GramSmem::STAGES) & 1);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * GramSmem::STAGE_BYTES);
-                const uint32_t d = tmem_base + (uint32_t)buf * TILE;
+                const uint32_t d_hh = tmem_base + (uint32_t)hb * TILE;
+                const uint32_t d_rest = tmem_base + 2 * TILE + (uint32_t)rb * TILE;
 #pragma unroll
-                for (int ks = 0; ks < BK / UK; ks++) {
+                for (int ks = 0; ks < BK / UK; ks++)
+                    umma_bf16(d_hh, smem_desc(st + ks * 32, 16, 1024), smem_desc(st + 3 * PLANE_TILE + ks * 32, 16, 1024), idesc, ks != 0);
+                umma_commit(&hh_full[hb]);                                // the epilogue drains this chain while the corrections run
 #pragma unroll
-                    for (int t = 0; t < 6; t++) {
-                        const uint64_t da = smem_desc(st + TERM_A[t] * PLANE_TILE + ks * 32, 16, 1024);
-                        const uint64_t db = smem_desc(st + (3 + TERM_B[t]) * PLANE_TILE + ks * 32, 16, 1024);
-                        umma_bf16(d, da, db, idesc, (within | ks | t) != 0);
+                for (int t = 0; t < 5; t++) {
+#pragma unroll
+                    for (int ks = 0; ks < BK / UK; ks++) {
+                        const uint64_t da = smem_desc(st + REST_A[t] * PLANE_TILE + ks * 32, 16, 1024);
+                        const uint64_t db = smem_desc(st + (3 + REST_B[t]) * PLANE_TILE + ks * 32, 16, 1024);
+                        umma_bf16(d_rest, da, db, idesc, (rwithin | t | ks) != 0);
                     }
                 }
                 umma_commit(&empty[s]);                                   // the stage is free once these MMAs have read it
-                if (within == chunk - 1 || kt == nk - 1) umma_commit(&acc_full[buf]);
+                if (rwithin == rest_every - 1 || kt == nk - 1) umma_commit(&rest_full[rb]);
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ---- epilogue: drain the accumulator of every chunk into float64 registers ----
+        // ---- epilogue: every chain into float64 registers ----
         const int q = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
         double acc[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) acc[i] = 0.0;
-        for (int c = 0; c < n_chunks; c++) {
-            const int buf = c & 1;
-            mbar_wait(&acc_full[buf], (c >> 1) & 1);
+        for (int kt = 0; kt < nk; kt++) {
+            const int hb = kt & 1;
+            mbar_wait(&hh_full[hb], (kt >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < 2; g++) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE + half * 64 + g * 32), v);
+                tmem_ld32(lane_base + (uint32_t)(hb * TILE + g * 32), v);
 #pragma unroll
                 for (int i = 0; i < 32; i++) acc[g * 32 + i] += (double)__uint_as_float(v[i]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) mbar_arrive(&hh_empty[hb]);
+            const int rc = kt / rest_every, rwithin = kt - rc * rest_every, rb = rc & 1;
+            if (rwithin == rest_every - 1 || kt == nk - 1) {
+                mbar_wait(&rest_full[rb], (rc >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + (uint32_t)(2 * TILE + rb * TILE + g * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[g * 32 + i] += (double)__uint_as_float(v[i]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rest_empty[rb]);
+            }
         }
         double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * TILE + (size_t)(q * 32 + lane) * TILE + half * 64;
 #pragma unroll
@@ -307,7 +344,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -336,12 +373,13 @@ struct GemmSmem {
     static constexpr int B_PLANE = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + 3 * B_PLANE;
     static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BARRIER_OFF + 128 + 1024;
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;
 };
 
 // A_MN / B_MN: operand stored MN-major (planes are [k][mn]) instead of K-major ([mn][k]).
 // OUT_T: write C transposed (C[n][m], lanes = consecutive m: coalesced) instead of row-major (through a
 // per-warp shared-memory transpose so that rows leave in 128-byte lines).
+// TMEM columns: [0, BN) h.h buffer 0, [BN, 2 BN) h.h buffer 1, [2 BN, 3 BN) corrections (one chain over all of k).
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool OUT_T, class TC>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t m, int64_t n,
@@ -351,19 +389,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BARRIER_OFF);
     uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* hh_full = empty + STAGES;        // [2]
+    uint64_t* hh_empty = hh_full + 2;          // [2]
+    uint64_t* rest_full = hh_empty + 2;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rest_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TILE, n0 = (int64_t)blockIdx.y * BN;
     const int nk = (int)((k + BK - 1) / BK);
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = BN == 64 ? 256 : 512;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&hh_full[b], 1); mbar_init(&hh_empty[b], EPI_THREADS / 32); }
+        mbar_init(rest_full, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -399,49 +440,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = instr_desc(TILE, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        constexpr uint32_t A_STEP = A_MN ? 2048 : 32, B_STEP = B_MN ? 2048 : 32;
+        constexpr uint32_t A_LBO = A_MN ? 8192 : 16, B_LBO = B_MN ? 8192 : 16;
         for (int kt = 0; kt < nk; kt++) {
-            const int s = kt % STAGES;
+            const int s = kt % STAGES, hb = kt & 1;
+            mbar_wait(&hh_empty[hb], ((kt >> 1) & 1) ^ 1);
             mbar_wait(&full[s], (kt / STAGES) & 1);
             tc_fence_after();
-            const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
+            const uint32_t d_hh = tmem_base + (uint32_t)hb * BN, d_rest = tmem_base + 2 * BN;
 #pragma unroll
-            for (int ks = 0; ks < BK / UK; ks++) {
+            for (int ks = 0; ks < BK / UK; ks++)
+                umma_bf16(d_hh, smem_desc(sa + ks * A_STEP, A_LBO, 1024), smem_desc(sb + ks * B_STEP, B_LBO, 1024), idesc, ks != 0);
+            umma_commit(&hh_full[hb]);
 #pragma unroll
-                for (int t = 0; t < 6; t++) {
-                    const uint32_t a_addr = st + TERM_A[t] * PLANE_TILE + (A_MN ? ks * 2048 : ks * 32);
-                    const uint32_t b_addr = st + S::A_BYTES + TERM_B[t] * S::B_PLANE + (B_MN ? ks * 2048 : ks * 32);
-                    const uint64_t da = A_MN ? smem_desc(a_addr, 8192, 1024) : smem_desc(a_addr, 16, 1024);
-                    const uint64_t db = B_MN ? smem_desc(b_addr, 8192, 1024) : smem_desc(b_addr, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kt | ks | t) != 0);
+            for (int t = 0; t < 5; t++) {
+#pragma unroll
+                for (int ks = 0; ks < BK / UK; ks++) {
+                    const uint64_t da = smem_desc(sa + REST_A[t] * PLANE_TILE + ks * A_STEP, A_LBO, 1024);
+                    const uint64_t db = smem_desc(sb + REST_B[t] * S::B_PLANE + ks * B_STEP, B_LBO, 1024);
+                    umma_bf16(d_rest, da, db, idesc, (kt | t | ks) != 0);
                 }
             }
             umma_commit(&empty[s]);
-            if (kt == nk - 1) umma_commit(acc_full);
+            if (kt == nk - 1) umma_commit(rest_full);
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
-        // stage buffers are dead once acc_full has fired: reuse them for the per-warp transpose (33-float rows)
-        float* xpose = reinterpret_cast<float*>(smem) + (warp - 4) * 32 * 33;
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
         constexpr int CPW = BN / 2;                       // columns per warp (the two halves split N)
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * CPW);
+        float acc[CPW];
+#pragma unroll
+        for (int i = 0; i < CPW; i++) acc[i] = 0.f;
+        for (int kt = 0; kt < nk; kt++) {
+            const int hb = kt & 1;
+            mbar_wait(&hh_full[hb], (kt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < CPW / 32; g++) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + (uint32_t)(hb * BN + g * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[g * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hh_empty[hb]);
+        }
+        mbar_wait(rest_full, 0);
+        tc_fence_after();
+        // every MMA has completed: the stage buffers are dead, reuse them for the per-warp transpose (33-float rows)
+        float* xpose = reinterpret_cast<float*>(smem) + (warp - 4) * 32 * 33;
         const int64_t row = m0 + q * 32 + lane;
 #pragma unroll
         for (int g = 0; g < CPW / 32; g++) {
             uint32_t v[32];
             const int col0 = half * CPW + g * 32;
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+            tmem_ld32(lane_base + (uint32_t)(2 * BN + g * 32), v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc[g * 32 + i] += __uint_as_float(v[i]);
             if constexpr (OUT_T) {
                 if (row < m) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         const int64_t cn = n0 + col0 + i;
-                        if (cn < n) C[cn * ldc + row] = (TC)__uint_as_float(v[i]);
+                        if (cn < n) C[cn * ldc + row] = (TC)acc[g * 32 + i];
                     }
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; i++) xpose[lane * 33 + i] = __uint_as_float(v[i]);
+                for (int i = 0; i < 32; i++) xpose[lane * 33 + i] = acc[g * 32 + i];
                 __syncwarp();
                 const int64_t cn = n0 + col0 + lane;
 #pragma unroll 4
@@ -530,14 +598,16 @@ int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t
     __nv_bfloat16* planes = nullptr;
     int64_t ldp = 0, pstride = 0;
     NDMPS_TRY(tc_split(ctx, mat, dtype, rows, cols, ld, false, 1.0, &planes, &ldp, &pstride));
+    ctx->tc_planes.src = mat; ctx->tc_planes.rows = rows; ctx->tc_planes.cols = cols; ctx->tc_planes.ld = ld;
+    ctx->tc_planes.planes = planes; ctx->tc_planes.ldp = ldp; ctx->tc_planes.pstride = pstride; ctx->tc_planes.gen = ctx->ws.generation;
     CUtensorMap map;
     NDMPS_TRY(make_plane_map(&map, planes, rows, cols, ldp, pstride, TILE));
     const int m = (int)rows, nt = (m + TILE - 1) / TILE, ntiles = nt * (nt + 1) / 2;
-    const int chunk = ctx->opt_tc_chunk > 0 ? (int)ctx->opt_tc_chunk : 4;          // k-tiles of 64 between accumulator drains
-    // whole waves of one CTA per SM; a CTA's K range is a multiple of the drain chunk
+    const int chunk = ctx->opt_tc_chunk > 0 ? (int)ctx->opt_tc_chunk : 8;          // k-tiles of 64 per chain of the correction accumulator
+    // whole waves of one CTA per SM
     int64_t splits = (int64_t)ctx->sm_count / ntiles;
     if (splits < 1) splits = 1;
-    const int64_t unit = (int64_t)BK * chunk;
+    const int64_t unit = (int64_t)BK;
     int64_t k_per = (cols + splits - 1) / splits;
     k_per = ((k_per + unit - 1) / unit) * unit;
     splits = (cols + k_per - 1) / k_per;
@@ -585,7 +655,10 @@ int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const
     // plane matrices as stored: K-major A planes are [m][k]; MN-major A planes are [k][m]; same for B with n
     __nv_bfloat16 *pa = nullptr, *pb = nullptr;
     int64_t lda = 0, sa = 0, ldb = 0, sb = 0;
-    if (a_mn) NDMPS_TRY(tc_split(ctx, a, dtype_a, k, m, a_cs, false, alpha, &pa, &lda, &sa));
+    const auto& pc = ctx->tc_planes;
+    if (a_mn && alpha == 1.0 && pc.planes && pc.gen == ctx->ws.generation && pc.src == a && pc.rows == k && pc.cols == m && pc.ld == a_cs && dtype_a == NDMPS_F32) {
+        pa = static_cast<__nv_bfloat16*>(pc.planes); lda = pc.ldp; sa = pc.pstride;     // split by the Gram of this sweep step
+    } else if (a_mn) NDMPS_TRY(tc_split(ctx, a, dtype_a, k, m, a_cs, false, alpha, &pa, &lda, &sa));
     else NDMPS_TRY(tc_split(ctx, a, dtype_a, m, k, a_rs, false, alpha, &pa, &lda, &sa));
     if (b_mn) NDMPS_TRY(tc_split(ctx, b, dtype_b, k, n, b_rs, false, 1.0, &pb, &ldb, &sb));
     else NDMPS_TRY(tc_split(ctx, b, dtype_b, n, k, b_cs, false, 1.0, &pb, &ldb, &sb));

@@ -285,6 +285,10 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
         NDMPS_CUDA_TRY(cudaMemcpyAsync(cores_out[0], dense, (size_t)total * esz, cudaMemcpyDeviceToDevice, ctx->stream));
         return NDMPS_OK;
     }
+    // float32 payload with a bond cap: the long Gram and projection passes run on tcgen05 (tc_gemm.cu); the rank
+    // decisions of an UNCAPPED sweep sit at lambda / lambda_1 ~ 1e-10 and keep the exact FP64-pipe path
+    struct TcScope { ndmps_ctx* c; ~TcScope() { c->tc_sweep = false; } } tc_scope{ctx};
+    ctx->tc_sweep = ctx->opt_tc && dtype == NDMPS_F32 && opt.max_bond > 0;
     const void* M = dense;         // current remainder, (r_prev * remaining) elements
     int64_t r_prev = 1;
     int64_t remaining = total;     // elements of the remainder divided by r_prev
@@ -385,11 +389,16 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             NDMPS_TRY(ctx->ws.alloc((size_t)(r_out * C) * esz, &T));
             {
                 StageScope sc(ctx, ST_PROJECT);
-                // P^T made explicit (r x D, tiny) so the big product reads both operands along their rows
-                double* Pt = nullptr;
-                NDMPS_TRY(ctx->ws.get<double>((size_t)(r_out * D), &Pt));
-                NDMPS_TRY(scaled_transpose(ctx, P, r_out, D, r_out, nullptr, 1.0, Pt, NDMPS_F64));
-                NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, Pt, NDMPS_F64, D, 1, M, dtype, C, 1, T, dtype, C));
+                bool on_tc = false;
+                if (ctx->tc_sweep && C >= 2048)   // T^T = M^T P on tcgen05: the unfolding is the MN-major operand, T leaves transposed
+                    NDMPS_TRY(gemm_tc(ctx, C, r_out, D, 1.0, M, dtype, 1, C, P, NDMPS_F64, r_out, 1, T, dtype, C, true, &on_tc));
+                if (!on_tc) {
+                    // P^T made explicit (r x D, tiny) so the big product reads both operands along their rows
+                    double* Pt = nullptr;
+                    NDMPS_TRY(ctx->ws.get<double>((size_t)(r_out * D), &Pt));
+                    NDMPS_TRY(scaled_transpose(ctx, P, r_out, D, r_out, nullptr, 1.0, Pt, NDMPS_F64));
+                    NDMPS_TRY(gemm(ctx, r_out, C, D, 1.0, Pt, NDMPS_F64, D, 1, M, dtype, C, 1, T, dtype, C));
+                }
             }
         } else {
             // more rows than columns: Gram on the column side, G' = M^T M = V s^2 V^T
@@ -557,6 +566,11 @@ static int contract_dense(ndmps_ctx* ctx, const void* const* cores, int dtype, i
         cols *= dims[k];
     }
     const int64_t r = ranks[s - 1];
+    if (ctx->opt_tc && dtype == NDMPS_F32 && rows * cols >= (int64_t(1) << 20)) {   // float32 payload: the one big product on tcgen05
+        bool on_tc = false;
+        NDMPS_TRY(gemm_tc(ctx, rows, cols, r, 1.0, X, dtype, r, 1, W, dtype, cols, 1, dense_out, dtype, cols, false, &on_tc));
+        if (on_tc) return NDMPS_OK;
+    }
     return gemm(ctx, rows, cols, r, 1.0, X, dtype, r, 1, W, dtype, cols, 1, dense_out, dtype, cols);
 }
 

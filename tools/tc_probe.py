@@ -45,15 +45,16 @@ def gram_case(name, m):
     exact = _ops.gram(m)
     t_dmma = timed(lambda: _ops.gram(m))
     lam = torch.linalg.eigvalsh(exact).flip(0)
-    for chunk in (1, 2, 4, 8, 16, 64):
+    for chunk in (1, 8, 64):
         ctx.set_option("gram_path", 3)
         ctx.set_option("tc_chunk", chunk)
         g = _ops.gram(m)
         t_tc = timed(lambda: _ops.gram(m))
         err = (g - exact)
         rel_max = float(err.abs().max() / exact.abs().max())
-        rel_diag = float((err.diagonal().abs() / exact.diagonal().abs()).max())
-        mean_rel_diag = float((err.diagonal() / exact.diagonal()).mean())
+        nz = exact.diagonal() > 0
+        rel_diag = float((err.diagonal()[nz].abs() / exact.diagonal()[nz]).max())
+        mean_rel_diag = float((err.diagonal()[nz] / exact.diagonal()[nz]).mean())
         lam_tc = torch.linalg.eigvalsh(g).flip(0)
         k = min(64, lam.numel())
         sv_err = float(((lam_tc[:k].clamp_min(0).sqrt() - lam[:k].clamp_min(0).sqrt()).abs() / lam[0].sqrt()).max())
