@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(const T* __restrict__ x, 
         // every step rounded separately (no FMA contraction) so the bytes match numpy's
         double u = __ddiv_rn(__dsub_rn((double)x[i], lo), span);
         double v = __dmul_rn(u, qmax);
-        q[i] = (Q)(long long)v;
+        q[i] = (Q)v;
     }
 }
 
@@ -156,6 +156,35 @@ int minmax_device(ndmps_ctx* ctx, const void* x, int64_t n, int dtype, double* o
 }  // namespace ndmps
 
 using namespace ndmps;
+
+// integer codes of the quantised type: +8/+16/+32/+64 unsigned, -8/-16/-32/-64 signed (numpy iinfo dtypes)
+static bool qcode_ok(int code) { int a = code < 0 ? -code : code; return a == 8 || a == 16 || a == 32 || a == 64; }
+static double qcode_max(int code) {
+    switch (code) {
+        case 8: return 255.0; case 16: return 65535.0; case 32: return 4294967295.0; case 64: return 18446744073709551615.0;
+        case -8: return 127.0; case -16: return 32767.0; case -32: return 2147483647.0; default: return 9223372036854775807.0;
+    }
+}
+
+template <class T>
+static void launch_quantize(ndmps_ctx* ctx, int grid, const T* x, int64_t n, double lo, double span, double qmax, int code, void* q) {
+#define NDMPS_Q(CODE, Q) case CODE: quantize_kernel<T, Q><<<grid, 256, 0, ctx->stream>>>(x, n, lo, span, qmax, (Q*)q); break
+    switch (code) {
+        NDMPS_Q(8, uint8_t); NDMPS_Q(16, uint16_t); NDMPS_Q(32, uint32_t); NDMPS_Q(64, uint64_t);
+        NDMPS_Q(-8, int8_t); NDMPS_Q(-16, int16_t); NDMPS_Q(-32, int32_t); NDMPS_Q(-64, int64_t);
+    }
+#undef NDMPS_Q
+}
+
+template <class T>
+static void launch_dequantize(ndmps_ctx* ctx, int grid, const void* q, int64_t n, double lo, double hi, double qmax, int code, T* x) {
+#define NDMPS_Q(CODE, Q) case CODE: dequantize_kernel<T, Q><<<grid, 256, 0, ctx->stream>>>((const Q*)q, n, lo, hi, qmax, x); break
+    switch (code) {
+        NDMPS_Q(8, uint8_t); NDMPS_Q(16, uint16_t); NDMPS_Q(32, uint32_t); NDMPS_Q(64, uint64_t);
+        NDMPS_Q(-8, int8_t); NDMPS_Q(-16, int16_t); NDMPS_Q(-32, int32_t); NDMPS_Q(-64, int64_t);
+    }
+#undef NDMPS_Q
+}
 
 extern "C" {
 
@@ -211,17 +240,12 @@ int ndmps_psnr_terms(ndmps_ctx_t* ctx, const void* a, const void* b, int64_t n, 
 int ndmps_quantize(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double lo, double hi, int bits, void* q_out) {
     NDMPS_REQUIRE(ctx && x && q_out, "ndmps_quantize: NULL argument");
     NDMPS_REQUIRE(dtype_ok(dtype) && n >= 0, "ndmps_quantize: bad dtype or size");
-    NDMPS_REQUIRE(bits == 8 || bits == 16, "ndmps_quantize: bits must be 8 or 16, got %d", bits);
+    NDMPS_REQUIRE(qcode_ok(bits), "ndmps_quantize: bits must be +-8, +-16, +-32 or +-64 (negative: signed), got %d", bits);
     if (n == 0) return NDMPS_OK;
     int grid = reduce_grid(ctx, n, 4);
-    double span = hi - lo, qmax = bits == 8 ? 255.0 : 65535.0;
-    if (dtype == NDMPS_F32) {
-        if (bits == 8) quantize_kernel<float, uint8_t><<<grid, 256, 0, ctx->stream>>>((const float*)x, n, lo, span, qmax, (uint8_t*)q_out);
-        else quantize_kernel<float, uint16_t><<<grid, 256, 0, ctx->stream>>>((const float*)x, n, lo, span, qmax, (uint16_t*)q_out);
-    } else {
-        if (bits == 8) quantize_kernel<double, uint8_t><<<grid, 256, 0, ctx->stream>>>((const double*)x, n, lo, span, qmax, (uint8_t*)q_out);
-        else quantize_kernel<double, uint16_t><<<grid, 256, 0, ctx->stream>>>((const double*)x, n, lo, span, qmax, (uint16_t*)q_out);
-    }
+    const double span = hi - lo, qmax = qcode_max(bits);
+    if (dtype == NDMPS_F32) launch_quantize<float>(ctx, grid, (const float*)x, n, lo, span, qmax, bits, q_out);
+    else launch_quantize<double>(ctx, grid, (const double*)x, n, lo, span, qmax, bits, q_out);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -229,17 +253,12 @@ int ndmps_quantize(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double
 int ndmps_dequantize(ndmps_ctx_t* ctx, const void* q, int64_t n, int bits, double lo, double hi, int dtype, void* x_out) {
     NDMPS_REQUIRE(ctx && q && x_out, "ndmps_dequantize: NULL argument");
     NDMPS_REQUIRE(dtype_ok(dtype) && n >= 0, "ndmps_dequantize: bad dtype or size");
-    NDMPS_REQUIRE(bits == 8 || bits == 16, "ndmps_dequantize: bits must be 8 or 16, got %d", bits);
+    NDMPS_REQUIRE(qcode_ok(bits), "ndmps_dequantize: bits must be +-8, +-16, +-32 or +-64 (negative: signed), got %d", bits);
     if (n == 0) return NDMPS_OK;
     int grid = reduce_grid(ctx, n, 4);
-    double qmax = bits == 8 ? 255.0 : 65535.0;
-    if (dtype == NDMPS_F32) {
-        if (bits == 8) dequantize_kernel<float, uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)q, n, lo, hi, qmax, (float*)x_out);
-        else dequantize_kernel<float, uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)q, n, lo, hi, qmax, (float*)x_out);
-    } else {
-        if (bits == 8) dequantize_kernel<double, uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)q, n, lo, hi, qmax, (double*)x_out);
-        else dequantize_kernel<double, uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)q, n, lo, hi, qmax, (double*)x_out);
-    }
+    const double qmax = qcode_max(bits);
+    if (dtype == NDMPS_F32) launch_dequantize<float>(ctx, grid, q, n, lo, hi, qmax, bits, (float*)x_out);
+    else launch_dequantize<double>(ctx, grid, q, n, lo, hi, qmax, bits, (double*)x_out);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }

@@ -348,10 +348,25 @@ def overlap(cores_a, cores_b) -> float:
 
 
 # ---- K12 ---------------------------------------------------------------------------
+def int_code(np_dtype) -> int:
+    """The C ABI's name of an integer type: its bit count, negative when signed.  ValueError for anything
+    ``np.iinfo`` rejects, as ``scale_to_dtype`` (``utils/filetools.py:26``) raises."""
+    info = np.iinfo(np.dtype(np_dtype))            # ValueError for non-integer dtypes
+    return int(info.bits) if info.min == 0 else -int(info.bits)
+
+
+def _torch_int(code: int):
+    torch = _torch()
+    return {8: torch.uint8, 16: torch.uint16, 32: torch.uint32, 64: torch.uint64,
+            -8: torch.int8, -16: torch.int16, -32: torch.int32, -64: torch.int64}[code]
+
+
 def quantize(x, lo: float, hi: float, bits: int):
+    """Min-max quantisation of a device tensor to the integer type `bits` names (8 / 16 / 32 / 64 unsigned, negative:
+    signed) -- ``scale_to_dtype`` for every dtype ``np.iinfo`` knows."""
     torch = _torch()
     _dev(x)
-    q = torch.empty(x.shape, dtype=torch.uint8 if bits == 8 else torch.uint16, device=x.device)
+    q = torch.empty(x.shape, dtype=_torch_int(int(bits)), device=x.device)
     N.check(N.load_library().ndmps_quantize(N.handle(), N.ptr(x), x.numel(), N.dtype_code(x.dtype), float(lo), float(hi),
                                             int(bits), N.ptr(q)), "ndmps_quantize")
     return q
@@ -364,6 +379,20 @@ def dequantize(q, lo: float, hi: float, bits: int, dtype):
     N.check(N.load_library().ndmps_dequantize(N.handle(), N.ptr(q), q.numel(), int(bits), float(lo), float(hi),
                                               N.dtype_code(dtype), N.ptr(x)), "ndmps_dequantize")
     return x
+
+
+def to_host_int(q, np_dtype) -> np.ndarray:
+    """Device integer tensor -> numpy array of `np_dtype` (bit reinterpretation where torch lacks numpy interop)."""
+    np_dtype = np.dtype(np_dtype)
+    try:
+        out = q.cpu().numpy()
+        if out.dtype == np_dtype:
+            return out
+    except (TypeError, RuntimeError):
+        pass
+    torch = _torch()
+    raw = q.contiguous().view(torch.uint8).cpu().numpy()
+    return raw.view(np_dtype).reshape(tuple(q.shape))
 
 
 # ---- K9 ---------------------------------------------------------------------------

@@ -192,12 +192,9 @@ class NDMPS:
     def _quantised_device(self, dtype):
         """[uint core on device], following scale_to_dtype (``filetools.py:20-26``) with each
         core's own current min/max."""
-        dtype = np.dtype(dtype)
-        if dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
-            raise ValueError(f"Unsupported dtype {dtype!r}: device quantisation supports uint8 and uint16")
-        bits = get_num_bits(dtype)
+        code = _ops.int_code(dtype)              # any np.iinfo dtype, like the reference; ValueError otherwise
         bounds = _ops.minmax(self.mps.cores)
-        return [_ops.quantize(c, lo, hi, bits) for c, (lo, hi) in zip(self.mps.cores, bounds)], bits
+        return [_ops.quantize(c, lo, hi, code) for c, (lo, hi) in zip(self.mps.cores, bounds)], code
 
     def compress_to_dtype(self, dtype=np.uint16, replace: bool = False):
         """Integer-truncate each core (``core/ndmps.py:182-207``).  De-quantisation uses the
@@ -207,7 +204,7 @@ class NDMPS:
             scaled_back = [_ops.dequantize(q, float(b[0]), float(b[1]), bits, c.dtype)
                            for q, b, c in zip(q_dev, self.boundary_list, self.mps.cores)]
             self.replace_tensordata(scaled_back)
-        return [q.cpu().numpy() for q in q_dev]
+        return [_ops.to_host_int(q, dtype) for q in q_dev]
 
     def get_bytesize_on_disk(self, dtype=np.uint16, replace: bool = False) -> int:
         """Sum of gzip sizes of the quantised cores (``core/ndmps.py:209-234``); the deflate

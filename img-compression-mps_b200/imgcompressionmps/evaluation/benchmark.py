@@ -1,24 +1,44 @@
-"""The reference's cutoff sweep on device-resident data.
+"""The reference's benchmark module on device-resident data.
 
-Mirrors the three functions of ``evaluation/benchmark.py`` that sit directly on the NDMPS path --
-``compress_list`` (:103-118), ``benchmark_metric`` (:121-146) and ``run_benchmark`` (:149-194) --
-with the same names, arguments, result keys and post-processing, so the reference's callers
-(``run_full_benchmark``, the notebook) can import them unchanged.  What differs is how the work
+Mirrors ``evaluation/benchmark.py`` with the same names, arguments, result keys and post-processing:
+``load_tensors`` (:16-55, in ``loader.py``), ``conv_to_mps`` / ``conv_to_tensors`` (:58-100),
+``compress_list`` (:103-118), ``benchmark_metric`` (:121-146), ``run_benchmark`` (:149-194) and
+``run_full_benchmark`` (:197-242, same JSON keys), so the reference's callers (``main.py``, the
+notebook) can import them unchanged.  What differs is how the work
 is issued: the original tensors are put on the device once, every (tensor, cutoff) pair is
 reconstructed ONCE and that reconstruction serves both SSIM and PSNR (the reference calls
 ``to_tensor()`` per metric), nothing but scalars comes back to the host, and the tensors of a
-list are independent, so they run several at a time (``batch.VolumePipeline``).  File loading,
-plotting and result files stay out."""
+list are independent, so they run several at a time (``batch.VolumePipeline``); uploads are
+prefetched through pinned buffers (``loader.prefetch_to_device``).  Plotting stays out."""
 from __future__ import annotations
 
+import json
 from copy import deepcopy
+from pathlib import Path
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
+from ..utils.filetools import find_specific_files, get_shapes, mri_to_slices
 from ..utils.metrics import compute_overlap, compute_psnr, compute_ssim_by_dim
+from .loader import conv_to_mps_streamed, load_tensors          # noqa: F401  (load_tensors is part of this module's API)
 
 _METRICS = ("ssim", "compression_ratio", "bond_dims", "psnr", "fidelity", "storage", "gzip_bytes", "gzip_ratio")
+
+
+def conv_to_mps(data_list, mode="DCT", *, max_bond=None, cutoff: float = 1e-10):
+    """``NDMPS.from_tensor(data, norm=False, mode=mode)`` for every tensor (``benchmark.py:58-79``), one progress line
+    each; the host-to-device copies run ahead of the encoding."""
+    return conv_to_mps_streamed(data_list, mode, max_bond=max_bond, cutoff=cutoff)
+
+
+def conv_to_tensors(mps_list):
+    """``mps.to_tensor()`` for every item (``benchmark.py:82-100``)."""
+    data_list = []
+    for index, mps in enumerate(mps_list):
+        print(f"Converting file {index + 1}/{len(mps_list)}")
+        data_list.append(mps.to_tensor())
+    return data_list
 
 
 def compress_list(mps_list, compression_factors):
@@ -123,3 +143,30 @@ def _layout(name: str, levels: List[List]):
     if name == "bond_dims":
         return levels
     return np.asarray(levels).transpose()
+
+
+def run_full_benchmark(dataset_path, cutoff_list, result_file, datatype="MRI", mode="DCT", start=0, end=-1, ending=".gz",
+                       shape=None):
+    """Data set -> result JSON (``benchmark.py:197-242``): find the files, load (and optionally crop / slice) them,
+    build the MPS list, run the cutoff sweep and write ``datatype, mode, files, cutoff_list, bitsize_list, shapes``
+    plus one list per metric.  Relative result paths land under ``src/evaluation/results`` as in the reference."""
+    result_path = Path(result_file)
+    if not result_path.is_absolute() and not str(result_path).startswith("src/evaluation/results"):
+        result_path = Path("src/evaluation/results") / result_path
+    files = find_specific_files(Path(dataset_path), ending)
+    files = files[start:] if end == -1 else files[start:end]
+    if not files:
+        raise FileNotFoundError(f"No files with extension {ending} found in {dataset_path}")
+    data_list, bitsize_list = load_tensors(files, ending, shape)
+    if datatype == "MRI_Slice":
+        data_list, bitsize_list = mri_to_slices(data_list, bitsize_list)
+    mps_list = conv_to_mps(data_list, mode)
+    print("Starting benchmark...")
+    metrics = run_benchmark(mps_list, data_list, cutoff_list)
+    print(f"Saving results to {result_path}")
+    result_dict = {"datatype": datatype, "mode": mode, "files": files, "cutoff_list": np.asarray(cutoff_list).tolist(),
+                   "bitsize_list": bitsize_list, "shapes": get_shapes(data_list)}
+    result_dict.update({key: value.tolist() if hasattr(value, "tolist") else value for key, value in metrics.items()})
+    result_path.parent.mkdir(parents=True, exist_ok=True)
+    with open(result_path, "w") as f:
+        json.dump(result_dict, f, indent=2)

@@ -7,8 +7,8 @@ the reference computes (its inputs are float64).  Note the reference's order
 sensitivity, kept here: the SECOND argument is the one clipped at 0, and PSNR's
 peak is ``max`` of the FIRST argument.
 
-``compute_mean_std`` (``metrics.py:163-202``) is host-side plotting support and out
-of scope.
+``compute_mean_std`` (``metrics.py:163-202``) is host-side curve aggregation on result
+dictionaries (numpy only).
 """
 from __future__ import annotations
 
@@ -117,3 +117,41 @@ def compute_psnr(original, compressed) -> float:
 def compute_overlap(mps1, mps2) -> float:
     """Normalised overlap <a|b> / (|a| |b|) of two NDMPS objects (``metrics.py:149-160``)."""
     return (mps1.mps @ mps2.mps) / (mps1.norm_value * mps2.norm_value)
+
+
+def _is_prime(n: int) -> bool:
+    n = int(n)
+    if n < 2:
+        return False
+    if n < 4:
+        return True
+    if n % 2 == 0:
+        return False
+    f = 3
+    while f * f <= n:
+        if n % f == 0:
+            return False
+        f += 2
+    return True
+
+
+def compute_mean_std(dict, num_common_points, key_x="compressionratio_list_disk", key_y="ssim_list"):
+    """Mean and standard deviation of the ``key_y`` curves over a common compression-FACTOR grid
+    (``metrics.py:163-202``): x is ``1 / dict[key_x]`` per sample, the grid spans the range every sample
+    covers (from the largest first factor to the smallest last factor), samples whose shape consists of
+    primes only are left out, values outside a sample's own range are NaN (linear interpolation without
+    extrapolation).  Returns ``(mean, std, grid)``; ``(nan, nan, grid)`` when no sample qualifies."""
+    ratios = np.array(dict[key_x])
+    values = np.array(dict[key_y])
+    shapes = np.array(dict["shapes"])
+    factors = 1 / ratios
+    grid = np.linspace(np.max(factors[:, 0]), np.min(factors[:, -1]), num_common_points)
+    curves = []
+    for x, y, shape in zip(factors, values, shapes):
+        if all(_is_prime(extent) for extent in np.atleast_1d(shape)):
+            continue
+        order = np.argsort(x, kind="stable")
+        curves.append(np.interp(grid, x[order], y[order], left=np.nan, right=np.nan))
+    if not curves:
+        return np.nan, np.nan, grid
+    return np.mean(curves, axis=0), np.std(curves, axis=0), np.array(grid)

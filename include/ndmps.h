@@ -205,7 +205,8 @@ int ndmps_overlap(ndmps_ctx_t* ctx, const void* const* cores_a, const int64_t* r
 
 /* ---- K12: min-max quantisation ----------------------------------------------
  * utils/filetools.py:20-26 (scale_to_dtype, truncating cast) and :29-39
- * (scale_back), used by core/ndmps.py:200-204.  bits is 8 or 16. */
+ * (scale_back), used by core/ndmps.py:200-204.  `bits` names the integer type like numpy's iinfo
+ * dtypes: 8 / 16 / 32 / 64 unsigned, -8 / -16 / -32 / -64 signed; iinfo(dtype).max is the scale. */
 int ndmps_quantize(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double lo, double hi, int bits, void* q_out);
 int ndmps_dequantize(ndmps_ctx_t* ctx, const void* q, int64_t n, int bits, double lo, double hi, int dtype, void* x_out);
 
