@@ -58,7 +58,7 @@ WORKLOADS = {
              "name": "configs[0]: 256x256 fp32 synthetic image, chi = 32, reconstruct + PSNR + SSIM"},
     "cfg2": {"shape": (256, 256, 256), "chi": 128, "mode": "Std", "in_flight": 8, "batch": 16, "passes": len(CHI_SWEEP),
              "name": "configs[1]: 256x256x256 fp32 synthetic MRI volume, chi sweep 128/64/32/16/8 + fidelity + 3-D SSIM + PSNR"},
-    "cfg3": {"shape": (512, 512, 512), "chi": 64, "mode": "Std", "in_flight": 4, "batch": 16, "passes": 1,
+    "cfg3": {"shape": (512, 512, 512), "chi": 64, "mode": "Std", "in_flight": 8, "batch": 16, "passes": 1,
              "name": "configs[2]: 512x512x512 fp32 synthetic volume, chi = 64, encode + TT-SVD + reconstruct (north-star target)"},
     "cfg4": {"shape": (64, 64, 32, 400), "chi": 64, "mode": "Std", "in_flight": 4, "batch": 8, "passes": 1,
              "name": "configs[3]: 64x64x32x400 fp32 synthetic fMRI subjects, chi = 64, reconstruct + 4-D SSIM"},
@@ -169,7 +169,7 @@ def algorithmic_work(dims, ranks):
         recon_flops += 2.0 * p * r[k] * dims[k] * r[k + 1]
         p *= dims[k]
     # Gram passes actually executed: sites are front-merged while the fused row count stays <= 512
-    executed = issued = 0.0
+    executed = issued = proj_bytes_exec = gram_bytes_exec = 0.0
     cols, i, rprev = n, 0, 1
     while i < L - 1:
         rows = rprev * dims[i]
@@ -183,10 +183,13 @@ def algorithmic_work(dims, ranks):
         executed += 2.0 * side * side * max(rows, cols)
         nt = -(-side // 128)                                  # gram_dmma computes the upper-triangle 128 x 128 tiles only
         issued += 2.0 * side * side * max(rows, cols) * ((nt + 1) / (2.0 * nt) if side >= 48 else 1.0)
+        gram_bytes_exec += 4.0 * rows * cols
+        proj_bytes_exec += 4.0 * (rows * cols + r[i + k] * cols)
         rprev = r[i + k]
         i += k
     return {"encode_bytes": 8.0 * n, "decode_bytes": 8.0 * n, "sweep_bytes": sweep_bytes, "gram_flops": gram_flops,
-            "gram_flops_executed": executed, "gram_flops_issued": issued,
+            "gram_flops_executed": executed, "gram_flops_issued": issued, "gram_bytes_executed": gram_bytes_exec,
+            "project_bytes_executed": proj_bytes_exec,
             "project_flops": proj_flops, "project_bytes": proj_bytes, "recon_bytes": recon_bytes, "recon_flops": recon_flops}
 
 
@@ -532,9 +535,10 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
                   fp64_tflops, "TFLOP/s (fp64)", "gram_dmma_kernel", {"algorithmic_fp32_flops_per_tensor": f})
     if have("project"):
         ms = stages_per_call["project"][0]
-        b = work["project_bytes"]
-        entry("project", "projection T = P^T M", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
-              "gemm_tc_kernel" if used_tc else "gemm_dmma_kernel", {"algorithmic_bytes_per_tensor": b, "flops_per_tensor": work["project_flops"]})
+        b = work["project_bytes_executed"]
+        entry("project", "projection T = P^T M (one pass per front-merged group)", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
+              "gemm_tc_kernel" if used_tc else "gemm_dmma_kernel", {"algorithmic_bytes_per_tensor": b, "survey_bytes_per_tensor_one_pass_per_site": work["project_bytes"],
+               "flops_per_tensor": work["project_flops"]})
     if have("contract"):
         ms = stages_per_call["contract"][0]
         b = work["recon_bytes"]

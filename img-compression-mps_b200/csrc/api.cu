@@ -301,6 +301,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "blocking_sync")) ctx->opt_blocking_sync = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
+    else if (!strcmp(name, "ssim_exact")) ctx->opt_ssim_exact = value;
     else if (!strcmp(name, "tc_chunk")) ctx->opt_tc_chunk = value;
     else if (!strcmp(name, "gemm_out_t")) ctx->opt_gemm_out_t = value;
     else {

@@ -164,6 +164,7 @@ struct ndmps_ctx {
     int64_t opt_topk_big_ctas = 0;        // CTAs per SM of the L2-streamed tridiagonalisation (0: occupancy, at most 3)
     int64_t opt_topk_passes = 0;          // bisection passes (0: 8, each divides the bracket by 129)
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
+    int64_t opt_ssim_exact = 0;           // 1: float64 SSIM arithmetic for float32 inputs too (default: shifted / normalised float32)
     int64_t opt_blocking_sync = 0;        // host waits sleep on a blocking event instead of spinning (many host threads per core)
     int64_t opt_verbose = 0;
     cudaEvent_t sync_event = nullptr;     // created on first blocking wait

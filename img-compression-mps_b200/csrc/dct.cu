@@ -41,6 +41,13 @@ int ndmps_dct_last_axis(ndmps_ctx_t* ctx, const void* src, void* dst, int64_t li
     int64_t want = (n * n + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
     dct_matrix_kernel<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>(C, n, inverse ? 0 : 1);
     NDMPS_LAUNCH_CHECK(ctx);
+    if (ctx->opt_tc && dtype == NDMPS_F32 && lines * n >= (int64_t(1) << 20)) {
+        // float32 payload: the line x cosine-matrix product on tcgen05 (bf16x3 planes, tc_gemm.cu); both directions are
+        // dst = src . C with the matrix the kernel above built for the direction
+        bool on_tc = false;
+        NDMPS_TRY(gemm_tc(ctx, lines, n, n, 1.0, src, dtype, n, 1, C, NDMPS_F64, n, 1, dst, dtype, n, false, &on_tc));
+        if (on_tc) return NDMPS_OK;
+    }
     if (!inverse)   // y[l, k] = sum_i x[l, i] C[k, i] = sum_i x[l, i] Ct[i, k]
         return gemm(ctx, lines, n, n, 1.0, src, dtype, n, 1, C, NDMPS_F64, n, 1, dst, dtype, n);
     // x[l, i] = sum_k y[l, k] C[k, i]

@@ -204,8 +204,10 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
 int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
 
 int gram(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev) {
-    if (side == 0 && (ctx->opt_gram_path == 3 || (ctx->opt_gram_path == 0 && ctx->opt_tc && ctx->tc_sweep))) {
-        // tcgen05 on bf16x3 planes, float64 drains (tc_gemm.cu): float32 unfoldings of a capped sweep
+    if (side == 0 && ctx->opt_gram_path == 3) {
+        // sliced-integer Gram on tcgen05 kind::i8 (tc_gemm.cu).  NOT the default: with four digits its error on rows with a
+        // heavy-tailed distribution (DCT coefficients, fMRI) moves the trailing kept eigenvectors visibly - measured numbers
+        // in profiles/r02_summary.md - so the sweep keeps the exact FP64-pipe Gram below
         bool done = false;
         NDMPS_TRY(gram_tc(ctx, mat, rows, cols, ld, dtype, g_dev, &done));
         if (done) return NDMPS_OK;

@@ -8,8 +8,20 @@
 // array contributes frames x slices per family.
 //
 // Pass 1: per-slice data range.  Pass 2: tiles of TILE_H x TILE_W interior pixels,
-// separable box sums of x, y, xx, yy, xy in float64 from a shared-memory patch, one
-// partial sum per tile.  Pass 3: fixed-order reduction (deterministic).
+// separable box sums of x, y, xx, yy, xy from a shared-memory patch, one partial sum per
+// tile.  Pass 3: fixed-order reduction (deterministic).
+//
+// Arithmetic (template parameter A of the tile kernels):
+//   * double - what the reference computes (its inputs are float64): float64 inputs always,
+//     float32 inputs when the context option `ssim_exact` is set;
+//   * float  - float32 inputs by default.  SSIM is invariant under x -> x / R and its variance terms
+//     under x -> x - mu, so every tile works on (x - mu) / R with mu its first pixel (per slice in
+//     the slice-batched kernel) and R the slice's data range: values are O(1), C1 = 1e-4 and
+//     C2 = 9e-4 are constants, and the cancellation in E[xx] - E[x]^2 acts on deviations from a
+//     nearby pixel instead of on the raw means.  Tile sums are float32, everything across tiles is
+//     float64.  Agreement with the float64 arithmetic: ~1e-6 per slice (tests), against a 1e-4 bar.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ndmps {
@@ -77,13 +89,14 @@ __global__ void __launch_bounds__(256) ssim_range_kernel(const T* __restrict__ a
 // Horizontal pass: direct win-tap sums.  Vertical pass: a warp owns a strip of TILE_H / 8 output rows
 // (lane = column) and slides the window down with one add and one subtract per quantity instead of
 // `win` adds (for float32 inputs every intermediate is exact in float64).
-template <class T>
+template <class T, class A>
 __global__ void __launch_bounds__(256)
 ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                  int tiles_y, int tiles_x, double* __restrict__ partial) {
+    constexpr bool FAST = std::is_same<A, float>::value;                // shifted / normalised float32 arithmetic
     extern __shared__ unsigned char tile_smem[];
     constexpr int HS_LD = TILE_W + 1;                                   // row stride of the horizontal sums (bank spread)
-    double* hs = reinterpret_cast<double*>(tile_smem);                  // [5][PATCH_H][HS_LD]
+    A* hs = reinterpret_cast<A*>(tile_smem);                            // [5][PATCH_H][HS_LD]
     T* pa = reinterpret_cast<T*>(hs + 5 * PATCH_H * HS_LD);             // [PATCH_H][PATCH_W + 1]
     T* pb = pa + PATCH_H * (PATCH_W + 1);
     __shared__ double scratch[32];
@@ -95,6 +108,14 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
     const int64_t base = slice_base(f, s);
     const int64_t oy = (int64_t)ty * TILE_H, ox = (int64_t)tx * TILE_W;   // interior coordinates
     const int ph = TILE_H + win - 1, pw = TILE_W + win - 1;
+    const double R = range[s];
+    T mu_a = (T)0, mu_b = (T)0, inv_r = (T)1;
+    if (FAST) {
+        const int64_t off0 = base + oy * f.sh + ox * f.sw;                // the tile's first pixel: always inside the slice
+        mu_a = a[off0];
+        mu_b = b[off0] > (T)0 ? b[off0] : (T)0;
+        inv_r = (T)(1.0 / R);                                            // R == 0: inf -> NaN scores, as the reference's 0 / 0
+    }
     for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
         const int r = e / pw, c = e - r * pw;
         const int64_t h = oy + r, w = ox + c;
@@ -104,6 +125,7 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
             va = a[off];
             vb = b[off];
             vb = vb > (T)0 ? vb : (T)0;
+            if (FAST) { va = (va - mu_a) * inv_r; vb = (vb - mu_b) * inv_r; }
         }
         pa[r * (PATCH_W + 1) + c] = va;
         pb[r * (PATCH_W + 1) + c] = vb;
@@ -115,9 +137,9 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
         const int r = e / TILE_W, c = e - r * TILE_W;
         const T* xa = pa + r * (PATCH_W + 1) + c;
         const T* xb = pb + r * (PATCH_W + 1) + c;
-        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        A sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
         for (int j = 0; j < win; j++) {
-            const double x = (double)xa[j], y = (double)xb[j];
+            const A x = (A)xa[j], y = (A)xb[j];
             sx += x; sy += y;
             sxx = fma(x, x, sxx); syy = fma(y, y, syy); sxy = fma(x, y, sxy);
         }
@@ -125,19 +147,20 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
         hs[(3 * PATCH_H + r) * HS_LD + c] = syy; hs[(4 * PATCH_H + r) * HS_LD + c] = sxy;
     }
     __syncthreads();
-    const double R = range[s];
-    const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
-    const double np = (double)(win * win);
-    const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+    // normalised data (FAST): the data range is 1, the means carry the tile's shift back
+    const A c1 = FAST ? (A)1e-4 : (A)((0.01 * R) * (0.01 * R)), c2 = FAST ? (A)9e-4 : (A)((0.03 * R) * (0.03 * R));
+    const A off_x = FAST ? (A)mu_a * (A)inv_r : (A)0, off_y = FAST ? (A)mu_b * (A)inv_r : (A)0;
+    const A np = (A)(win * win);
+    const A inv_np = (A)1 / np, cov_norm = np / (np - (A)1);
     const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;   // interior extent
     double acc = 0.0;
     {
         constexpr int STRIP = TILE_H / 8;
         const int x = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * STRIP;
-        double v[5];
+        A v[5];
 #pragma unroll
         for (int q = 0; q < 5; q++) {
-            double t = 0.0;
+            A t = 0;
             for (int i = 0; i < win; i++) t += hs[(q * PATCH_H + y0 + i) * HS_LD + x];
             v[q] = t;
         }
@@ -150,12 +173,13 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
                     v[q] += hs[(q * PATCH_H + y + win - 1) * HS_LD + x] - hs[(q * PATCH_H + y - 1) * HS_LD + x];
             }
             if (oy + y < ih && ox + x < iw) {
-                const double ux = v[0] * inv_np, uy = v[1] * inv_np;
-                const double vx = cov_norm * (v[2] * inv_np - ux * ux), vy = cov_norm * (v[3] * inv_np - uy * uy);
-                const double vxy = cov_norm * (v[4] * inv_np - ux * uy);
-                const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
-                const double den = (ux * ux + uy * uy + c1) * (vx + vy + c2);
-                acc += num / den;
+                const A ux = v[0] * inv_np, uy = v[1] * inv_np;
+                const A vx = cov_norm * (v[2] * inv_np - ux * ux), vy = cov_norm * (v[3] * inv_np - uy * uy);
+                const A vxy = cov_norm * (v[4] * inv_np - ux * uy);
+                const A mx = ux + off_x, my = uy + off_y;               // true means (in units of R when FAST)
+                const A num = ((A)2 * mx * my + c1) * ((A)2 * vxy + c2);
+                const A den = (mx * mx + my * my + c1) * (vx + vy + c2);
+                acc += (double)(num / den);
             }
         }
     }
@@ -163,14 +187,24 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+static inline bool ssim_fast(const ndmps_ctx* ctx, const float*) { return ctx->opt_ssim_exact == 0; }
+static inline bool ssim_fast(const ndmps_ctx*, const double*) { return false; }
+
+template <class T, class A>
+static int launch_ssim_tile_as(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
+                               int64_t nt, double* partial) {
+    const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(A) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
+    NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_kernel<T, A>, ctx->device, 96 * 1024));
+    ssim_tile_kernel<T, A><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+
 template <class T>
 static int launch_ssim_tile(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
                             int64_t nt, double* partial) {
-    const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(double) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
-    NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_kernel<T>, ctx->device, 96 * 1024));
-    ssim_tile_kernel<T><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
-    NDMPS_LAUNCH_CHECK(ctx);
-    return NDMPS_OK;
+    if (ssim_fast(ctx, a)) return launch_ssim_tile_as<T, float>(ctx, a, b, f, range, ty, tx, nt, partial);
+    return launch_ssim_tile_as<T, double>(ctx, a, b, f, range, ty, tx, nt, partial);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -225,10 +259,11 @@ __global__ void __launch_bounds__(256) ssim_range_finalize_kernel(const unsigned
     if (s < S) range[s] = dkey_inv(keys[2 * s + 1]) - dkey_inv(keys[2 * s]);
 }
 
-template <class T, int WIN>
+template <class T, int WIN, class A>
 __global__ void __launch_bounds__(256)
 ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                          int tiles_y, int tiles_x, double* __restrict__ partial) {
+    constexpr bool FAST = std::is_same<A, float>::value;
     extern __shared__ unsigned char bt_smem[];
     constexpr int win = WIN, pad = (WIN - 1) / 2;
     const int ph = BT_H + win - 1, pw = BT_W + win - 1;
@@ -243,6 +278,14 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     const bool live = s < f.S;
     const int64_t base = live ? slice_base(f, s) : 0;
     const int64_t oy = (int64_t)ty * BT_H, ox = (int64_t)tx * BT_W;
+    const double R = live ? range[s] : 1.0;
+    T mu_a = (T)0, mu_b = (T)0, inv_r = (T)1;
+    if (FAST && live) {
+        const int64_t off0 = base + oy * f.sh + ox * f.sw;                // this slice's first pixel of the tile
+        mu_a = a[off0];
+        mu_b = b[off0] > (T)0 ? b[off0] : (T)0;
+        inv_r = (T)(1.0 / R);
+    }
     for (int e = warp; e < ph * pw; e += 8) {
         const int r = e / pw, c = e - r * pw;
         const int64_t h = oy + r, w = ox + c;
@@ -252,6 +295,7 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
             va = a[off];
             vb = b[off];
             vb = vb > (T)0 ? vb : (T)0;
+            if (FAST) { va = (va - mu_a) * inv_r; vb = (vb - mu_b) * inv_r; }
         }
         pa[(size_t)e * BT_SLICES + lane] = va;
         pb[(size_t)e * BT_SLICES + lane] = vb;
@@ -259,25 +303,25 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     __syncthreads();
     double acc = 0.0;
     if (live) {
-        const double R = range[s];
-        const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
-        constexpr double np = (double)(WIN * WIN);
-        constexpr double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
+        const A c1 = FAST ? (A)1e-4 : (A)((0.01 * R) * (0.01 * R)), c2 = FAST ? (A)9e-4 : (A)((0.03 * R) * (0.03 * R));
+        const A off_x = FAST ? (A)mu_a * (A)inv_r : (A)0, off_y = FAST ? (A)mu_b * (A)inv_r : (A)0;
+        constexpr A np = (A)(WIN * WIN);
+        constexpr A inv_np = (A)1 / np, cov_norm = np / (np - (A)1);
         const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
         // one output column per warp: horizontal WIN-tap sums per patch row, vertical running sum over
         // a register ring of the last WIN rows (everything unrolled, the ring is static registers)
         const int x = warp;
         if (ox + x < iw) {
-            double ring[WIN][5];
-            double vs[5] = {0, 0, 0, 0, 0};
+            A ring[WIN][5];
+            A vs[5] = {0, 0, 0, 0, 0};
 #pragma unroll
             for (int r = 0; r < BT_H + WIN - 1; r++) {
-                double hsum[5] = {0, 0, 0, 0, 0};
+                A hsum[5] = {0, 0, 0, 0, 0};
                 const size_t rowbase = ((size_t)r * pw + x) * BT_SLICES + lane;
 #pragma unroll
                 for (int j = 0; j < WIN; j++) {
-                    const double xv = (double)pa[rowbase + (size_t)j * BT_SLICES];
-                    const double yv = (double)pb[rowbase + (size_t)j * BT_SLICES];
+                    const A xv = (A)pa[rowbase + (size_t)j * BT_SLICES];
+                    const A yv = (A)pb[rowbase + (size_t)j * BT_SLICES];
                     hsum[0] += xv; hsum[1] += yv;
                     hsum[2] = fma(xv, xv, hsum[2]); hsum[3] = fma(yv, yv, hsum[3]); hsum[4] = fma(xv, yv, hsum[4]);
                 }
@@ -290,10 +334,11 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
                 if (r >= WIN - 1) {
                     const int y = r - (WIN - 1);
                     if (oy + y < ih) {
-                        const double ux = vs[0] * inv_np, uy = vs[1] * inv_np;
-                        const double vx = cov_norm * (vs[2] * inv_np - ux * ux), vy = cov_norm * (vs[3] * inv_np - uy * uy);
-                        const double vxy = cov_norm * (vs[4] * inv_np - ux * uy);
-                        acc += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+                        const A ux = vs[0] * inv_np, uy = vs[1] * inv_np;
+                        const A vx = cov_norm * (vs[2] * inv_np - ux * ux), vy = cov_norm * (vs[3] * inv_np - uy * uy);
+                        const A vxy = cov_norm * (vs[4] * inv_np - ux * uy);
+                        const A mx = ux + off_x, my = uy + off_y;
+                        acc += (double)((((A)2 * mx * my + c1) * ((A)2 * vxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2)));
                     }
                 }
             }
@@ -409,10 +454,16 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         int64_t nt = bounds_h[k + 1] - bounds_h[k];
         if (batched[k]) {
             const size_t bsm = (size_t)2 * (BT_H + f.win - 1) * (BT_W + f.win - 1) * BT_SLICES * sizeof(T);
-            NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7>, ctx->device, 112 * 1024));
             NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, true, range + slice_off));
-            ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
-                                                                                 partial + bounds_h[k]);
+            if (ssim_fast(ctx, a)) {
+                NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7, float>, ctx->device, 112 * 1024));
+                ssim_tile_batched_kernel<T, 7, float><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k],
+                                                                                            tiles_x[k], partial + bounds_h[k]);
+            } else {
+                NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7, double>, ctx->device, 112 * 1024));
+                ssim_tile_batched_kernel<T, 7, double><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k],
+                                                                                             tiles_x[k], partial + bounds_h[k]);
+            }
             NDMPS_LAUNCH_CHECK(ctx);
         } else {
             NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, false, range + slice_off));

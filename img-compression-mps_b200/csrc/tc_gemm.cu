@@ -206,43 +206,138 @@ __device__ __constant__ int8_t REST_A[5] = {1, 2, 0, 1, 0};
 __device__ __constant__ int8_t REST_B[5] = {1, 0, 2, 0, 1};
 
 // ---------------------------------------------------------------------------------------------
-// Gram: partial[split][tile] (float64 128 x 128) = sum over this CTA's K range of A_ti . A_tj^T
+// Gram on the INTEGER tensor cores (kind::i8, int32 accumulators): error-free accumulation.
+//
+// The left factor of a sweep step is decided by the trailing kept eigenvalues of G = M M^T, which sit at
+// lambda_chi / lambda_1 ~ 1e-6 with gaps of a few percent of that: a Gram matrix accumulated in float32 (the
+// bf16x3 route above is 1e-7 .. 3e-7 normwise on data with a wide dynamic range, e.g. DCT coefficients)
+// rotates those eigenvectors visibly (measured: reconstructions 2e-4 off on the video chunk).  So the Gram
+// uses sliced integers (Ozaki scheme): every row i is scaled by a power of two, y = x 2^-sc_i in (-1/2, 1/2),
+// and written as four signed 7-bit digits, y = sum_p a_p 2^(-7 (p + 1)) + O(2^-29), |a_p| <= 64 (round to
+// nearest at every digit, exact float32 arithmetic).  Digit products are exact in the int32 accumulator:
+//     y_i . y_j = sum_s 2^(-7 (s + 2)) ACC_s,    ACC_s = sum_k sum_{p + q = s} a_p b_q,   s = 0 .. 3
+// ten MMAs per k-step of 32 at the int8 rate (= five bf16 MMAs), four accumulators of 128 columns = all of
+// tensor memory, NO drains inside a chain (|ACC_s| <= 4096 (s + 1) K: K up to 2^15 per chain), one exact
+// int32 -> float64 combination at the end of a CTA's K range.  What is lost is the digits beyond 2^-28 of
+// each row's largest element and the products with p + q >= 4: ~1e-9 normwise, a hundred times below the
+// float32-accumulated route, at a lower tensor-core and HBM cost (4 bytes of digits per element).
 // ---------------------------------------------------------------------------------------------
-struct GramSmem {
-    static constexpr int STAGES = 2;
-    static constexpr int STAGE_BYTES = 6 * PLANE_TILE;          // A planes h, m, l + B planes h, m, l
+constexpr int I8_PLANES = 4;
+constexpr int I8_BK = 64;                        // int8 elements per k-tile: 64-byte rows (SWIZZLE_64B)
+constexpr int I8_UK = 32;                        // K of one tcgen05.mma.kind::i8
+constexpr int I8_TILE_BYTES = TILE * I8_BK;      // 8 KB: one 128 x 64 digit tile
+constexpr int I8_MAX_CHAIN_TILES = 512;          // 2^15 columns per accumulator chain: |ACC_3| <= 4 * 4096 * 2^15 = 2^29
+
+struct GramI8Smem {
+    static constexpr int STAGES = 3;
+    static constexpr int STAGE_BYTES = 2 * I8_PLANES * I8_TILE_BYTES;      // A digits 0..3 + B digits 0..3 = 64 KB
     static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;      // + alignment slack
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;
 };
 
-// TMEM columns: [0, 128) h.h buffer 0, [128, 256) h.h buffer 1, [256, 384) corrections buffer 0, [384, 512) buffer 1.
-// `rest_every`: k-tiles per chain of the correction accumulator.
+// 64-byte swizzle, K-major: 8-row groups are 512 B apart, a k-step of 32 int8 advances the start address by 32 B
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+    const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::i8 instruction descriptor: D int32, A and B signed int8, K-major both
+__host__ __device__ constexpr uint32_t instr_desc_i8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// rowmax[r] = max |x[r, :]| as float bits (non-negative floats order like unsigned integers); rowmax zeroed by the caller
+__global__ void __launch_bounds__(256)
+row_absmax_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, int64_t cols_per_cta, unsigned* __restrict__ rowmax) {
+    __shared__ float red[8];
+    const int64_t r = blockIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.y * cols_per_cta, c1 = c0 + cols_per_cta < cols ? c0 + cols_per_cta : cols;
+    const float* p = x + r * ld;
+    float m = 0.f;
+    if ((ld & 3) == 0 && (c0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+        const int64_t v1 = c0 + ((c1 - c0) & ~int64_t(3));
+        for (int64_t c = c0 + 4 * threadIdx.x; c < v1; c += 1024) {
+            const float4 v = *reinterpret_cast<const float4*>(p + c);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        for (int64_t c = v1 + threadIdx.x; c < c1; c += 256) m = fmaxf(m, fabsf(p[c]));
+    } else {
+        for (int64_t c = c0 + threadIdx.x; c < c1; c += 256) m = fmaxf(m, fabsf(p[c]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]);
+        if (m > 0.f && m < INFINITY) atomicMax(rowmax + r, __float_as_uint(m));
+    }
+}
+
+// sc[r]: y = x 2^-sc[r] lies in (-1/2, 1/2); digits[p][r][c] = digit p of y.  16 elements per thread (16-byte stores).
+__global__ void __launch_bounds__(256)
+split_i8_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, const unsigned* __restrict__ rowmax,
+                int8_t* __restrict__ digits, int64_t ldp, int64_t plane_stride, int* __restrict__ sc_out) {
+    const int64_t groups = ldp >> 4, total = rows * groups, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / groups, c0 = (i - r * groups) << 4;
+        const float mx = __uint_as_float(rowmax[r]);
+        int e = 0;
+        if (mx > 0.f) frexpf(mx, &e);                 // mx = f 2^e, f in [1/2, 1)
+        const int sc = e + 1;
+        if (c0 == 0) sc_out[r] = sc;
+        const float down = ldexpf(1.f, -sc);
+        __align__(16) int8_t d[I8_PLANES][16];
+        const float* p = x + r * ld + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            float t = (c0 + j < cols ? p[j] : 0.f) * down * 128.f;
+#pragma unroll
+            for (int q = 0; q < I8_PLANES; q++) {
+                const float a = rintf(t);
+                d[q][j] = (int8_t)(int)a;
+                t = (t - a) * 128.f;                  // exact: |t - a| <= 1/2 has fewer significant bits than t
+            }
+        }
+        int8_t* o = digits + r * ldp + c0;
+#pragma unroll
+        for (int q = 0; q < I8_PLANES; q++) *reinterpret_cast<uint4*>(o + q * plane_stride) = *reinterpret_cast<const uint4*>(d[q]);
+    }
+}
+
+// TMEM columns: accumulator s at [128 s, 128 s + 128), s = p + q = 0 .. 3.
 __global__ void __launch_bounds__(THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64_t k_per, int rest_every, double* __restrict__ partial) {
+gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K, int64_t k_per, const int* __restrict__ sc,
+               double* __restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GramSmem::BARRIER_OFF);
-    uint64_t* empty = full + GramSmem::STAGES;
-    uint64_t* hh_full = empty + GramSmem::STAGES;      // [2]
-    uint64_t* hh_empty = hh_full + 2;                  // [2]
-    uint64_t* rest_full = hh_empty + 2;                // [2]
-    uint64_t* rest_empty = rest_full + 2;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rest_empty + 2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GramI8Smem::BARRIER_OFF);
+    uint64_t* empty = full + GramI8Smem::STAGES;
+    uint64_t* acc_full = empty + GramI8Smem::STAGES;     // [1]
+    uint64_t* acc_empty = acc_full + 1;                  // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ti, tj;
     upper_tile(blockIdx.x, nt, ti, tj);
     const int64_t kbeg = (int64_t)blockIdx.y * k_per;
     const int64_t kend = kbeg + k_per < K ? kbeg + k_per : K;
-    const int nk = (int)((kend - kbeg + BK - 1) / BK);
+    const int nk = (int)((kend - kbeg + I8_BK - 1) / I8_BK);
+    const int n_chains = (nk + I8_MAX_CHAIN_TILES - 1) / I8_MAX_CHAIN_TILES;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map);
-        for (int s = 0; s < GramSmem::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&hh_full[b], 1); mbar_init(&hh_empty[b], EPI_THREADS / 32);
-            mbar_init(&rest_full[b], 1); mbar_init(&rest_empty[b], EPI_THREADS / 32);
-        }
+        for (int s = 0; s < GramI8Smem::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, EPI_THREADS / 32);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -256,89 +351,85 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map, int nt, int64_t K, int64
         if (warp == 0 && lane == 0) {
             // ---- TMA producer ----
             for (int kt = 0; kt < nk; kt++) {
-                const int s = kt % GramSmem::STAGES;
-                mbar_wait(&empty[s], ((kt / GramSmem::STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], GramSmem::STAGE_BYTES);
-                uint8_t* st = smem + s * GramSmem::STAGE_BYTES;
-                const int kc = (int)(kbeg + (int64_t)kt * BK);
+                const int s = kt % GramI8Smem::STAGES;
+                mbar_wait(&empty[s], ((kt / GramI8Smem::STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], GramI8Smem::STAGE_BYTES);
+                uint8_t* st = smem + s * GramI8Smem::STAGE_BYTES;
+                const int kc = (int)(kbeg + (int64_t)kt * I8_BK);
 #pragma unroll
-                for (int p = 0; p < 3; p++) {
-                    tma_load_3d(st + p * PLANE_TILE, &map, &full[s], kc, ti * TILE, p);
-                    tma_load_3d(st + (3 + p) * PLANE_TILE, &map, &full[s], kc, tj * TILE, p);
+                for (int p = 0; p < I8_PLANES; p++) {
+                    tma_load_3d(st + p * I8_TILE_BYTES, &map, &full[s], kc, ti * TILE, p);
+                    tma_load_3d(st + (I8_PLANES + p) * I8_TILE_BYTES, &map, &full[s], kc, tj * TILE, p);
                 }
             }
         } else if (warp == 1 && lane == 0) {
             // ---- MMA issuer ----
-            constexpr uint32_t idesc = instr_desc(TILE, TILE, 0, 0);
+            constexpr uint32_t idesc = instr_desc_i8(TILE, TILE);
             for (int kt = 0; kt < nk; kt++) {
-                const int s = kt % GramSmem::STAGES;
-                const int hb = kt & 1;
-                const int rc = kt / rest_every, rwithin = kt - rc * rest_every, rb = rc & 1;
-                mbar_wait(&hh_empty[hb], ((kt >> 1) & 1) ^ 1);
-                if (rwithin == 0) mbar_wait(&rest_empty[rb], ((rc >> 1) & 1) ^ 1);
-                mbar_wait(&full[s], (kt / GramSmem::STAGES) & 1);
+                const int s = kt % GramI8Smem::STAGES;
+                const int chain = kt / I8_MAX_CHAIN_TILES, within = kt - chain * I8_MAX_CHAIN_TILES;
+                if (within == 0 && chain > 0) {           // the epilogue has read the previous chain out of tensor memory
+                    mbar_wait(acc_empty, (chain - 1) & 1);
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], (kt / GramI8Smem::STAGES) & 1);
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * GramSmem::STAGE_BYTES);
-                const uint32_t d_hh = tmem_base + (uint32_t)hb * TILE;
-                const uint32_t d_rest = tmem_base + 2 * TILE + (uint32_t)rb * TILE;
+                const uint32_t st = smem_u32(smem + s * GramI8Smem::STAGE_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < BK / UK; ks++)
-                    umma_bf16(d_hh, smem_desc(st + ks * 32, 16, 1024), smem_desc(st + 3 * PLANE_TILE + ks * 32, 16, 1024), idesc, ks != 0);
-                umma_commit(&hh_full[hb]);                                // the epilogue drains this chain while the corrections run
+                for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
 #pragma unroll
-                for (int t = 0; t < 5; t++) {
+                    for (int p = 0; p < I8_PLANES; p++) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / UK; ks++) {
-                        const uint64_t da = smem_desc(st + REST_A[t] * PLANE_TILE + ks * 32, 16, 1024);
-                        const uint64_t db = smem_desc(st + (3 + REST_B[t]) * PLANE_TILE + ks * 32, 16, 1024);
-                        umma_bf16(d_rest, da, db, idesc, (rwithin | t | ks) != 0);
+                        for (int q = 0; q < I8_PLANES; q++) {
+                            if (p + q >= I8_PLANES) continue;
+                            const uint64_t da = smem_desc_sw64(st + p * I8_TILE_BYTES + ks * 32);
+                            const uint64_t db = smem_desc_sw64(st + (I8_PLANES + q) * I8_TILE_BYTES + ks * 32);
+                            // the first product of each accumulator in a chain overwrites: (p, q) = (0, s) comes first for every s
+                            umma_i8(tmem_base + (uint32_t)((p + q) * TILE), da, db, idesc, !(within == 0 && ks == 0 && p == 0));
+                        }
                     }
                 }
-                umma_commit(&empty[s]);                                   // the stage is free once these MMAs have read it
-                if (rwithin == rest_every - 1 || kt == nk - 1) umma_commit(&rest_full[rb]);
+                umma_commit(&empty[s]);
+                if (within == I8_MAX_CHAIN_TILES - 1 || kt == nk - 1) umma_commit(acc_full);
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ---- epilogue: every chain into float64 registers ----
-        const int q = warp & 3, half = (warp - 4) >> 2;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+        // ---- epilogue: exact int32 -> float64 combination of the four digit-sum accumulators ----
+        const int q4 = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
         double acc[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) acc[i] = 0.0;
-        for (int kt = 0; kt < nk; kt++) {
-            const int hb = kt & 1;
-            mbar_wait(&hh_full[hb], (kt >> 1) & 1);
+        for (int chain = 0; chain < n_chains; chain++) {
+            mbar_wait(acc_full, chain & 1);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < 2; g++) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(hb * TILE + g * 32), v);
-#pragma unroll
-                for (int i = 0; i < 32; i++) acc[g * 32 + i] += (double)__uint_as_float(v[i]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hh_empty[hb]);
-            const int rc = kt / rest_every, rwithin = kt - rc * rest_every, rb = rc & 1;
-            if (rwithin == rest_every - 1 || kt == nk - 1) {
-                mbar_wait(&rest_full[rb], (rc >> 1) & 1);
-                tc_fence_after();
+            for (int s = 0; s < I8_PLANES; s++) {
+                const double w = s == 0 ? 0x1p-14 : (s == 1 ? 0x1p-21 : (s == 2 ? 0x1p-28 : 0x1p-35));
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     uint32_t v[32];
-                    tmem_ld32(lane_base + (uint32_t)(2 * TILE + rb * TILE + g * 32), v);
+                    tmem_ld32(lane_base + (uint32_t)(s * TILE + g * 32), v);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) acc[g * 32 + i] += (double)__uint_as_float(v[i]);
+                    for (int i = 0; i < 32; i++) acc[g * 32 + i] = fma((double)(int)v[i], w, acc[g * 32 + i]);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&rest_empty[rb]);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
         }
-        double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * TILE + (size_t)(q * 32 + lane) * TILE + half * 64;
+        // undo the row scalings: G_ij = 2^(sc_i + sc_j) y_i . y_j
+        const int gi = ti * TILE + q4 * 32 + lane;
+        const int sci = gi < m ? sc[gi] : 0;
+        double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * TILE + (size_t)(q4 * 32 + lane) * TILE + half * 64;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) *reinterpret_cast<double2*>(out + i) = make_double2(acc[i], acc[i + 1]);
+        for (int i = 0; i < 64; i += 2) {
+            const int gj = tj * TILE + half * 64 + i;
+            const double s0 = ldexp(acc[i], sci + (gj < m ? sc[gj] : 0));
+            const double s1 = ldexp(acc[i + 1], sci + (gj + 1 < m ? sc[gj + 1] : 0));
+            *reinterpret_cast<double2*>(out + i) = make_double2(s0, s1);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -595,27 +686,57 @@ int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t
     using namespace tc;
     *done = false;
     if (dtype != NDMPS_F32 || rows < 64 || rows > 4096 || cols < 2048) return NDMPS_OK;
-    __nv_bfloat16* planes = nullptr;
-    int64_t ldp = 0, pstride = 0;
-    NDMPS_TRY(tc_split(ctx, mat, dtype, rows, cols, ld, false, 1.0, &planes, &ldp, &pstride));
-    ctx->tc_planes.src = mat; ctx->tc_planes.rows = rows; ctx->tc_planes.cols = cols; ctx->tc_planes.ld = ld;
-    ctx->tc_planes.planes = planes; ctx->tc_planes.ldp = ldp; ctx->tc_planes.pstride = pstride; ctx->tc_planes.gen = ctx->ws.generation;
+    // 1. row scales, 2. four int8 digit planes
+    unsigned* rowmax = nullptr;
+    int* sc = nullptr;
+    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)rows, &rowmax));
+    NDMPS_TRY(ctx->ws.get<int>((size_t)rows, &sc));
+    NDMPS_CUDA_TRY(cudaMemsetAsync(rowmax, 0, (size_t)rows * sizeof(unsigned), ctx->stream));
+    {
+        int64_t chunks = ((int64_t)ctx->sm_count * 8 + rows - 1) / rows;
+        const int64_t max_chunks = (cols + 4095) / 4096;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        int64_t per = (cols + chunks - 1) / chunks;
+        per = (per + 3) & ~int64_t(3);
+        chunks = (cols + per - 1) / per;
+        row_absmax_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, ctx->stream>>>((const float*)mat, cols, ld, per, rowmax);
+        NDMPS_LAUNCH_CHECK(ctx);
+    }
+    const int64_t ldp = (cols + 15) & ~int64_t(15), pstride = rows * ldp;
+    int8_t* digits = nullptr;
+    NDMPS_TRY(ctx->ws.get<int8_t>((size_t)(I8_PLANES * pstride), &digits));
+    {
+        const int64_t total = rows * (ldp >> 4);
+        int64_t want = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+        split_i8_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, ctx->stream>>>((const float*)mat, rows, cols, ld, rowmax, digits, ldp,
+                                                                                                pstride, sc);
+        NDMPS_LAUNCH_CHECK(ctx);
+    }
+    // 3. digit products on the integer tensor cores
     CUtensorMap map;
-    NDMPS_TRY(make_plane_map(&map, planes, rows, cols, ldp, pstride, TILE));
+    {
+        EncodeTiledFn fn = encode_fn();
+        if (!fn) { set_error("tc: cuTensorMapEncodeTiled is not available from the driver"); return NDMPS_ERR_CUDA; }
+        const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)I8_PLANES};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldp, (cuuint64_t)pstride};
+        const cuuint32_t box[3] = {(cuuint32_t)I8_BK, (cuuint32_t)TILE, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, digits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled (int8 digits) failed (%d)", (int)r); return NDMPS_ERR_CUDA; }
+    }
     const int m = (int)rows, nt = (m + TILE - 1) / TILE, ntiles = nt * (nt + 1) / 2;
-    const int chunk = ctx->opt_tc_chunk > 0 ? (int)ctx->opt_tc_chunk : 8;          // k-tiles of 64 per chain of the correction accumulator
-    // whole waves of one CTA per SM
-    int64_t splits = (int64_t)ctx->sm_count / ntiles;
+    int64_t splits = (int64_t)ctx->sm_count / ntiles;          // whole waves of one CTA per SM
     if (splits < 1) splits = 1;
-    const int64_t unit = (int64_t)BK;
     int64_t k_per = (cols + splits - 1) / splits;
-    k_per = ((k_per + unit - 1) / unit) * unit;
+    k_per = ((k_per + I8_BK - 1) / I8_BK) * I8_BK;
     splits = (cols + k_per - 1) / k_per;
     double* partial = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)splits * ntiles * TILE * TILE, &partial));
-    NDMPS_TRY(raise_dynamic_smem((const void*)gram_tc_kernel, ctx->device, GramSmem::TOTAL));
+    NDMPS_TRY(raise_dynamic_smem((const void*)gram_i8_kernel, ctx->device, GramI8Smem::TOTAL));
     dim3 grid((unsigned)ntiles, (unsigned)splits);
-    gram_tc_kernel<<<grid, THREADS, GramSmem::TOTAL, ctx->stream>>>(map, nt, cols, k_per, chunk, partial);
+    gram_i8_kernel<<<grid, THREADS, GramI8Smem::TOTAL, ctx->stream>>>(map, nt, m, cols, k_per, sc, partial);
     NDMPS_LAUNCH_CHECK(ctx);
     ctx->tc_launches++;
     dim3 rgrid(16, (unsigned)ntiles);

@@ -236,30 +236,69 @@ def _pair(shape, seed, dtype):
     return a.astype(dtype), b.astype(dtype)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def ssim_arithmetic(exact):
+    """float32 inputs: float64 arithmetic (the reference's) when `exact`, else the default shifted / normalised float32."""
+    from imgcompressionmps import _native
+    ctx = _native.context()
+    ctx.set_option("ssim_exact", 1 if exact else 0)
+    try:
+        yield
+    finally:
+        ctx.set_option("ssim_exact", 0)
+
+
+# float64 arithmetic agrees with the oracle to rounding; the float32 fast path to ~1e-6 per slice (north-star bar: 1e-4)
+SSIM_TOL = {True: 1e-10, False: 5e-6}
+
+
 @pytest.mark.parametrize("shape", [(16, 16), (40, 70), (7, 9), (5, 30), (6, 31), (256, 256), (33, 65), (70, 100), (39, 38)])
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_ssim_2d(ops, shape, dtype):
+@pytest.mark.parametrize("dtype,exact", [(np.float64, True), (np.float32, True), (np.float32, False)], ids=["f64", "f32-exact", "f32-fast"])
+def test_ssim_2d(ops, shape, dtype, exact):
     a, b = _pair(shape, 1, dtype)
     want = OM.compute_ssim_2d(a.astype(np.float64), b.astype(np.float64))
-    got = ops.ssim(dev(a), dev(b))
-    assert got == pytest.approx(want, abs=1e-10)            # north-star tolerance is 1e-4
+    with ssim_arithmetic(exact):
+        got = ops.ssim(dev(a), dev(b))
+    assert got == pytest.approx(want, abs=SSIM_TOL[exact])
 
 
 @pytest.mark.parametrize("shape", [(9, 10, 11), (32, 48, 40), (64, 64, 64), (37, 45, 50), (40, 71, 33)])
-def test_ssim_3d(ops, shape):
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_ssim_3d(ops, shape, exact):
     a, b = _pair(shape, 2, np.float32)
     a64, b64 = a.astype(np.float64), b.astype(np.float64)
-    assert ops.ssim(dev(a), dev(b)) == pytest.approx(OM.avg_ssim_3d(a64, b64), abs=1e-10)
-    for ax in range(3):
-        got = ops.ssim_slices(dev(a), dev(b), ax)
-        assert np.allclose(got, OM.ssim_3d_axis(a64, b64, ax), atol=1e-10)
+    with ssim_arithmetic(exact):
+        assert ops.ssim(dev(a), dev(b)) == pytest.approx(OM.avg_ssim_3d(a64, b64), abs=SSIM_TOL[exact])
+        for ax in range(3):
+            got = ops.ssim_slices(dev(a), dev(b), ax)
+            assert np.allclose(got, OM.ssim_3d_axis(a64, b64, ax), atol=SSIM_TOL[exact])
 
 
 @pytest.mark.parametrize("shape", [(16, 12, 10, 5), (12, 10, 9, 40), (40, 39, 8, 33)])
-def test_ssim_4d(ops, shape):
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_ssim_4d(ops, shape, exact):
     a, b = _pair(shape, 3, np.float32)
     want = OM.avg_ssim_4d(a.astype(np.float64), b.astype(np.float64))
-    assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=1e-10)
+    with ssim_arithmetic(exact):
+        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=SSIM_TOL[exact])
+
+
+def test_ssim_fast_path_offsets_and_scales(ops):
+    """The float32 arithmetic works on (x - first pixel) / range per tile: large offsets, tiny and huge scales and a
+    steep edge inside a flat tile must not cost more than the documented 5e-6."""
+    rng = np.random.default_rng(11)
+    base = rng.random((96, 80))
+    noisy = base + 0.03 * rng.standard_normal(base.shape)
+    edge = base.copy()
+    edge[:, 40:] += 5.0                                              # a step 5x the texture amplitude through every tile row
+    for a64, b64 in ((base + 1000.0, noisy + 1000.0), (base * 1e-6, noisy * 1e-6), (base * 1e6, noisy * 1e6),
+                     (edge, edge + 0.02 * rng.standard_normal(edge.shape))):
+        a, b = a64.astype(np.float32), b64.astype(np.float32)
+        want = OM.compute_ssim_2d(a.astype(np.float64), b.astype(np.float64))
+        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=5e-6)
 
 
 # ---- contractions ------------------------------------------------------------------------------------------
