@@ -201,13 +201,13 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
     return NDMPS_OK;
 }
 
-int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
+int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done,
+              const int* run_flag = nullptr);
 
 int gram(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev) {
-    if (side == 0 && ctx->opt_gram_path == 3) {
-        // sliced-integer Gram on tcgen05 kind::i8 (tc_gemm.cu).  NOT the default: with four digits its error on rows with a
-        // heavy-tailed distribution (DCT coefficients, fMRI) moves the trailing kept eigenvectors visibly - measured numbers
-        // in profiles/r02_summary.md - so the sweep keeps the exact FP64-pipe Gram below
+    if (side == 0 && (ctx->opt_gram_path == 3 || (ctx->opt_gram_path == 0 && ctx->opt_tc && ctx->tc_sweep))) {
+        // sliced-integer Gram on tcgen05 kind::i8 (tc_gemm.cu): float32 unfoldings of a capped sweep.  Exact accumulation,
+        // five 7-bit digits; rows too heavy-tailed for five digits go to the FP64-pipe kernel through a device-side flag
         bool done = false;
         NDMPS_TRY(gram_tc(ctx, mat, rows, cols, ld, dtype, g_dev, &done));
         if (done) return NDMPS_OK;

@@ -41,7 +41,9 @@ __device__ __forceinline__ void upper_tile(int t, int nt, int& ti, int& tj) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gram_dmma_kernel(const float* __restrict__ M, int m, int64_t K, int64_t ld, int nt, int64_t k_per, double* __restrict__ partial) {
+gram_dmma_kernel(const float* __restrict__ M, int m, int64_t K, int64_t ld, int nt, int64_t k_per, double* __restrict__ partial,
+                 const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && run_flag[0] == 0) return;     // the tensor-core Gram took this matrix (tc_gemm.cu)
     extern __shared__ float smem[];
     float* As = smem;                                   // STAGES x TM x LDS
     float* Bs = smem + (size_t)STAGES * TM * LDS;       // STAGES x TM x LDS
@@ -126,7 +128,9 @@ gram_dmma_kernel(const float* __restrict__ M, int m, int64_t K, int64_t ld, int 
 
 // G[i][j] = G[j][i] = sum over splits, in split order
 __global__ void __launch_bounds__(256)
-gram_dmma_reduce_kernel(const double* __restrict__ partial, int m, int nt, int ntiles, int splits, double* __restrict__ G) {
+gram_dmma_reduce_kernel(const double* __restrict__ partial, int m, int nt, int ntiles, int splits, double* __restrict__ G,
+                        const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && run_flag[0] == 0) return;
     const int tile = blockIdx.y;
     int ti, tj;
     upper_tile(tile, nt, ti, tj);
@@ -145,7 +149,9 @@ gram_dmma_reduce_kernel(const double* __restrict__ partial, int m, int nt, int n
 }  // namespace dmma
 
 // returns NDMPS_OK and sets *done = true when the fast path ran
-int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done) {
+// run_flag (device, optional): the kernels return at once unless run_flag[0] != 0
+int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done,
+              const int* run_flag) {
     using namespace dmma;
     *done = false;
     if (dtype != NDMPS_F32 || rows < 48 || rows > 4096 || cols < 4 * BK) return NDMPS_OK;
@@ -166,10 +172,10 @@ int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64
     const size_t smem = (size_t)2 * STAGES * TM * LDS * sizeof(float);
     NDMPS_TRY(raise_dynamic_smem((const void*)gram_dmma_kernel, ctx->device, (int)smem));
     dim3 grid((unsigned)ntiles, (unsigned)splits);
-    gram_dmma_kernel<<<grid, THREADS, smem, ctx->stream>>>((const float*)mat, m, cols, ld, nt, k_per, partial);
+    gram_dmma_kernel<<<grid, THREADS, smem, ctx->stream>>>((const float*)mat, m, cols, ld, nt, k_per, partial, run_flag);
     NDMPS_LAUNCH_CHECK(ctx);
     dim3 rgrid(16, (unsigned)ntiles);
-    gram_dmma_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, nt, ntiles, (int)splits, g_dev);
+    gram_dmma_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, nt, ntiles, (int)splits, g_dev, run_flag);
     NDMPS_LAUNCH_CHECK(ctx);
     *done = true;
     return NDMPS_OK;

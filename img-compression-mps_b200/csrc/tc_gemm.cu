@@ -209,28 +209,35 @@ __device__ __constant__ int8_t REST_B[5] = {1, 0, 2, 0, 1};
 // Gram on the INTEGER tensor cores (kind::i8, int32 accumulators): error-free accumulation.
 //
 // The left factor of a sweep step is decided by the trailing kept eigenvalues of G = M M^T, which sit at
-// lambda_chi / lambda_1 ~ 1e-6 with gaps of a few percent of that: a Gram matrix accumulated in float32 (the
-// bf16x3 route above is 1e-7 .. 3e-7 normwise on data with a wide dynamic range, e.g. DCT coefficients)
-// rotates those eigenvectors visibly (measured: reconstructions 2e-4 off on the video chunk).  So the Gram
-// uses sliced integers (Ozaki scheme): every row i is scaled by a power of two, y = x 2^-sc_i in (-1/2, 1/2),
-// and written as four signed 7-bit digits, y = sum_p a_p 2^(-7 (p + 1)) + O(2^-29), |a_p| <= 64 (round to
-// nearest at every digit, exact float32 arithmetic).  Digit products are exact in the int32 accumulator:
-//     y_i . y_j = sum_s 2^(-7 (s + 2)) ACC_s,    ACC_s = sum_k sum_{p + q = s} a_p b_q,   s = 0 .. 3
-// ten MMAs per k-step of 32 at the int8 rate (= five bf16 MMAs), four accumulators of 128 columns = all of
-// tensor memory, NO drains inside a chain (|ACC_s| <= 4096 (s + 1) K: K up to 2^15 per chain), one exact
-// int32 -> float64 combination at the end of a CTA's K range.  What is lost is the digits beyond 2^-28 of
-// each row's largest element and the products with p + q >= 4: ~1e-9 normwise, a hundred times below the
-// float32-accumulated route, at a lower tensor-core and HBM cost (4 bytes of digits per element).
+// lambda_chi / lambda_1 ~ 1e-6 with gaps of a few percent of that.  Measured (profiles/r02_summary.md): a Gram
+// accumulated in float32 on the tensor cores (bf16x3 planes: 1e-7 .. 3e-7 normwise, the accumulator truncates)
+// rotates those eigenvectors - reconstructions 2e-4 off on the DCT video chunk.  So the tensor-core Gram uses
+// sliced integers (Ozaki scheme): row i is scaled by a power of two, y = x 2^-sc_i in (-1/2, 1/2), and written
+// as five signed 7-bit digits, y = sum_p a_p 2^(-7 (p + 1)) + O(2^-36), |a_p| <= 64 (round to nearest at every
+// digit, exact in float32).  Digit products are exact in the int32 accumulators:
+//     y_i . y_j = sum_s 2^(-7 (s + 2)) ACC_s,    ACC_s = sum_k sum_{p + q = s} a_p b_q,   s = 0 .. 4
+// fifteen MMAs per k-step of 32, five accumulators of 64 columns (tiles are 128 x 64), NO drains inside a chain
+// (|ACC_4| <= 5 * 4096 K: chains of 2^16 columns), one exact int32 -> float64 combination per chain.
+// What is dropped: products with p + q >= 5.  Those with p + q = 5 are zero-mean (independent digits); the
+// first systematic term is the digit-3 square at 2^-56, i.e. a relative error of 8e-14 rho_i^2 on G_ii with
+// rho_i = max|row| / rms(row) (with FOUR digits the same term sits at 2^-42: 1.2e-9 rho^2, measured, and
+// breaks fMRI and DCT rows with rho ~ 25; exact zeros have all-zero digits, so rho runs over the nonzero
+// elements).  rho is known before the products run (the scaling pass measures max, sum of squares and nonzero
+// count of every row): if 8e-14 max rho^2 exceeds 3e-10 a device-side flag hands the matrix to the exact
+// FP64-pipe kernel instead (gram_dmma.cu), without a host round trip.
 // ---------------------------------------------------------------------------------------------
-constexpr int I8_PLANES = 4;
+constexpr int I8_PLANES = 5;
+constexpr int I8_TN = 64;                        // columns of a Gram tile (five accumulators of 64 columns)
 constexpr int I8_BK = 64;                        // int8 elements per k-tile: 64-byte rows (SWIZZLE_64B)
 constexpr int I8_UK = 32;                        // K of one tcgen05.mma.kind::i8
-constexpr int I8_TILE_BYTES = TILE * I8_BK;      // 8 KB: one 128 x 64 digit tile
-constexpr int I8_MAX_CHAIN_TILES = 512;          // 2^15 columns per accumulator chain: |ACC_3| <= 4 * 4096 * 2^15 = 2^29
+constexpr int I8_BOX_BYTES = 64 * I8_BK;         // 4 KB: one TMA box of 64 rows x 64 digits
+constexpr int I8_MAX_CHAIN_TILES = 1024;         // 2^16 columns per accumulator chain: |ACC_4| <= 5 * 4096 * 2^16 < 2^31
+constexpr double I8_RHO2_LIMIT = 4096.0;         // 8e-14 * 4096 = 3.3e-10 relative on the worst diagonal entry
 
 struct GramI8Smem {
     static constexpr int STAGES = 3;
-    static constexpr int STAGE_BYTES = 2 * I8_PLANES * I8_TILE_BYTES;      // A digits 0..3 + B digits 0..3 = 64 KB
+    static constexpr int A_BYTES = I8_PLANES * 2 * I8_BOX_BYTES;       // 128 rows per digit plane
+    static constexpr int STAGE_BYTES = A_BYTES + I8_PLANES * I8_BOX_BYTES;   // + 64 rows per digit plane = 60 KB
     static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;
 };
@@ -254,52 +261,96 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t desc_a, uint64
         : "memory");
 }
 
-// rowmax[r] = max |x[r, :]| as float bits (non-negative floats order like unsigned integers); rowmax zeroed by the caller
+// tile t -> (row tile of 128, column tile of 64) over the tiles that touch the upper triangle: tj >= 2 ti
+__device__ __forceinline__ void upper_tile_i8(int t, int ntc, int& ti, int& tj) {
+    int row = 0, left = t;
+    while (left >= ntc - 2 * row) { left -= ntc - 2 * row; row++; }
+    ti = row;
+    tj = 2 * row + left;
+}
+
+// stats[(r * chunks + c) * 3 + {0, 1, 2}] = max |x|, sum x^2 (float64), number of nonzero elements of columns chunk c of row r
 __global__ void __launch_bounds__(256)
-row_absmax_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, int64_t cols_per_cta, unsigned* __restrict__ rowmax) {
-    __shared__ float red[8];
+row_stats_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, int64_t cols_per_cta, double* __restrict__ stats) {
+    __shared__ double red[3][8];
     const int64_t r = blockIdx.x;
     const int64_t c0 = (int64_t)blockIdx.y * cols_per_cta, c1 = c0 + cols_per_cta < cols ? c0 + cols_per_cta : cols;
     const float* p = x + r * ld;
     float m = 0.f;
+    double sq = 0.0;
+    int nz = 0;
     if ((ld & 3) == 0 && (c0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
         const int64_t v1 = c0 + ((c1 - c0) & ~int64_t(3));
         for (int64_t c = c0 + 4 * threadIdx.x; c < v1; c += 1024) {
             const float4 v = *reinterpret_cast<const float4*>(p + c);
             m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            sq += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+            nz += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
         }
-        for (int64_t c = v1 + threadIdx.x; c < c1; c += 256) m = fmaxf(m, fabsf(p[c]));
+        for (int64_t c = v1 + threadIdx.x; c < c1; c += 256) { m = fmaxf(m, fabsf(p[c])); sq += (double)p[c] * p[c]; nz += p[c] != 0.f; }
     } else {
-        for (int64_t c = c0 + threadIdx.x; c < c1; c += 256) m = fmaxf(m, fabsf(p[c]));
+        for (int64_t c = c0 + threadIdx.x; c < c1; c += 256) { m = fmaxf(m, fabsf(p[c])); sq += (double)p[c] * p[c]; nz += p[c] != 0.f; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    double md = (double)m, cnt = (double)nz;
+    md = warp_max(md);
+    sq = warp_sum(sq);
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = md; red[1][threadIdx.x >> 5] = sq; red[2][threadIdx.x >> 5] = cnt; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]);
-        if (m > 0.f && m < INFINITY) atomicMax(rowmax + r, __float_as_uint(m));
+        for (int w = 1; w < 8; w++) { md = fmax(md, red[0][w]); sq += red[1][w]; cnt += red[2][w]; }
+        double* o = stats + ((size_t)r * gridDim.y + blockIdx.y) * 3;
+        o[0] = md; o[1] = sq; o[2] = cnt;
     }
 }
 
-// sc[r]: y = x 2^-sc[r] lies in (-1/2, 1/2); digits[p][r][c] = digit p of y.  16 elements per thread (16-byte stores).
+// sc[r]: y = x 2^-sc[r] lies in (-1/2, 1/2).  use_exact[0] = 1 when a row is too heavy-tailed for five digits
+// (or not finite): the FP64-pipe kernel computes this Gram instead.  One CTA, fixed summation order.
 __global__ void __launch_bounds__(256)
-split_i8_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, const unsigned* __restrict__ rowmax,
-                int8_t* __restrict__ digits, int64_t ldp, int64_t plane_stride, int* __restrict__ sc_out) {
+row_scale_kernel(const double* __restrict__ stats, int64_t rows, int chunks, int* __restrict__ sc, int* __restrict__ use_exact) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < rows; r += 256) {
+        double mx = 0.0, sq = 0.0, nz = 0.0;
+        for (int c = 0; c < chunks; c++) {
+            const double* st = stats + (r * chunks + c) * 3;
+            mx = fmax(mx, st[0]); sq += st[1]; nz += st[2];
+        }
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);                  // mx = f 2^e, f in [1/2, 1)
+        sc[r] = e + 1;
+        const bool finite = mx < INFINITY && sq < INFINITY && sq == sq;
+        // rho^2 over the NONZERO elements: an exact zero has all-zero digits and contributes nothing to the dropped products
+        if (!finite || (sq > 0.0 && mx * mx * nz > I8_RHO2_LIMIT * sq)) atomicOr(&bad, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) use_exact[0] = bad;
+}
+
+// digits[p][r][c] = digit p of y = x 2^-sc[r].  16 elements per thread (16-byte stores).
+__global__ void __launch_bounds__(256)
+split_i8_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, const int* __restrict__ sc,
+                const int* __restrict__ use_exact, int8_t* __restrict__ digits, int64_t ldp, int64_t plane_stride) {
+    if (use_exact[0]) return;
     const int64_t groups = ldp >> 4, total = rows * groups, stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int64_t r = i / groups, c0 = (i - r * groups) << 4;
-        const float mx = __uint_as_float(rowmax[r]);
-        int e = 0;
-        if (mx > 0.f) frexpf(mx, &e);                 // mx = f 2^e, f in [1/2, 1)
-        const int sc = e + 1;
-        if (c0 == 0) sc_out[r] = sc;
-        const float down = ldexpf(1.f, -sc);
+        const float down = ldexpf(1.f, 7 - sc[r]);     // y * 128
         __align__(16) int8_t d[I8_PLANES][16];
+        __align__(16) float v[16];
         const float* p = x + r * ld + c0;
+        if (vec && c0 + 16 <= cols) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(v + 4 * j) = __ldcs(reinterpret_cast<const float4*>(p) + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = c0 + j < cols ? p[j] : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            float t = (c0 + j < cols ? p[j] : 0.f) * down * 128.f;
+            float t = v[j] * down;
 #pragma unroll
             for (int q = 0; q < I8_PLANES; q++) {
                 const float a = rintf(t);
@@ -313,10 +364,11 @@ split_i8_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t
     }
 }
 
-// TMEM columns: accumulator s at [128 s, 128 s + 128), s = p + q = 0 .. 3.
+// TMEM columns: accumulator s at [64 s, 64 s + 64), s = p + q = 0 .. 4.  partial[split][tile]: 128 x 64 float64.
 __global__ void __launch_bounds__(THREADS, 1)
-gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K, int64_t k_per, const int* __restrict__ sc,
-               double* __restrict__ partial) {
+gram_i8_kernel(const __grid_constant__ CUtensorMap map, int ntc, int m, int64_t K, int64_t k_per, const int* __restrict__ sc,
+               const int* __restrict__ use_exact, double* __restrict__ partial) {
+    if (use_exact[0]) return;                         // uniform over the grid: the FP64-pipe kernel takes this matrix
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GramI8Smem::BARRIER_OFF);
@@ -327,7 +379,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ti, tj;
-    upper_tile(blockIdx.x, nt, ti, tj);
+    upper_tile_i8(blockIdx.x, ntc, ti, tj);
     const int64_t kbeg = (int64_t)blockIdx.y * k_per;
     const int64_t kend = kbeg + k_per < K ? kbeg + k_per : K;
     const int nk = (int)((kend - kbeg + I8_BK - 1) / I8_BK);
@@ -346,74 +398,68 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 0 && lane == 0) {
-            // ---- TMA producer ----
-            for (int kt = 0; kt < nk; kt++) {
-                const int s = kt % GramI8Smem::STAGES;
-                mbar_wait(&empty[s], ((kt / GramI8Smem::STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], GramI8Smem::STAGE_BYTES);
-                uint8_t* st = smem + s * GramI8Smem::STAGE_BYTES;
-                const int kc = (int)(kbeg + (int64_t)kt * I8_BK);
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer: per digit plane two boxes of 64 rows for A, one for B ----
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % GramI8Smem::STAGES;
+            mbar_wait(&empty[s], ((kt / GramI8Smem::STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full[s], GramI8Smem::STAGE_BYTES);
+            uint8_t* st = smem + s * GramI8Smem::STAGE_BYTES;
+            const int kc = (int)(kbeg + (int64_t)kt * I8_BK);
 #pragma unroll
-                for (int p = 0; p < I8_PLANES; p++) {
-                    tma_load_3d(st + p * I8_TILE_BYTES, &map, &full[s], kc, ti * TILE, p);
-                    tma_load_3d(st + (I8_PLANES + p) * I8_TILE_BYTES, &map, &full[s], kc, tj * TILE, p);
-                }
-            }
-        } else if (warp == 1 && lane == 0) {
-            // ---- MMA issuer ----
-            constexpr uint32_t idesc = instr_desc_i8(TILE, TILE);
-            for (int kt = 0; kt < nk; kt++) {
-                const int s = kt % GramI8Smem::STAGES;
-                const int chain = kt / I8_MAX_CHAIN_TILES, within = kt - chain * I8_MAX_CHAIN_TILES;
-                if (within == 0 && chain > 0) {           // the epilogue has read the previous chain out of tensor memory
-                    mbar_wait(acc_empty, (chain - 1) & 1);
-                    tc_fence_after();
-                }
-                mbar_wait(&full[s], (kt / GramI8Smem::STAGES) & 1);
-                tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * GramI8Smem::STAGE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
-#pragma unroll
-                    for (int p = 0; p < I8_PLANES; p++) {
-#pragma unroll
-                        for (int q = 0; q < I8_PLANES; q++) {
-                            if (p + q >= I8_PLANES) continue;
-                            const uint64_t da = smem_desc_sw64(st + p * I8_TILE_BYTES + ks * 32);
-                            const uint64_t db = smem_desc_sw64(st + (I8_PLANES + q) * I8_TILE_BYTES + ks * 32);
-                            // the first product of each accumulator in a chain overwrites: (p, q) = (0, s) comes first for every s
-                            umma_i8(tmem_base + (uint32_t)((p + q) * TILE), da, db, idesc, !(within == 0 && ks == 0 && p == 0));
-                        }
-                    }
-                }
-                umma_commit(&empty[s]);
-                if (within == I8_MAX_CHAIN_TILES - 1 || kt == nk - 1) umma_commit(acc_full);
+            for (int p = 0; p < I8_PLANES; p++) {
+                tma_load_3d(st + (2 * p) * I8_BOX_BYTES, &map, &full[s], kc, ti * TILE, p);
+                tma_load_3d(st + (2 * p + 1) * I8_BOX_BYTES, &map, &full[s], kc, ti * TILE + 64, p);
+                tma_load_3d(st + GramI8Smem::A_BYTES + p * I8_BOX_BYTES, &map, &full[s], kc, tj * I8_TN, p);
             }
         }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ---- epilogue: exact int32 -> float64 combination of the four digit-sum accumulators ----
-        const int q4 = warp & 3, half = (warp - 4) >> 2;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
-        double acc[64];
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = instr_desc_i8(TILE, I8_TN);
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % GramI8Smem::STAGES;
+            const int chain = kt / I8_MAX_CHAIN_TILES, within = kt - chain * I8_MAX_CHAIN_TILES;
+            if (within == 0 && chain > 0) {           // the epilogue has read the previous chain out of tensor memory
+                mbar_wait(acc_empty, (chain - 1) & 1);
+                tc_fence_after();
+            }
+            mbar_wait(&full[s], (kt / GramI8Smem::STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * GramI8Smem::STAGE_BYTES);
 #pragma unroll
-        for (int i = 0; i < 64; i++) acc[i] = 0.0;
+            for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
+#pragma unroll
+                for (int p = 0; p < I8_PLANES; p++) {
+#pragma unroll
+                    for (int q = 0; q < I8_PLANES; q++) {
+                        if (p + q >= I8_PLANES) continue;
+                        const uint64_t da = smem_desc_sw64(st + (2 * p) * I8_BOX_BYTES + ks * 32);
+                        const uint64_t db = smem_desc_sw64(st + GramI8Smem::A_BYTES + q * I8_BOX_BYTES + ks * 32);
+                        // the first product into each accumulator of a chain overwrites: (0, s) comes first for every s
+                        umma_i8(tmem_base + (uint32_t)((p + q) * I8_TN), da, db, idesc, !(within == 0 && ks == 0 && p == 0));
+                    }
+                }
+            }
+            umma_commit(&empty[s]);
+            if (within == I8_MAX_CHAIN_TILES - 1 || kt == nk - 1) umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: exact int32 -> float64 combination of the five digit-sum accumulators ----
+        const int q4 = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 32);
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = 0.0;
         for (int chain = 0; chain < n_chains; chain++) {
             mbar_wait(acc_full, chain & 1);
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < I8_PLANES; s++) {
-                const double w = s == 0 ? 0x1p-14 : (s == 1 ? 0x1p-21 : (s == 2 ? 0x1p-28 : 0x1p-35));
+                const double w = s == 0 ? 0x1p-14 : (s == 1 ? 0x1p-21 : (s == 2 ? 0x1p-28 : (s == 3 ? 0x1p-35 : 0x1p-42)));
+                uint32_t v[32];
+                tmem_ld32(lane_base + (uint32_t)(s * I8_TN), v);
 #pragma unroll
-                for (int g = 0; g < 2; g++) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + (uint32_t)(s * TILE + g * 32), v);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) acc[g * 32 + i] = fma((double)(int)v[i], w, acc[g * 32 + i]);
-                }
+                for (int i = 0; i < 32; i++) acc[i] = fma((double)(int)v[i], w, acc[i]);
             }
             tc_fence_before();
             __syncwarp();
@@ -422,10 +468,10 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K
         // undo the row scalings: G_ij = 2^(sc_i + sc_j) y_i . y_j
         const int gi = ti * TILE + q4 * 32 + lane;
         const int sci = gi < m ? sc[gi] : 0;
-        double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * TILE + (size_t)(q4 * 32 + lane) * TILE + half * 64;
+        double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TILE * I8_TN + (size_t)(q4 * 32 + lane) * I8_TN + half * 32;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-            const int gj = tj * TILE + half * 64 + i;
+        for (int i = 0; i < 32; i += 2) {
+            const int gj = tj * I8_TN + half * 32 + i;
             const double s0 = ldexp(acc[i], sci + (gj < m ? sc[gj] : 0));
             const double s1 = ldexp(acc[i + 1], sci + (gj + 1 < m ? sc[gj + 1] : 0));
             *reinterpret_cast<double2*>(out + i) = make_double2(s0, s1);
@@ -441,15 +487,17 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int nt, int m, int64_t K
 
 // G[i][j] = G[j][i] = sum over splits, in split order
 __global__ void __launch_bounds__(256)
-gram_tc_reduce_kernel(const double* __restrict__ partial, int m, int nt, int ntiles, int splits, double* __restrict__ G) {
+gram_i8_reduce_kernel(const double* __restrict__ partial, int m, int ntc, int ntiles, int splits, const int* __restrict__ use_exact,
+                      double* __restrict__ G) {
+    if (use_exact[0]) return;
     int ti, tj;
-    upper_tile(blockIdx.y, nt, ti, tj);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TILE * TILE; e += gridDim.x * blockDim.x) {
-        const int r = e / TILE, c = e - r * TILE;
-        const int gi = ti * TILE + r, gj = tj * TILE + c;
-        if (gi >= m || gj >= m || (ti == tj && gj < gi)) continue;
+    upper_tile_i8(blockIdx.y, ntc, ti, tj);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TILE * I8_TN; e += gridDim.x * blockDim.x) {
+        const int r = e / I8_TN, c = e - r * I8_TN;
+        const int gi = ti * TILE + r, gj = tj * I8_TN + c;
+        if (gi >= m || gj >= m || gj < gi) continue;
         double s = 0.0;
-        for (int z = 0; z < splits; z++) s += partial[((size_t)z * ntiles + blockIdx.y) * TILE * TILE + e];
+        for (int z = 0; z < splits; z++) s += partial[((size_t)z * ntiles + blockIdx.y) * TILE * I8_TN + e];
         G[(size_t)gi * m + gj] = s;
         G[(size_t)gj * m + gi] = s;
     }
@@ -681,36 +729,45 @@ int tc_split(ndmps_ctx* ctx, const void* src, int dtype, int64_t rows, int64_t c
     return NDMPS_OK;
 }
 
+int gram_dmma(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done,
+              const int* run_flag);
+
 // G = M M^T from the float32 unfolding `mat` (rows x cols, row stride ld).  *done = false: shape not eligible.
+// Launches BOTH the sliced-integer tensor-core Gram and the exact FP64-pipe Gram; a device-side flag set by the
+// row-scaling pass lets exactly one of them run (the other returns at once), so no host round trip is needed.
 int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done) {
     using namespace tc;
     *done = false;
     if (dtype != NDMPS_F32 || rows < 64 || rows > 4096 || cols < 2048) return NDMPS_OK;
-    // 1. row scales, 2. four int8 digit planes
-    unsigned* rowmax = nullptr;
-    int* sc = nullptr;
-    NDMPS_TRY(ctx->ws.get<unsigned>((size_t)rows, &rowmax));
-    NDMPS_TRY(ctx->ws.get<int>((size_t)rows, &sc));
-    NDMPS_CUDA_TRY(cudaMemsetAsync(rowmax, 0, (size_t)rows * sizeof(unsigned), ctx->stream));
+    if ((ld & 3) != 0 || (reinterpret_cast<uintptr_t>(mat) & 15) != 0) return NDMPS_OK;      // the FP64-pipe fallback needs it
+    // 1. row statistics -> power-of-two row scales + the exactness flag
+    int64_t chunks = ((int64_t)ctx->sm_count * 8 + rows - 1) / rows;
     {
-        int64_t chunks = ((int64_t)ctx->sm_count * 8 + rows - 1) / rows;
         const int64_t max_chunks = (cols + 4095) / 4096;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
-        int64_t per = (cols + chunks - 1) / chunks;
-        per = (per + 3) & ~int64_t(3);
-        chunks = (cols + per - 1) / per;
-        row_absmax_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, ctx->stream>>>((const float*)mat, cols, ld, per, rowmax);
-        NDMPS_LAUNCH_CHECK(ctx);
     }
+    int64_t per = (cols + chunks - 1) / chunks;
+    per = (per + 3) & ~int64_t(3);
+    chunks = (cols + per - 1) / per;
+    double* stats = nullptr;
+    int *sc = nullptr, *use_exact = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)(3 * rows * chunks), &stats));
+    NDMPS_TRY(ctx->ws.get<int>((size_t)rows, &sc));
+    NDMPS_TRY(ctx->ws.get<int>(4, &use_exact));
+    row_stats_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, ctx->stream>>>((const float*)mat, cols, ld, per, stats);
+    NDMPS_LAUNCH_CHECK(ctx);
+    row_scale_kernel<<<1, 256, 0, ctx->stream>>>(stats, rows, (int)chunks, sc, use_exact);
+    NDMPS_LAUNCH_CHECK(ctx);
+    // 2. five int8 digit planes
     const int64_t ldp = (cols + 15) & ~int64_t(15), pstride = rows * ldp;
     int8_t* digits = nullptr;
     NDMPS_TRY(ctx->ws.get<int8_t>((size_t)(I8_PLANES * pstride), &digits));
     {
         const int64_t total = rows * (ldp >> 4);
         int64_t want = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
-        split_i8_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, ctx->stream>>>((const float*)mat, rows, cols, ld, rowmax, digits, ldp,
-                                                                                                pstride, sc);
+        split_i8_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, ctx->stream>>>((const float*)mat, rows, cols, ld, sc, use_exact,
+                                                                                                digits, ldp, pstride);
         NDMPS_LAUNCH_CHECK(ctx);
     }
     // 3. digit products on the integer tensor cores
@@ -720,28 +777,34 @@ int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t
         if (!fn) { set_error("tc: cuTensorMapEncodeTiled is not available from the driver"); return NDMPS_ERR_CUDA; }
         const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)I8_PLANES};
         const cuuint64_t strides[2] = {(cuuint64_t)ldp, (cuuint64_t)pstride};
-        const cuuint32_t box[3] = {(cuuint32_t)I8_BK, (cuuint32_t)TILE, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)I8_BK, 64, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, digits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled (int8 digits) failed (%d)", (int)r); return NDMPS_ERR_CUDA; }
     }
-    const int m = (int)rows, nt = (m + TILE - 1) / TILE, ntiles = nt * (nt + 1) / 2;
+    const int m = (int)rows, ntr = (m + TILE - 1) / TILE, ntc = (m + I8_TN - 1) / I8_TN;
+    int ntiles = 0;
+    for (int ti = 0; ti < ntr; ti++) ntiles += ntc - 2 * ti > 0 ? ntc - 2 * ti : 0;
     int64_t splits = (int64_t)ctx->sm_count / ntiles;          // whole waves of one CTA per SM
     if (splits < 1) splits = 1;
     int64_t k_per = (cols + splits - 1) / splits;
     k_per = ((k_per + I8_BK - 1) / I8_BK) * I8_BK;
     splits = (cols + k_per - 1) / k_per;
     double* partial = nullptr;
-    NDMPS_TRY(ctx->ws.get<double>((size_t)splits * ntiles * TILE * TILE, &partial));
+    NDMPS_TRY(ctx->ws.get<double>((size_t)splits * ntiles * TILE * I8_TN, &partial));
     NDMPS_TRY(raise_dynamic_smem((const void*)gram_i8_kernel, ctx->device, GramI8Smem::TOTAL));
     dim3 grid((unsigned)ntiles, (unsigned)splits);
-    gram_i8_kernel<<<grid, THREADS, GramI8Smem::TOTAL, ctx->stream>>>(map, nt, m, cols, k_per, sc, partial);
+    gram_i8_kernel<<<grid, THREADS, GramI8Smem::TOTAL, ctx->stream>>>(map, ntc, m, cols, k_per, sc, use_exact, partial);
     NDMPS_LAUNCH_CHECK(ctx);
     ctx->tc_launches++;
-    dim3 rgrid(16, (unsigned)ntiles);
-    gram_tc_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, nt, ntiles, (int)splits, g_dev);
+    dim3 rgrid(8, (unsigned)ntiles);
+    gram_i8_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, ntc, ntiles, (int)splits, use_exact, g_dev);
     NDMPS_LAUNCH_CHECK(ctx);
+    // 4. the exact kernel: runs only when the flag is set
+    bool exact_ok = false;
+    NDMPS_TRY(gram_dmma(ctx, mat, rows, cols, ld, dtype, g_dev, &exact_ok, use_exact));
+    NDMPS_REQUIRE(exact_ok, "gram_tc: the FP64-pipe fallback declined a %lld x %lld unfolding", (long long)rows, (long long)cols);
     *done = true;
     return NDMPS_OK;
 }

