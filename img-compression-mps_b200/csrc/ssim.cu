@@ -8,20 +8,15 @@
 // array contributes frames x slices per family.
 //
 // Pass 1: per-slice data range.  Pass 2: tiles of TILE_H x TILE_W interior pixels,
-// separable box sums of x, y, xx, yy, xy from a shared-memory patch, one partial sum per
-// tile.  Pass 3: fixed-order reduction (deterministic).
+// separable box sums of x, y, xx, yy, xy in float64 from a shared-memory patch, one
+// partial sum per tile.  Pass 3: fixed-order reduction (deterministic).
 //
-// Arithmetic (template parameter A of the tile kernels):
-//   * double - what the reference computes (its inputs are float64): float64 inputs always,
-//     float32 inputs when the context option `ssim_exact` is set;
-//   * float  - float32 inputs by default.  SSIM is invariant under x -> x / R and its variance terms
-//     under x -> x - mu, so every tile works on (x - mu) / R with mu its first pixel (per slice in
-//     the slice-batched kernel) and R the slice's data range: values are O(1), C1 = 1e-4 and
-//     C2 = 9e-4 are constants, and the cancellation in E[xx] - E[x]^2 acts on deviations from a
-//     nearby pixel instead of on the raw means.  Tile sums are float32, everything across tiles is
-//     float64.  Agreement with the float64 arithmetic: ~1e-6 per slice (tests), against a 1e-4 bar.
-#include <type_traits>
-
+// float32 inputs with the 7 x 7 window take the STREAMING kernels further down instead of the tile
+// kernels (context option `ssim_exact` = 1 forces the tile kernels): a warp walks down the rows of a
+// strip, every thread keeps the last seven rows of its column in registers, window sums are float64
+// (products and sums of float32 values are exact there, so the cancellation in E[xx] - E[x]^2 costs
+// nothing), only the final SSIM formula is evaluated in float32 on range-normalised moments.
+// No shared memory, no index tables; agreement with the float64 formula ~1e-7.
 #include "common.cuh"
 
 namespace ndmps {
@@ -89,14 +84,13 @@ __global__ void __launch_bounds__(256) ssim_range_kernel(const T* __restrict__ a
 // Horizontal pass: direct win-tap sums.  Vertical pass: a warp owns a strip of TILE_H / 8 output rows
 // (lane = column) and slides the window down with one add and one subtract per quantity instead of
 // `win` adds (for float32 inputs every intermediate is exact in float64).
-template <class T, class A>
+template <class T>
 __global__ void __launch_bounds__(256)
 ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                  int tiles_y, int tiles_x, double* __restrict__ partial) {
-    constexpr bool FAST = std::is_same<A, float>::value;                // shifted / normalised float32 arithmetic
     extern __shared__ unsigned char tile_smem[];
     constexpr int HS_LD = TILE_W + 1;                                   // row stride of the horizontal sums (bank spread)
-    A* hs = reinterpret_cast<A*>(tile_smem);                            // [5][PATCH_H][HS_LD]
+    double* hs = reinterpret_cast<double*>(tile_smem);                  // [5][PATCH_H][HS_LD]
     T* pa = reinterpret_cast<T*>(hs + 5 * PATCH_H * HS_LD);             // [PATCH_H][PATCH_W + 1]
     T* pb = pa + PATCH_H * (PATCH_W + 1);
     __shared__ double scratch[32];
@@ -108,14 +102,6 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
     const int64_t base = slice_base(f, s);
     const int64_t oy = (int64_t)ty * TILE_H, ox = (int64_t)tx * TILE_W;   // interior coordinates
     const int ph = TILE_H + win - 1, pw = TILE_W + win - 1;
-    const double R = range[s];
-    T mu_a = (T)0, mu_b = (T)0, inv_r = (T)1;
-    if (FAST) {
-        const int64_t off0 = base + oy * f.sh + ox * f.sw;                // the tile's first pixel: always inside the slice
-        mu_a = a[off0];
-        mu_b = b[off0] > (T)0 ? b[off0] : (T)0;
-        inv_r = (T)(1.0 / R);                                            // R == 0: inf -> NaN scores, as the reference's 0 / 0
-    }
     for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
         const int r = e / pw, c = e - r * pw;
         const int64_t h = oy + r, w = ox + c;
@@ -125,7 +111,6 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
             va = a[off];
             vb = b[off];
             vb = vb > (T)0 ? vb : (T)0;
-            if (FAST) { va = (va - mu_a) * inv_r; vb = (vb - mu_b) * inv_r; }
         }
         pa[r * (PATCH_W + 1) + c] = va;
         pb[r * (PATCH_W + 1) + c] = vb;
@@ -137,9 +122,9 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
         const int r = e / TILE_W, c = e - r * TILE_W;
         const T* xa = pa + r * (PATCH_W + 1) + c;
         const T* xb = pb + r * (PATCH_W + 1) + c;
-        A sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
         for (int j = 0; j < win; j++) {
-            const A x = (A)xa[j], y = (A)xb[j];
+            const double x = (double)xa[j], y = (double)xb[j];
             sx += x; sy += y;
             sxx = fma(x, x, sxx); syy = fma(y, y, syy); sxy = fma(x, y, sxy);
         }
@@ -147,20 +132,19 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
         hs[(3 * PATCH_H + r) * HS_LD + c] = syy; hs[(4 * PATCH_H + r) * HS_LD + c] = sxy;
     }
     __syncthreads();
-    // normalised data (FAST): the data range is 1, the means carry the tile's shift back
-    const A c1 = FAST ? (A)1e-4 : (A)((0.01 * R) * (0.01 * R)), c2 = FAST ? (A)9e-4 : (A)((0.03 * R) * (0.03 * R));
-    const A off_x = FAST ? (A)mu_a * (A)inv_r : (A)0, off_y = FAST ? (A)mu_b * (A)inv_r : (A)0;
-    const A np = (A)(win * win);
-    const A inv_np = (A)1 / np, cov_norm = np / (np - (A)1);
+    const double R = range[s];
+    const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
+    const double np = (double)(win * win);
+    const double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
     const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;   // interior extent
     double acc = 0.0;
     {
         constexpr int STRIP = TILE_H / 8;
         const int x = threadIdx.x & 31, y0 = (threadIdx.x >> 5) * STRIP;
-        A v[5];
+        double v[5];
 #pragma unroll
         for (int q = 0; q < 5; q++) {
-            A t = 0;
+            double t = 0.0;
             for (int i = 0; i < win; i++) t += hs[(q * PATCH_H + y0 + i) * HS_LD + x];
             v[q] = t;
         }
@@ -173,13 +157,12 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
                     v[q] += hs[(q * PATCH_H + y + win - 1) * HS_LD + x] - hs[(q * PATCH_H + y - 1) * HS_LD + x];
             }
             if (oy + y < ih && ox + x < iw) {
-                const A ux = v[0] * inv_np, uy = v[1] * inv_np;
-                const A vx = cov_norm * (v[2] * inv_np - ux * ux), vy = cov_norm * (v[3] * inv_np - uy * uy);
-                const A vxy = cov_norm * (v[4] * inv_np - ux * uy);
-                const A mx = ux + off_x, my = uy + off_y;               // true means (in units of R when FAST)
-                const A num = ((A)2 * mx * my + c1) * ((A)2 * vxy + c2);
-                const A den = (mx * mx + my * my + c1) * (vx + vy + c2);
-                acc += (double)(num / den);
+                const double ux = v[0] * inv_np, uy = v[1] * inv_np;
+                const double vx = cov_norm * (v[2] * inv_np - ux * ux), vy = cov_norm * (v[3] * inv_np - uy * uy);
+                const double vxy = cov_norm * (v[4] * inv_np - ux * uy);
+                const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
+                const double den = (ux * ux + uy * uy + c1) * (vx + vy + c2);
+                acc += num / den;
             }
         }
     }
@@ -187,24 +170,14 @@ ssim_tile_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-static inline bool ssim_fast(const ndmps_ctx* ctx, const float*) { return ctx->opt_ssim_exact == 0; }
-static inline bool ssim_fast(const ndmps_ctx*, const double*) { return false; }
-
-template <class T, class A>
-static int launch_ssim_tile_as(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
-                               int64_t nt, double* partial) {
-    const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(A) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
-    NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_kernel<T, A>, ctx->device, 96 * 1024));
-    ssim_tile_kernel<T, A><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
-    NDMPS_LAUNCH_CHECK(ctx);
-    return NDMPS_OK;
-}
-
 template <class T>
 static int launch_ssim_tile(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, const double* range, int ty, int tx,
                             int64_t nt, double* partial) {
-    if (ssim_fast(ctx, a)) return launch_ssim_tile_as<T, float>(ctx, a, b, f, range, ty, tx, nt, partial);
-    return launch_ssim_tile_as<T, double>(ctx, a, b, f, range, ty, tx, nt, partial);
+    const size_t smem = (size_t)5 * PATCH_H * (TILE_W + 1) * sizeof(double) + (size_t)2 * PATCH_H * (PATCH_W + 1) * sizeof(T);
+    NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_kernel<T>, ctx->device, 96 * 1024));
+    ssim_tile_kernel<T><<<(unsigned)nt, 256, smem, ctx->stream>>>(a, b, f, range, ty, tx, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -259,11 +232,10 @@ __global__ void __launch_bounds__(256) ssim_range_finalize_kernel(const unsigned
     if (s < S) range[s] = dkey_inv(keys[2 * s + 1]) - dkey_inv(keys[2 * s]);
 }
 
-template <class T, int WIN, class A>
+template <class T, int WIN>
 __global__ void __launch_bounds__(256)
 ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                          int tiles_y, int tiles_x, double* __restrict__ partial) {
-    constexpr bool FAST = std::is_same<A, float>::value;
     extern __shared__ unsigned char bt_smem[];
     constexpr int win = WIN, pad = (WIN - 1) / 2;
     const int ph = BT_H + win - 1, pw = BT_W + win - 1;
@@ -278,14 +250,6 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     const bool live = s < f.S;
     const int64_t base = live ? slice_base(f, s) : 0;
     const int64_t oy = (int64_t)ty * BT_H, ox = (int64_t)tx * BT_W;
-    const double R = live ? range[s] : 1.0;
-    T mu_a = (T)0, mu_b = (T)0, inv_r = (T)1;
-    if (FAST && live) {
-        const int64_t off0 = base + oy * f.sh + ox * f.sw;                // this slice's first pixel of the tile
-        mu_a = a[off0];
-        mu_b = b[off0] > (T)0 ? b[off0] : (T)0;
-        inv_r = (T)(1.0 / R);
-    }
     for (int e = warp; e < ph * pw; e += 8) {
         const int r = e / pw, c = e - r * pw;
         const int64_t h = oy + r, w = ox + c;
@@ -295,7 +259,6 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
             va = a[off];
             vb = b[off];
             vb = vb > (T)0 ? vb : (T)0;
-            if (FAST) { va = (va - mu_a) * inv_r; vb = (vb - mu_b) * inv_r; }
         }
         pa[(size_t)e * BT_SLICES + lane] = va;
         pb[(size_t)e * BT_SLICES + lane] = vb;
@@ -303,25 +266,25 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     __syncthreads();
     double acc = 0.0;
     if (live) {
-        const A c1 = FAST ? (A)1e-4 : (A)((0.01 * R) * (0.01 * R)), c2 = FAST ? (A)9e-4 : (A)((0.03 * R) * (0.03 * R));
-        const A off_x = FAST ? (A)mu_a * (A)inv_r : (A)0, off_y = FAST ? (A)mu_b * (A)inv_r : (A)0;
-        constexpr A np = (A)(WIN * WIN);
-        constexpr A inv_np = (A)1 / np, cov_norm = np / (np - (A)1);
+        const double R = range[s];
+        const double c1 = (0.01 * R) * (0.01 * R), c2 = (0.03 * R) * (0.03 * R);
+        constexpr double np = (double)(WIN * WIN);
+        constexpr double inv_np = 1.0 / np, cov_norm = np / (np - 1.0);
         const int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
         // one output column per warp: horizontal WIN-tap sums per patch row, vertical running sum over
         // a register ring of the last WIN rows (everything unrolled, the ring is static registers)
         const int x = warp;
         if (ox + x < iw) {
-            A ring[WIN][5];
-            A vs[5] = {0, 0, 0, 0, 0};
+            double ring[WIN][5];
+            double vs[5] = {0, 0, 0, 0, 0};
 #pragma unroll
             for (int r = 0; r < BT_H + WIN - 1; r++) {
-                A hsum[5] = {0, 0, 0, 0, 0};
+                double hsum[5] = {0, 0, 0, 0, 0};
                 const size_t rowbase = ((size_t)r * pw + x) * BT_SLICES + lane;
 #pragma unroll
                 for (int j = 0; j < WIN; j++) {
-                    const A xv = (A)pa[rowbase + (size_t)j * BT_SLICES];
-                    const A yv = (A)pb[rowbase + (size_t)j * BT_SLICES];
+                    const double xv = (double)pa[rowbase + (size_t)j * BT_SLICES];
+                    const double yv = (double)pb[rowbase + (size_t)j * BT_SLICES];
                     hsum[0] += xv; hsum[1] += yv;
                     hsum[2] = fma(xv, xv, hsum[2]); hsum[3] = fma(yv, yv, hsum[3]); hsum[4] = fma(xv, yv, hsum[4]);
                 }
@@ -334,11 +297,10 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
                 if (r >= WIN - 1) {
                     const int y = r - (WIN - 1);
                     if (oy + y < ih) {
-                        const A ux = vs[0] * inv_np, uy = vs[1] * inv_np;
-                        const A vx = cov_norm * (vs[2] * inv_np - ux * ux), vy = cov_norm * (vs[3] * inv_np - uy * uy);
-                        const A vxy = cov_norm * (vs[4] * inv_np - ux * uy);
-                        const A mx = ux + off_x, my = uy + off_y;
-                        acc += (double)((((A)2 * mx * my + c1) * ((A)2 * vxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2)));
+                        const double ux = vs[0] * inv_np, uy = vs[1] * inv_np;
+                        const double vx = cov_norm * (vs[2] * inv_np - ux * ux), vy = cov_norm * (vs[3] * inv_np - uy * uy);
+                        const double vxy = cov_norm * (vs[4] * inv_np - ux * uy);
+                        acc += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
                     }
                 }
             }
@@ -347,6 +309,147 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
     acc = block_sum(acc, scratch);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Streaming kernels for float32 inputs, window 7
+// ---------------------------------------------------------------------------------------------
+namespace stream {
+
+constexpr int WIN = 7, PAD = 3, NP = 49;
+constexpr int STRIP = 32 - (WIN - 1);          // output columns per warp of the column kernel
+constexpr int BAND = 64;                        // output rows per unit
+
+// SSIM of one window from its float64 sums (x, y, xx + yy, xy); inv_r = 1 / data range of the slice
+__device__ __forceinline__ float window_score(double sx, double sy, double sq, double sxy, double inv_r) {
+    constexpr double inv_np = 1.0 / NP, cov_norm = (double)NP / (NP - 1);
+    const double ux = sx * inv_np, uy = sy * inv_np;
+    const double vsum = cov_norm * (sq * inv_np - ux * ux - uy * uy);      // vx + vy, exact cancellation
+    const double vxy = cov_norm * (sxy * inv_np - ux * uy);
+    // range-normalised moments: C1 = 1e-4, C2 = 9e-4 are constants; the formula itself in float32
+    const float mx = (float)(ux * inv_r), my = (float)(uy * inv_r);
+    const float vs = (float)(vsum * inv_r * inv_r), vc = (float)(vxy * inv_r * inv_r);
+    const float num = (2.f * mx * my + 1e-4f) * (2.f * vc + 9e-4f);
+    const float den = (mx * mx + my * my + 1e-4f) * (vs + 9e-4f);
+    return num / den;
+}
+
+// lane = column (f.sw == 1).  Unit = (slice, strip of STRIP output columns, band of BAND output rows), one warp each.
+// partial[unit] = sum of the window scores of the unit (float64).
+__global__ void __launch_bounds__(256, 2)
+ssim_col_kernel(const float* __restrict__ a, const float* __restrict__ b, SliceFamily f, const double* __restrict__ range,
+                int n_strips, int n_bands, int64_t n_units, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (u >= n_units) return;
+    const int rb = (int)(u % n_bands);
+    const int cs = (int)((u / n_bands) % n_strips);
+    const int64_t s = u / ((int64_t)n_bands * n_strips);
+    const int64_t base = slice_base(f, s);
+    const int64_t ih = f.H - 2 * PAD, iw = f.W - 2 * PAD;
+    const int64_t oy0 = (int64_t)rb * BAND, oy1 = oy0 + BAND < ih ? oy0 + BAND : ih;     // output rows [oy0, oy1)
+    const int64_t col = (int64_t)cs * STRIP + lane;                                       // input column of this lane
+    const bool col_ok = col < f.W;
+    const bool out_ok = lane < STRIP && col < iw;
+    const double inv_r = 1.0 / range[s];
+    const float* pa = a + base + col;
+    const float* pb = b + base + col;
+    double ring[WIN][4];
+#pragma unroll
+    for (int j = 0; j < WIN; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0.0;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    double acc = 0.0;
+    const int64_t nrows = oy1 - oy0 + (WIN - 1);
+    for (int64_t r0 = 0; r0 < nrows; r0 += WIN) {
+        // the fourteen loads of a seven-row group are issued together (memory-level parallelism), then consumed
+        float xf[WIN], yf[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; j++) {
+            const bool ok = col_ok && r0 + j < nrows;
+            const int64_t off = (oy0 + r0 + j) * f.sh;
+            xf[j] = ok ? __ldg(pa + off) : 0.f;
+            yf[j] = ok ? __ldg(pb + off) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < WIN; j++) {
+            const int64_t r = r0 + j;
+            if (r < nrows) {
+                const double x = (double)xf[j], y = (double)fmaxf(yf[j], 0.f);
+                const double q2 = fma(x, x, y * y), q3 = x * y;
+                v0 += x - ring[j][0]; v1 += y - ring[j][1]; v2 += q2 - ring[j][2]; v3 += q3 - ring[j][3];
+                ring[j][0] = x; ring[j][1] = y; ring[j][2] = q2; ring[j][3] = q3;
+                if (r >= WIN - 1) {
+                    // horizontal 7-sum over lanes: 4 + 2 + 1
+                    double t, h0, h1, h2, h3;
+                    t = v0 + __shfl_down_sync(0xffffffffu, v0, 1);
+                    h0 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v0, 6);
+                    t = v1 + __shfl_down_sync(0xffffffffu, v1, 1);
+                    h1 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v1, 6);
+                    t = v2 + __shfl_down_sync(0xffffffffu, v2, 1);
+                    h2 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v2, 6);
+                    t = v3 + __shfl_down_sync(0xffffffffu, v3, 1);
+                    h3 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v3, 6);
+                    if (out_ok) acc += (double)window_score(h0, h1, h2, h3, inv_r);
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) partial[u] = acc;
+}
+
+// lane = slice (32 consecutive slices are 32 consecutive addresses).  Unit = (group of 32 slices, output column,
+// band of BAND output rows), one warp each; every thread owns one slice's column: seven loads per array and row.
+// partial[(slice) * units_per_slice + unit_in_slice] = sum of the window scores.
+__global__ void __launch_bounds__(256, 2)
+ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, SliceFamily f, const double* __restrict__ range,
+                      int n_cols, int n_bands, int64_t n_units, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (u >= n_units) return;
+    const int rb = (int)(u % n_bands);
+    const int oc = (int)((u / n_bands) % n_cols);                                         // output column
+    const int64_t g = u / ((int64_t)n_bands * n_cols);
+    const int64_t s = g * 32 + lane;
+    if (s >= f.S) return;
+    const int64_t base = slice_base(f, s);
+    const int64_t ih = f.H - 2 * PAD;
+    const int64_t oy0 = (int64_t)rb * BAND, oy1 = oy0 + BAND < ih ? oy0 + BAND : ih;
+    const double inv_r = 1.0 / range[s];
+    const float* pa = a + base + (int64_t)oc * f.sw;
+    const float* pb = b + base + (int64_t)oc * f.sw;
+    double ring[WIN][4];
+#pragma unroll
+    for (int j = 0; j < WIN; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0.0;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    double acc = 0.0;
+    const int64_t nrows = oy1 - oy0 + (WIN - 1);
+    for (int64_t r0 = 0; r0 < nrows; r0 += WIN) {
+#pragma unroll
+        for (int j = 0; j < WIN; j++) {
+            const int64_t r = r0 + j;
+            if (r < nrows) {
+                const int64_t off = (oy0 + r) * f.sh;
+                float xf[WIN], yf[WIN];
+#pragma unroll
+                for (int t = 0; t < WIN; t++) { xf[t] = __ldg(pa + off + t * f.sw); yf[t] = __ldg(pb + off + t * f.sw); }
+                asm volatile("" ::: "memory");           // keep the loads of later rows from being hoisted above (register pressure)
+                double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+#pragma unroll
+                for (int t = 0; t < WIN; t++) {
+                    const double x = (double)xf[t], y = (double)fmaxf(yf[t], 0.f);
+                    h0 += x; h1 += y; h2 += fma(x, x, y * y); h3 = fma(x, y, h3);
+                }
+                v0 += h0 - ring[j][0]; v1 += h1 - ring[j][1]; v2 += h2 - ring[j][2]; v3 += h3 - ring[j][3];
+                ring[j][0] = h0; ring[j][1] = h1; ring[j][2] = h2; ring[j][3] = h3;
+                if (r >= WIN - 1) acc += (double)window_score(v0, v1, v2, v3, inv_r);
+            }
+        }
+    }
+    partial[s * ((int64_t)n_cols * n_bands) + (int64_t)oc * n_bands + rb] = acc;
+}
+
+}  // namespace stream
 
 // out[fam] = sum(partial[begin..end)) * scale, one CTA per family
 __global__ void __launch_bounds__(256) ssim_final_kernel(const double* __restrict__ partial, const int64_t* __restrict__ bounds,
@@ -391,11 +494,70 @@ static int slice_ranges(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamil
     return NDMPS_OK;
 }
 
+// ---- streaming path: which kernel serves a family, how many partials it writes, launch ------------------
+static inline bool slices_contiguous(const SliceFamily& f) { return (f.nT > 1 && f.s_t == 1) || (f.nT == 1 && f.s_axis == 1); }
+static inline int stream_kind(const ndmps_ctx* ctx, const SliceFamily& f, const float*) {
+    if (ctx->opt_ssim_exact || f.win != 7) return 0;
+    if (f.sw == 1) return 1;                          // lane = column
+    if (slices_contiguous(f)) return 2;               // lane = slice
+    return 0;
+}
+static inline int stream_kind(const ndmps_ctx*, const SliceFamily&, const double*) { return 0; }
+
+struct StreamPlan { int kind = 0, n_a = 0, n_bands = 0; int64_t n_units = 0, n_partials = 0, per_slice = 0; };
+
+static StreamPlan stream_plan(int kind, const SliceFamily& f) {
+    StreamPlan p;
+    p.kind = kind;
+    const int64_t ih = f.H - 6, iw = f.W - 6;
+    p.n_bands = (int)((ih + stream::BAND - 1) / stream::BAND);
+    if (kind == 1) {
+        p.n_a = (int)((iw + stream::STRIP - 1) / stream::STRIP);                 // strips
+        p.per_slice = (int64_t)p.n_a * p.n_bands;
+        p.n_units = f.S * p.per_slice;
+        p.n_partials = p.n_units;
+    } else {
+        p.n_a = (int)iw;                                                          // output columns
+        p.per_slice = (int64_t)p.n_a * p.n_bands;
+        p.n_units = ((f.S + 31) / 32) * p.per_slice;
+        p.n_partials = f.S * p.per_slice;
+    }
+    return p;
+}
+
+static int launch_stream(ndmps_ctx* ctx, const float* a, const float* b, const SliceFamily& f, const StreamPlan& p, const double* range,
+                         double* partial) {
+    const unsigned grid = (unsigned)((p.n_units + 7) / 8);
+    if (p.kind == 1) stream::ssim_col_kernel<<<grid, 256, 0, ctx->stream>>>(a, b, f, range, p.n_a, p.n_bands, p.n_units, partial);
+    else stream::ssim_slice_kernel_f32<<<grid, 256, 0, ctx->stream>>>(a, b, f, range, p.n_a, p.n_bands, p.n_units, partial);
+    NDMPS_LAUNCH_CHECK(ctx);
+    return NDMPS_OK;
+}
+static int launch_stream(ndmps_ctx*, const double*, const double*, const SliceFamily&, const StreamPlan&, const double*, double*) {
+    return NDMPS_ERR_INVALID;                          // never selected for float64 inputs
+}
+
 template <class T>
 static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const SliceFamily& f, double* scores_host) {
     NDMPS_TRY(ensure_pinned(ctx, (size_t)f.S + 64));
     int pad = (f.win - 1) / 2;
     int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
+    if (const int kind = stream_kind(ctx, f, a)) {
+        const StreamPlan p = stream_plan(kind, f);
+        NDMPS_REQUIRE(p.n_units < (int64_t(1) << 33) && p.per_slice < (int64_t(1) << 31), "ssim: too many units");
+        double *range = nullptr, *partial = nullptr, *scores = nullptr;
+        NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &range));
+        NDMPS_TRY(ctx->ws.get<double>((size_t)p.n_partials, &partial));
+        NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &scores));
+        NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, kind == 2, range));
+        NDMPS_TRY(launch_stream(ctx, a, b, f, p, range, partial));
+        ssim_slice_kernel<<<(unsigned)f.S, 128, 0, ctx->stream>>>(partial, (int)p.per_slice, 1.0 / ((double)ih * (double)iw), scores);
+        NDMPS_LAUNCH_CHECK(ctx);
+        NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, scores, (size_t)f.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_CUDA_TRY(stream_wait(ctx));
+        memcpy(scores_host, ctx->pinned, (size_t)f.S * sizeof(double));
+        return NDMPS_OK;
+    }
     int ty = (int)((ih + TILE_H - 1) / TILE_H), tx = (int)((iw + TILE_W - 1) / TILE_W);
     int64_t nt = f.S * ty * tx;
     NDMPS_REQUIRE(nt < (int64_t(1) << 31), "ssim: too many tiles");
@@ -421,11 +583,23 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
     double scale_h[3] = {0, 0, 0};
     int tiles_y[3], tiles_x[3];
     bool batched[3];
+    StreamPlan splan[3];
     int64_t total_tiles = 0, total_slices = 0;
     for (int k = 0; k < nfam; k++) {
         const SliceFamily& f = fams[k];
         int pad = (f.win - 1) / 2;
         int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
+        if (const int kind = stream_kind(ctx, f, a)) {      // float32, window 7: streaming kernel, partials = its units
+            splan[k] = stream_plan(kind, f);
+            batched[k] = kind == 2;
+            tiles_y[k] = tiles_x[k] = 0;
+            bounds_h[k] = total_tiles;
+            total_tiles += splan[k].n_partials;
+            bounds_h[k + 1] = total_tiles;
+            scale_h[k] = 1.0 / ((double)f.S * (double)ih * (double)iw);
+            total_slices += f.S;
+            continue;
+        }
         // consecutive slice indices are consecutive addresses: frames (4-D) or the last axis (3-D)
         batched[k] = f.win == 7 && f.S >= 8 && ((f.nT > 1 && f.s_t == 1) || (f.nT == 1 && f.s_axis == 1));
         const int th = batched[k] ? BT_H : TILE_H, tw = batched[k] ? BT_W : TILE_W;
@@ -452,18 +626,15 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
     for (int k = 0; k < nfam; k++) {
         const SliceFamily& f = fams[k];
         int64_t nt = bounds_h[k + 1] - bounds_h[k];
-        if (batched[k]) {
+        if (splan[k].kind) {
+            NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, splan[k].kind == 2, range + slice_off));
+            NDMPS_TRY(launch_stream(ctx, a, b, f, splan[k], range + slice_off, partial + bounds_h[k]));
+        } else if (batched[k]) {
             const size_t bsm = (size_t)2 * (BT_H + f.win - 1) * (BT_W + f.win - 1) * BT_SLICES * sizeof(T);
+            NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7>, ctx->device, 112 * 1024));
             NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, true, range + slice_off));
-            if (ssim_fast(ctx, a)) {
-                NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7, float>, ctx->device, 112 * 1024));
-                ssim_tile_batched_kernel<T, 7, float><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k],
-                                                                                            tiles_x[k], partial + bounds_h[k]);
-            } else {
-                NDMPS_TRY(raise_dynamic_smem((const void*)ssim_tile_batched_kernel<T, 7, double>, ctx->device, 112 * 1024));
-                ssim_tile_batched_kernel<T, 7, double><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k],
-                                                                                             tiles_x[k], partial + bounds_h[k]);
-            }
+            ssim_tile_batched_kernel<T, 7><<<(unsigned)nt, 256, bsm, ctx->stream>>>(a, b, f, range + slice_off, tiles_y[k], tiles_x[k],
+                                                                                 partial + bounds_h[k]);
             NDMPS_LAUNCH_CHECK(ctx);
         } else {
             NDMPS_TRY(slice_ranges<T>(ctx, a, b, f, false, range + slice_off));

@@ -251,8 +251,9 @@ def ssim_arithmetic(exact):
         ctx.set_option("ssim_exact", 0)
 
 
-# float64 arithmetic agrees with the oracle to rounding; the float32 fast path to ~1e-6 per slice (north-star bar: 1e-4)
-SSIM_TOL = {True: 1e-10, False: 5e-5}
+# float64 arithmetic agrees with the oracle to rounding; the streaming kernels for float32 inputs (float64 window sums,
+# float32 formula) to ~1e-7 (north-star bar: 1e-4)
+SSIM_TOL = {True: 1e-10, False: 1e-6}
 
 
 @pytest.mark.parametrize("shape", [(16, 16), (40, 70), (7, 9), (5, 30), (6, 31), (256, 256), (33, 65), (70, 100), (39, 38)])
@@ -287,8 +288,8 @@ def test_ssim_4d(ops, shape, exact):
 
 
 def test_ssim_fast_path_offsets_and_scales(ops):
-    """The float32 arithmetic works on (x - first pixel) / range per tile: large offsets, tiny and huge scales and a
-    steep edge inside a flat tile must not cost more than the documented 5e-6."""
+    """The streaming kernels sum in float64 and evaluate the formula in float32 on range-normalised moments: large
+    offsets, tiny and huge scales and a steep edge next to flat texture must stay within the documented 1e-6."""
     rng = np.random.default_rng(11)
     base = rng.random((96, 80))
     noisy = base + 0.03 * rng.standard_normal(base.shape)
@@ -298,7 +299,7 @@ def test_ssim_fast_path_offsets_and_scales(ops):
                      (edge, edge + 0.02 * rng.standard_normal(edge.shape))):
         a, b = a64.astype(np.float32), b64.astype(np.float32)
         want = OM.compute_ssim_2d(a.astype(np.float64), b.astype(np.float64))
-        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=5e-5)
+        assert ops.ssim(dev(a), dev(b)) == pytest.approx(want, abs=1e-6)
 
 
 # ---- contractions ------------------------------------------------------------------------------------------
