@@ -144,9 +144,13 @@ struct ndmps_ctx {
     int64_t opt_tc = 1;             // tcgen05 contractions on bf16x3 split planes for float32 payloads of a capped sweep / the reconstruction (0: off)
     int64_t opt_tc_chunk = 0;       // k-tiles (64 columns each) between drains of the tcgen05 Gram accumulator into float64 (0: 4)
     int64_t opt_gemm_out_t = 0;     // test hook: ndmps_gemm writes C transposed (n x m) through the tcgen05 epilogue
-    // planes of the unfolding the tcgen05 Gram split last (workspace memory: valid until the next ws.reset); the
-    // projection of the same sweep step reuses them instead of splitting the unfolding again
-    struct { const void* src = nullptr; int64_t rows = 0, cols = 0, ld = 0; void* planes = nullptr; int64_t ldp = 0, pstride = 0; uint64_t gen = 0; } tc_planes;
+    // int8 digit planes of the unfolding the tcgen05 Gram sliced last (workspace memory: valid until the next ws.reset);
+    // the projection of the same sweep step multiplies the same digits.  exact_host: the device-side "use the FP64 pipe"
+    // flag once it has been copied to the host beside the eigenvalues (-1: not yet known)
+    struct {
+        const void* src = nullptr; int64_t rows = 0, cols = 0, ld = 0; void* digits = nullptr; int64_t ldp = 0, pstride = 0;
+        const int* sc = nullptr; const int* use_exact = nullptr; uint64_t gen = 0; int exact_host = -1;
+    } tc_digits;
     bool tc_sweep = false;          // set by the sweep while the tcgen05 Gram / projection are admissible (float32, bond cap)
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_gemm_path = 0;      // 0: FP64 tensor pipe for large row-major products, 2: SIMT only
@@ -221,6 +225,8 @@ int gemm(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
 int gram(ndmps_ctx* ctx, const void* m, int64_t rows, int64_t cols, int64_t ld, int dtype, int side, double* g_dev);
 // tcgen05 paths (tc_gemm.cu); *done = false when the shape is not eligible
 int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t ld, int dtype, double* g_dev, bool* done);
+int proj_tc_digits(ndmps_ctx* ctx, const void* mat, int64_t D, int64_t C, int64_t ld, const double* P, int64_t r, void* T, int dtype_t,
+                   int64_t ldt, bool* done);
 int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const void* a, int dtype_a, int64_t a_rs, int64_t a_cs,
             const void* b, int dtype_b, int64_t b_rs, int64_t b_cs, void* c, int dtype_c, int64_t ldc, bool out_t, bool* done);
 // tol_override > 0 loosens the relative off-diagonal threshold (float32 payloads do not need 1e-15)

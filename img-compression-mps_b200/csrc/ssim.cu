@@ -317,25 +317,50 @@ ssim_tile_batched_kernel(const T* __restrict__ a, const T* __restrict__ b, Slice
 namespace stream {
 
 constexpr int WIN = 7, PAD = 3, NP = 49;
-constexpr int STRIP = 32 - (WIN - 1);          // output columns per warp of the column kernel
-constexpr int BAND = 64;                        // output rows per unit
+constexpr int STRIP = 128 - (WIN - 1);         // output columns per warp of the column kernel (four columns per lane)
+constexpr int BAND = 32;                        // output rows per unit (more, smaller units: the float64 pipe is the bound, whole waves matter)
 
 // SSIM of one window from its float64 sums (x, y, xx + yy, xy); inv_r = 1 / data range of the slice
 __device__ __forceinline__ float window_score(double sx, double sy, double sq, double sxy, double inv_r) {
-    constexpr double inv_np = 1.0 / NP, cov_norm = (double)NP / (NP - 1);
+    constexpr double inv_np = 1.0 / NP;
+    constexpr float cov_norm = (float)NP / (NP - 1);
     const double ux = sx * inv_np, uy = sy * inv_np;
-    const double vsum = cov_norm * (sq * inv_np - ux * ux - uy * uy);      // vx + vy, exact cancellation
-    const double vxy = cov_norm * (sxy * inv_np - ux * uy);
-    // range-normalised moments: C1 = 1e-4, C2 = 9e-4 are constants; the formula itself in float32
-    const float mx = (float)(ux * inv_r), my = (float)(uy * inv_r);
-    const float vs = (float)(vsum * inv_r * inv_r), vc = (float)(vxy * inv_r * inv_r);
+    const double vsum = fma(-uy, uy, fma(-ux, ux, sq * inv_np));           // (vx + vy) / cov_norm: the cancellation happens in float64
+    const double vxy = fma(-ux, uy, sxy * inv_np);
+    // range-normalised moments: C1 = 1e-4, C2 = 9e-4 are constants; everything after the cancellation in float32
+    const float fr = (float)inv_r, fr2 = cov_norm * fr * fr;
+    const float mx = (float)ux * fr, my = (float)uy * fr;
+    const float vs = (float)vsum * fr2, vc = (float)vxy * fr2;
     const float num = (2.f * mx * my + 1e-4f) * (2.f * vc + 9e-4f);
     const float den = (mx * mx + my * my + 1e-4f) * (vs + 9e-4f);
     return num / den;
 }
 
-// lane = column (f.sw == 1).  Unit = (slice, strip of STRIP output columns, band of BAND output rows), one warp each.
-// partial[unit] = sum of the window scores of the unit (float64).
+// lane = four consecutive columns (f.sw == 1).  Unit = (slice, strip of STRIP output columns, band of BAND output rows),
+// one warp each: a row of the strip is one 16-byte load per lane and array.  Per row the column sums of the 7-row window
+// slide (the row leaving the window is read again - it is still in L1/L2 - so no register ring is needed), then the
+// seven-column window sums of a thread's four outputs come from its own four column sums plus six from the next two
+// lanes (24 shuffles per quantity set instead of 4 per output).  partial[unit] = sum of the unit's window scores.
+struct Quad { double q[4]; };     // x, y, xx + yy, xy of one column
+
+__device__ __forceinline__ void quad_add(Quad& v, float xf, float yf, double sign) {
+    const double x = (double)xf, y = (double)fmaxf(yf, 0.f);
+    v.q[0] = fma(sign, x, v.q[0]);
+    v.q[1] = fma(sign, y, v.q[1]);
+    v.q[2] = fma(sign, fma(x, x, y * y), v.q[2]);
+    v.q[3] = fma(sign * x, y, v.q[3]);
+}
+
+__device__ __forceinline__ float4 load4(const float* p, int64_t col, int64_t W, bool vec) {
+    if (vec && col + 4 <= W) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < W) v.x = __ldg(p);
+    if (col + 1 < W) v.y = __ldg(p + 1);
+    if (col + 2 < W) v.z = __ldg(p + 2);
+    if (col + 3 < W) v.w = __ldg(p + 3);
+    return v;
+}
+
 __global__ void __launch_bounds__(256, 2)
 ssim_col_kernel(const float* __restrict__ a, const float* __restrict__ b, SliceFamily f, const double* __restrict__ range,
                 int n_strips, int n_bands, int64_t n_units, double* __restrict__ partial) {
@@ -348,51 +373,48 @@ ssim_col_kernel(const float* __restrict__ a, const float* __restrict__ b, SliceF
     const int64_t base = slice_base(f, s);
     const int64_t ih = f.H - 2 * PAD, iw = f.W - 2 * PAD;
     const int64_t oy0 = (int64_t)rb * BAND, oy1 = oy0 + BAND < ih ? oy0 + BAND : ih;     // output rows [oy0, oy1)
-    const int64_t col = (int64_t)cs * STRIP + lane;                                       // input column of this lane
-    const bool col_ok = col < f.W;
-    const bool out_ok = lane < STRIP && col < iw;
+    const int64_t col = (int64_t)cs * STRIP + 4 * lane;                                   // first of this lane's four input columns
     const double inv_r = 1.0 / range[s];
     const float* pa = a + base + col;
     const float* pb = b + base + col;
-    double ring[WIN][4];
+    // 16-byte loads need 16-byte aligned rows
+    const bool vec = ((f.sh & 3) == 0) && (((base + col) & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    Quad v[4];
 #pragma unroll
-    for (int j = 0; j < WIN; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0.0;
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    for (int k = 0; k < 4; k++) v[k].q[0] = v[k].q[1] = v[k].q[2] = v[k].q[3] = 0.0;
     double acc = 0.0;
     const int64_t nrows = oy1 - oy0 + (WIN - 1);
-    for (int64_t r0 = 0; r0 < nrows; r0 += WIN) {
-        // the fourteen loads of a seven-row group are issued together (memory-level parallelism), then consumed
-        float xf[WIN], yf[WIN];
-#pragma unroll
-        for (int j = 0; j < WIN; j++) {
-            const bool ok = col_ok && r0 + j < nrows;
-            const int64_t off = (oy0 + r0 + j) * f.sh;
-            xf[j] = ok ? __ldg(pa + off) : 0.f;
-            yf[j] = ok ? __ldg(pb + off) : 0.f;
+    float4 xa = load4(pa + oy0 * f.sh, col, f.W, vec), xb = load4(pb + oy0 * f.sh, col, f.W, vec);
+    for (int64_t r = 0; r < nrows; r++) {
+        // prefetch the next incoming row and this row's outgoing one before consuming the current
+        float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na, oa = na, ob = na;
+        if (r + 1 < nrows) { na = load4(pa + (oy0 + r + 1) * f.sh, col, f.W, vec); nb = load4(pb + (oy0 + r + 1) * f.sh, col, f.W, vec); }
+        const bool drop = r >= WIN;
+        if (drop) { oa = load4(pa + (oy0 + r - WIN) * f.sh, col, f.W, vec); ob = load4(pb + (oy0 + r - WIN) * f.sh, col, f.W, vec); }
+        quad_add(v[0], xa.x, xb.x, 1.0); quad_add(v[1], xa.y, xb.y, 1.0); quad_add(v[2], xa.z, xb.z, 1.0); quad_add(v[3], xa.w, xb.w, 1.0);
+        if (drop) {
+            quad_add(v[0], oa.x, ob.x, -1.0); quad_add(v[1], oa.y, ob.y, -1.0); quad_add(v[2], oa.z, ob.z, -1.0); quad_add(v[3], oa.w, ob.w, -1.0);
         }
+        if (r >= WIN - 1) {
+            double hs[4][4];                                  // [output column][quantity]
 #pragma unroll
-        for (int j = 0; j < WIN; j++) {
-            const int64_t r = r0 + j;
-            if (r < nrows) {
-                const double x = (double)xf[j], y = (double)fmaxf(yf[j], 0.f);
-                const double q2 = fma(x, x, y * y), q3 = x * y;
-                v0 += x - ring[j][0]; v1 += y - ring[j][1]; v2 += q2 - ring[j][2]; v3 += q3 - ring[j][3];
-                ring[j][0] = x; ring[j][1] = y; ring[j][2] = q2; ring[j][3] = q3;
-                if (r >= WIN - 1) {
-                    // horizontal 7-sum over lanes: 4 + 2 + 1
-                    double t, h0, h1, h2, h3;
-                    t = v0 + __shfl_down_sync(0xffffffffu, v0, 1);
-                    h0 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v0, 6);
-                    t = v1 + __shfl_down_sync(0xffffffffu, v1, 1);
-                    h1 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v1, 6);
-                    t = v2 + __shfl_down_sync(0xffffffffu, v2, 1);
-                    h2 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v2, 6);
-                    t = v3 + __shfl_down_sync(0xffffffffu, v3, 1);
-                    h3 = t + __shfl_down_sync(0xffffffffu, t, 2) + __shfl_down_sync(0xffffffffu, t, 4) + __shfl_down_sync(0xffffffffu, v3, 6);
-                    if (out_ok) acc += (double)window_score(h0, h1, h2, h3, inv_r);
-                }
+            for (int q = 0; q < 4; q++) {
+                // columns 4..7 from the next lane, 8..9 from the one after
+                const double c4 = __shfl_down_sync(0xffffffffu, v[0].q[q], 1), c5 = __shfl_down_sync(0xffffffffu, v[1].q[q], 1);
+                const double c6 = __shfl_down_sync(0xffffffffu, v[2].q[q], 1), c7 = __shfl_down_sync(0xffffffffu, v[3].q[q], 1);
+                const double c8 = __shfl_down_sync(0xffffffffu, v[0].q[q], 2), c9 = __shfl_down_sync(0xffffffffu, v[1].q[q], 2);
+                const double h0 = ((v[0].q[q] + v[1].q[q]) + (v[2].q[q] + v[3].q[q])) + ((c4 + c5) + c6);
+                const double h1 = h0 - v[0].q[q] + c7, h2 = h1 - v[1].q[q] + c8, h3 = h2 - v[2].q[q] + c9;
+                hs[0][q] = h0; hs[1][q] = h1; hs[2][q] = h2; hs[3][q] = h3;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t oc = col + k;                   // output column (window starts here)
+                if (4 * lane + k < STRIP && oc < iw) acc += (double)window_score(hs[k][0], hs[k][1], hs[k][2], hs[k][3], inv_r);
             }
         }
+        xa = na; xb = nb;
     }
     acc = warp_sum(acc);
     if (lane == 0) partial[u] = acc;
@@ -400,10 +422,11 @@ ssim_col_kernel(const float* __restrict__ a, const float* __restrict__ b, SliceF
 
 // lane = slice (32 consecutive slices are 32 consecutive addresses).  Unit = (group of 32 slices, output column,
 // band of BAND output rows), one warp each; every thread owns one slice's column: seven loads per array and row.
-// partial[(slice) * units_per_slice + unit_in_slice] = sum of the window scores.
+// per_slice: partial[slice * units_per_slice + unit_in_slice] = sum of the window scores (for ssim_slices);
+// otherwise partial[unit] = the same summed over the unit's 32 slices.
 __global__ void __launch_bounds__(256, 2)
 ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, SliceFamily f, const double* __restrict__ range,
-                      int n_cols, int n_bands, int64_t n_units, double* __restrict__ partial) {
+                      int n_cols, int n_bands, int64_t n_units, int per_slice, double* __restrict__ partial) {
     const int lane = threadIdx.x & 31;
     const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (u >= n_units) return;
@@ -411,11 +434,11 @@ ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, 
     const int oc = (int)((u / n_bands) % n_cols);                                         // output column
     const int64_t g = u / ((int64_t)n_bands * n_cols);
     const int64_t s = g * 32 + lane;
-    if (s >= f.S) return;
-    const int64_t base = slice_base(f, s);
+    const bool live = s < f.S;                             // dead lanes of the last slice group only join the final reduction
+    const int64_t base = live ? slice_base(f, s) : 0;
     const int64_t ih = f.H - 2 * PAD;
     const int64_t oy0 = (int64_t)rb * BAND, oy1 = oy0 + BAND < ih ? oy0 + BAND : ih;
-    const double inv_r = 1.0 / range[s];
+    const double inv_r = live ? 1.0 / range[s] : 0.0;
     const float* pa = a + base + (int64_t)oc * f.sw;
     const float* pb = b + base + (int64_t)oc * f.sw;
     double ring[WIN][4];
@@ -423,7 +446,7 @@ ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, 
     for (int j = 0; j < WIN; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0.0;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
     double acc = 0.0;
-    const int64_t nrows = oy1 - oy0 + (WIN - 1);
+    const int64_t nrows = live ? oy1 - oy0 + (WIN - 1) : 0;
     for (int64_t r0 = 0; r0 < nrows; r0 += WIN) {
 #pragma unroll
         for (int j = 0; j < WIN; j++) {
@@ -446,7 +469,12 @@ ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, 
             }
         }
     }
-    partial[s * ((int64_t)n_cols * n_bands) + (int64_t)oc * n_bands + rb] = acc;
+    if (per_slice) {
+        if (live) partial[s * ((int64_t)n_cols * n_bands) + (int64_t)oc * n_bands + rb] = acc;
+    } else {                                               // family total: the 32 slices of the unit summed in lane order
+        acc = warp_sum(acc);
+        if (lane == 0) partial[u] = acc;
+    }
 }
 
 }  // namespace stream
@@ -504,11 +532,12 @@ static inline int stream_kind(const ndmps_ctx* ctx, const SliceFamily& f, const 
 }
 static inline int stream_kind(const ndmps_ctx*, const SliceFamily&, const double*) { return 0; }
 
-struct StreamPlan { int kind = 0, n_a = 0, n_bands = 0; int64_t n_units = 0, n_partials = 0, per_slice = 0; };
+struct StreamPlan { int kind = 0, n_a = 0, n_bands = 0, by_slice = 0; int64_t n_units = 0, n_partials = 0, per_slice = 0; };
 
-static StreamPlan stream_plan(int kind, const SliceFamily& f) {
+static StreamPlan stream_plan(int kind, const SliceFamily& f, bool by_slice) {
     StreamPlan p;
     p.kind = kind;
+    p.by_slice = by_slice ? 1 : 0;
     const int64_t ih = f.H - 6, iw = f.W - 6;
     p.n_bands = (int)((ih + stream::BAND - 1) / stream::BAND);
     if (kind == 1) {
@@ -520,7 +549,7 @@ static StreamPlan stream_plan(int kind, const SliceFamily& f) {
         p.n_a = (int)iw;                                                          // output columns
         p.per_slice = (int64_t)p.n_a * p.n_bands;
         p.n_units = ((f.S + 31) / 32) * p.per_slice;
-        p.n_partials = f.S * p.per_slice;
+        p.n_partials = by_slice ? f.S * p.per_slice : p.n_units;
     }
     return p;
 }
@@ -529,7 +558,7 @@ static int launch_stream(ndmps_ctx* ctx, const float* a, const float* b, const S
                          double* partial) {
     const unsigned grid = (unsigned)((p.n_units + 7) / 8);
     if (p.kind == 1) stream::ssim_col_kernel<<<grid, 256, 0, ctx->stream>>>(a, b, f, range, p.n_a, p.n_bands, p.n_units, partial);
-    else stream::ssim_slice_kernel_f32<<<grid, 256, 0, ctx->stream>>>(a, b, f, range, p.n_a, p.n_bands, p.n_units, partial);
+    else stream::ssim_slice_kernel_f32<<<grid, 256, 0, ctx->stream>>>(a, b, f, range, p.n_a, p.n_bands, p.n_units, p.by_slice, partial);
     NDMPS_LAUNCH_CHECK(ctx);
     return NDMPS_OK;
 }
@@ -543,7 +572,7 @@ static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const Slice
     int pad = (f.win - 1) / 2;
     int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
     if (const int kind = stream_kind(ctx, f, a)) {
-        const StreamPlan p = stream_plan(kind, f);
+        const StreamPlan p = stream_plan(kind, f, true);
         NDMPS_REQUIRE(p.n_units < (int64_t(1) << 33) && p.per_slice < (int64_t(1) << 31), "ssim: too many units");
         double *range = nullptr, *partial = nullptr, *scores = nullptr;
         NDMPS_TRY(ctx->ws.get<double>((size_t)f.S, &range));
@@ -590,7 +619,7 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         int pad = (f.win - 1) / 2;
         int64_t ih = f.H - 2 * pad, iw = f.W - 2 * pad;
         if (const int kind = stream_kind(ctx, f, a)) {      // float32, window 7: streaming kernel, partials = its units
-            splan[k] = stream_plan(kind, f);
+            splan[k] = stream_plan(kind, f, false);
             batched[k] = kind == 2;
             tiles_y[k] = tiles_x[k] = 0;
             bounds_h[k] = total_tiles;

@@ -485,6 +485,153 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int ntc, int m, int64_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Projection T = P^T M on the digits the Gram already made (no second pass over the unfolding):
+//     T[i, c] = sum_k P[k, i] M[k, c] = 2^tc_i sum_k b(k, i) y(k, c),   b = P[k, i] 2^(sc_k - tc_i),  y = M 2^-sc_k
+// y are the Gram's digit planes ([digit][k][c]: the MN-major A operand, 128-byte swizzle); b is sliced the same way
+// per output row i (K-major B operand, [digit][i][k]).  Fifteen digit products into five int32 accumulators
+// (tile: 128 columns c x 64 rows i), one chain over all of k (k <= 4096: |ACC_4| <= 5 * 4096 * 4096), exact.
+// ---------------------------------------------------------------------------------------------
+struct ProjI8Smem {
+    static constexpr int STAGES = 3;
+    static constexpr int A_PLANE = I8_BK * TILE;                 // 64 k-rows x 128 bytes of c = 8 KB
+    static constexpr int A_BYTES = I8_PLANES * A_PLANE;
+    static constexpr int STAGE_BYTES = A_BYTES + I8_PLANES * I8_BOX_BYTES;   // + 64 rows i x 64 digits of k per plane = 60 KB
+    static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;
+};
+
+// bdig[p][i][k] = digit p of P[k, i] 2^(sc_k - tc_i); tc[i] chosen so that the scaled column lies in (-1/2, 1/2).
+// One CTA per output row i (column of P).  P: D x r row-major (float64).
+__global__ void __launch_bounds__(256)
+split_i8_proj_kernel(const double* __restrict__ P, int64_t D, int64_t r, const int* __restrict__ sc, int8_t* __restrict__ bdig,
+                     int64_t ldk, int64_t plane_stride, int* __restrict__ tc_out) {
+    __shared__ double red[8];
+    __shared__ int s_tc;
+    const int64_t i = blockIdx.x;
+    double mx = 0.0;
+    for (int64_t k = threadIdx.x; k < D; k += 256) mx = fmax(mx, fabs(ldexp(P[k * r + i], sc[k])));
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) mx = fmax(mx, red[w]);
+        int e = 0;
+        if (mx > 0.0 && mx < INFINITY) frexp(mx, &e);
+        s_tc = e + 1;
+        tc_out[i] = e + 1;
+    }
+    __syncthreads();
+    const int tcv = s_tc;
+    for (int64_t k = threadIdx.x; k < ldk; k += 256) {
+        double t = k < D ? ldexp(P[k * r + i], sc[k] - tcv + 7) : 0.0;      // b * 128
+#pragma unroll
+        for (int p = 0; p < I8_PLANES; p++) {
+            const double a = rint(t);
+            bdig[p * plane_stride + i * ldk + k] = (int8_t)(int)a;
+            t = (t - a) * 128.0;
+        }
+    }
+}
+
+// TMEM columns: accumulator s at [64 s, 64 s + 64).  T: r x C row-major (ldt), written transposed from the accumulator.
+template <class TT>
+__global__ void __launch_bounds__(THREADS, 1)
+proj_i8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_b, int64_t C, int64_t r, int64_t D,
+               const int* __restrict__ tc, TT* __restrict__ T, int64_t ldt) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + ProjI8Smem::BARRIER_OFF);
+    uint64_t* empty = full + ProjI8Smem::STAGES;
+    uint64_t* acc_full = empty + ProjI8Smem::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c0 = (int64_t)blockIdx.x * TILE, i0 = (int64_t)blockIdx.y * I8_TN;
+    const int nk = (int)((D + I8_BK - 1) / I8_BK);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_y);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < ProjI8Smem::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % ProjI8Smem::STAGES;
+            mbar_wait(&empty[s], ((kt / ProjI8Smem::STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full[s], ProjI8Smem::STAGE_BYTES);
+            uint8_t* st = smem + s * ProjI8Smem::STAGE_BYTES;
+            const int k0 = kt * I8_BK;
+#pragma unroll
+            for (int p = 0; p < I8_PLANES; p++) {
+                tma_load_3d(st + p * ProjI8Smem::A_PLANE, &map_y, &full[s], (int)c0, k0, p);                       // 64 k-rows x 128 c
+                tma_load_3d(st + ProjI8Smem::A_BYTES + p * I8_BOX_BYTES, &map_b, &full[s], k0, (int)i0, p);        // 64 rows i x 64 k
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = instr_desc_i8(TILE, I8_TN) | (1u << 15);        // A is MN-major
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % ProjI8Smem::STAGES;
+            mbar_wait(&full[s], (kt / ProjI8Smem::STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * ProjI8Smem::STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
+#pragma unroll
+                for (int p = 0; p < I8_PLANES; p++) {
+#pragma unroll
+                    for (int q = 0; q < I8_PLANES; q++) {
+                        if (p + q >= I8_PLANES) continue;
+                        // A: 32 k-rows of 128 bytes per k-step (4096 B), 8-row groups 1024 B apart, one 128-byte atom along c
+                        const uint64_t da = smem_desc(st + p * ProjI8Smem::A_PLANE + ks * 4096, 8192, 1024);
+                        const uint64_t db = smem_desc_sw64(st + ProjI8Smem::A_BYTES + q * I8_BOX_BYTES + ks * 32);
+                        umma_i8(tmem_base + (uint32_t)((p + q) * I8_TN), da, db, idesc, !(kt == 0 && ks == 0 && p == 0));
+                    }
+                }
+            }
+            umma_commit(&empty[s]);
+            if (kt == nk - 1) umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int q4 = warp & 3, half = (warp - 4) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 32);
+        double acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = 0.0;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < I8_PLANES; s++) {
+            const double w = s == 0 ? 0x1p-14 : (s == 1 ? 0x1p-21 : (s == 2 ? 0x1p-28 : (s == 3 ? 0x1p-35 : 0x1p-42)));
+            uint32_t v[32];
+            tmem_ld32(lane_base + (uint32_t)(s * I8_TN), v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = fma((double)(int)v[j], w, acc[j]);
+        }
+        const int64_t c = c0 + q4 * 32 + lane;
+        if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int64_t i = i0 + half * 32 + j;
+                if (i < r) T[i * ldt + c] = (TT)ldexp(acc[j], tc[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // G[i][j] = G[j][i] = sum over splits, in split order
 __global__ void __launch_bounds__(256)
 gram_i8_reduce_kernel(const double* __restrict__ partial, int m, int ntc, int ntiles, int splits, const int* __restrict__ use_exact,
@@ -801,10 +948,67 @@ int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t
     dim3 rgrid(8, (unsigned)ntiles);
     gram_i8_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partial, m, ntc, ntiles, (int)splits, use_exact, g_dev);
     NDMPS_LAUNCH_CHECK(ctx);
+    // the projection of this sweep step can reuse the digits (proj_tc_digits below)
+    ctx->tc_digits.src = mat; ctx->tc_digits.rows = rows; ctx->tc_digits.cols = cols; ctx->tc_digits.ld = ld;
+    ctx->tc_digits.digits = digits; ctx->tc_digits.ldp = ldp; ctx->tc_digits.pstride = pstride; ctx->tc_digits.sc = sc;
+    ctx->tc_digits.use_exact = use_exact; ctx->tc_digits.gen = ctx->ws.generation; ctx->tc_digits.exact_host = -1;
     // 4. the exact kernel: runs only when the flag is set
     bool exact_ok = false;
     NDMPS_TRY(gram_dmma(ctx, mat, rows, cols, ld, dtype, g_dev, &exact_ok, use_exact));
     NDMPS_REQUIRE(exact_ok, "gram_tc: the FP64-pipe fallback declined a %lld x %lld unfolding", (long long)rows, (long long)cols);
+    *done = true;
+    return NDMPS_OK;
+}
+
+// T (r x C, row-major ldt) = P^T M on the digit planes gram_tc made of M (rows D x cols C), P: D x r float64 row-major.
+// *done = false: no digits for this unfolding (the Gram fell back to the FP64 pipe, or another matrix) - the caller
+// takes the bf16x3 route.  The exactness flag must have reached the host (ttsvd copies it beside the eigenvalues).
+int proj_tc_digits(ndmps_ctx* ctx, const void* mat, int64_t D, int64_t C, int64_t ld, const double* P, int64_t r, void* T, int dtype_t,
+                   int64_t ldt, bool* done) {
+    using namespace tc;
+    *done = false;
+    const auto& dg = ctx->tc_digits;
+    if (!dg.digits || dg.gen != ctx->ws.generation || dg.src != mat || dg.rows != D || dg.cols != C || dg.ld != ld) return NDMPS_OK;
+    if (dg.exact_host != 0 || D > 4096 || r < 1 || C < TILE) return NDMPS_OK;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tc: cuTensorMapEncodeTiled is not available from the driver"); return NDMPS_ERR_CUDA; }
+    // digits of the scaled columns of P: [digit][i][k], k padded to 16
+    const int64_t ldk = (D + 15) & ~int64_t(15), bstride = r * ldk;
+    int8_t* bdig = nullptr;
+    int* tcs = nullptr;
+    NDMPS_TRY(ctx->ws.get<int8_t>((size_t)(I8_PLANES * bstride), &bdig));
+    NDMPS_TRY(ctx->ws.get<int>((size_t)r, &tcs));
+    split_i8_proj_kernel<<<(unsigned)r, 256, 0, ctx->stream>>>(P, D, r, dg.sc, bdig, ldk, bstride, tcs);
+    NDMPS_LAUNCH_CHECK(ctx);
+    CUtensorMap map_y, map_b;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)D, (cuuint64_t)I8_PLANES};
+        const cuuint64_t strides[2] = {(cuuint64_t)dg.ldp, (cuuint64_t)dg.pstride};
+        const cuuint32_t box[3] = {(cuuint32_t)TILE, (cuuint32_t)I8_BK, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = fn(&map_y, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, dg.digits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled (projection digits) failed (%d)", (int)rc); return NDMPS_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)r, (cuuint64_t)I8_PLANES};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)bstride};
+        const cuuint32_t box[3] = {(cuuint32_t)I8_BK, 64, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = fn(&map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, bdig, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled (projector digits) failed (%d)", (int)rc); return NDMPS_ERR_CUDA; }
+    }
+    dim3 grid((unsigned)((C + TILE - 1) / TILE), (unsigned)((r + I8_TN - 1) / I8_TN));
+    if (dtype_t == NDMPS_F32) {
+        NDMPS_TRY(raise_dynamic_smem((const void*)proj_i8_kernel<float>, ctx->device, ProjI8Smem::TOTAL));
+        proj_i8_kernel<float><<<grid, THREADS, ProjI8Smem::TOTAL, ctx->stream>>>(map_y, map_b, C, r, D, tcs, (float*)T, ldt);
+    } else {
+        NDMPS_TRY(raise_dynamic_smem((const void*)proj_i8_kernel<double>, ctx->device, ProjI8Smem::TOTAL));
+        proj_i8_kernel<double><<<grid, THREADS, ProjI8Smem::TOTAL, ctx->stream>>>(map_y, map_b, C, r, D, tcs, (double*)T, ldt);
+    }
+    NDMPS_LAUNCH_CHECK(ctx);
+    ctx->tc_launches++;
     *done = true;
     return NDMPS_OK;
 }
@@ -839,10 +1043,7 @@ int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const
     // plane matrices as stored: K-major A planes are [m][k]; MN-major A planes are [k][m]; same for B with n
     __nv_bfloat16 *pa = nullptr, *pb = nullptr;
     int64_t lda = 0, sa = 0, ldb = 0, sb = 0;
-    const auto& pc = ctx->tc_planes;
-    if (a_mn && alpha == 1.0 && pc.planes && pc.gen == ctx->ws.generation && pc.src == a && pc.rows == k && pc.cols == m && pc.ld == a_cs && dtype_a == NDMPS_F32) {
-        pa = static_cast<__nv_bfloat16*>(pc.planes); lda = pc.ldp; sa = pc.pstride;     // split by the Gram of this sweep step
-    } else if (a_mn) NDMPS_TRY(tc_split(ctx, a, dtype_a, k, m, a_cs, false, alpha, &pa, &lda, &sa));
+    if (a_mn) NDMPS_TRY(tc_split(ctx, a, dtype_a, k, m, a_cs, false, alpha, &pa, &lda, &sa));
     else NDMPS_TRY(tc_split(ctx, a, dtype_a, m, k, a_rs, false, alpha, &pa, &lda, &sa));
     if (b_mn) NDMPS_TRY(tc_split(ctx, b, dtype_b, k, n, b_rs, false, 1.0, &pb, &ldb, &sb));
     else NDMPS_TRY(tc_split(ctx, b, dtype_b, n, k, b_cs, false, 1.0, &pb, &ldb, &sb));

@@ -188,11 +188,28 @@ static double renorm_factor(const double* s, int64_t n, int64_t keep, int power)
     return pow((k + l) / k, 1.0 / power);
 }
 
+// The tcgen05 Gram decides ON THE DEVICE whether its digits are exact enough (tc_gemm.cu); the projection needs that
+// answer on the host to pick its kernel.  It rides along with the eigenvalue readback every sweep step does anyway:
+// the 4-byte flag is copied into an unused slot of the pinned scratch before the same synchronisation.
+static int fetch_exact_flag(ndmps_ctx* ctx, size_t slot) {
+    auto& dg = ctx->tc_digits;
+    if (dg.use_exact == nullptr || dg.gen != ctx->ws.generation || dg.exact_host >= 0) return NDMPS_OK;
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned + slot, dg.use_exact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    dg.exact_host = -2;                                  // in flight
+    return NDMPS_OK;
+}
+static void note_exact_flag(ndmps_ctx* ctx, size_t slot) {
+    auto& dg = ctx->tc_digits;
+    if (dg.exact_host == -2) dg.exact_host = *reinterpret_cast<const int*>(ctx->pinned + slot) != 0 ? 1 : 0;
+}
+
 // copy n eigenvalues to the host, return sqrt(max(l, 0)) in sv (host vector)
 static int fetch_svals(ndmps_ctx* ctx, const double* evals_dev, int64_t n, std::vector<double>& sv) {
     NDMPS_TRY(ensure_pinned(ctx, (size_t)n + 64));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, evals_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(fetch_exact_flag(ctx, (size_t)n + 8));
     NDMPS_CUDA_TRY(stream_wait(ctx));
+    note_exact_flag(ctx, (size_t)n + 8);
     sv.resize((size_t)n);
     for (int64_t i = 0; i < n; i++) sv[i] = ctx->pinned[i] > 0.0 ? sqrt(ctx->pinned[i]) : 0.0;
     return NDMPS_OK;
@@ -230,7 +247,9 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     if (!done) return NDMPS_OK;
     NDMPS_TRY(ensure_pinned(ctx, (size_t)k + 64));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(fetch_exact_flag(ctx, (size_t)k + 8));
     NDMPS_CUDA_TRY(stream_wait(ctx));
+    note_exact_flag(ctx, (size_t)k + 8);
     const double* ev = ctx->pinned;
     const double trace = ev[k], rank_loss = ev[k + 1];
     double kept = 0.0;
@@ -390,8 +409,12 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
             {
                 StageScope sc(ctx, ST_PROJECT);
                 bool on_tc = false;
-                if (ctx->tc_sweep && C >= 2048)   // T^T = M^T P on tcgen05: the unfolding is the MN-major operand, T leaves transposed
-                    NDMPS_TRY(gemm_tc(ctx, C, r_out, D, 1.0, M, dtype, 1, C, P, NDMPS_F64, r_out, 1, T, dtype, C, true, &on_tc));
+                if (ctx->tc_sweep && C >= 2048) {
+                    // the digits the Gram of this step sliced, when it ran on the integer tensor cores (exact accumulation) ...
+                    NDMPS_TRY(proj_tc_digits(ctx, M, D, C, C, P, r_out, T, dtype, C, &on_tc));
+                    // ... else T^T = M^T P on bf16x3 planes: the unfolding is the MN-major operand, T leaves transposed
+                    if (!on_tc) NDMPS_TRY(gemm_tc(ctx, C, r_out, D, 1.0, M, dtype, 1, C, P, NDMPS_F64, r_out, 1, T, dtype, C, true, &on_tc));
+                }
                 if (!on_tc) {
                     // P^T made explicit (r x D, tiny) so the big product reads both operands along their rows
                     double* Pt = nullptr;

@@ -76,7 +76,12 @@ class VolumePipeline:
         # node) than cores they would starve each other, so they sleep on blocking events instead
         if blocking_sync is None:
             ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-            blocking_sync = self.workers * ranks_here > max(1, (os.cpu_count() or 1) - 1)
+            try:                                        # the cores this process may actually run on (cgroup / taskset aware)
+                usable = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                usable = os.cpu_count() or 1
+            # a spinning waiter per worker of every rank of the node, plus the ranks' main threads, must each find a core
+            blocking_sync = (self.workers + 1) * ranks_here > max(1, usable - 1)
         self.blocking_sync = bool(blocking_sync)
         self._ctx_lock = threading.Lock()
         self._contexts = []                             # the workers' native contexts (for launch counts / options)
