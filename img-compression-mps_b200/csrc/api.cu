@@ -298,6 +298,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "topk_big_ctas")) ctx->opt_topk_big_ctas = value;
     else if (!strcmp(name, "topk_passes")) ctx->opt_topk_passes = value;
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;
+    else if (!strcmp(name, "topk_rr_skip")) ctx->opt_topk_rr_skip = value;
     else if (!strcmp(name, "blocking_sync")) ctx->opt_blocking_sync = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;

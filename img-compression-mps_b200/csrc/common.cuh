@@ -168,6 +168,7 @@ struct ndmps_ctx {
     int64_t opt_topk_big_ctas = 0;        // CTAs per SM of the L2-streamed tridiagonalisation (0: occupancy, at most 3)
     int64_t opt_topk_passes = 0;          // bisection passes (0: 8, each divides the bracket by 129)
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
+    int64_t opt_topk_rr_skip = 1;         // pass an already diagonal Rayleigh-Ritz block through without the Jacobi solve
     int64_t opt_ssim_exact = 0;           // 1: float64 SSIM arithmetic for float32 inputs too (default: shifted / normalised float32)
     int64_t opt_blocking_sync = 0;        // host waits sleep on a blocking event instead of spinning (many host threads per core)
     int64_t opt_verbose = 0;
@@ -231,7 +232,9 @@ int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const
             const void* b, int dtype_b, int64_t b_rs, int64_t b_cs, void* c, int dtype_c, int64_t ldc, bool out_t, bool* done);
 // tol_override > 0 loosens the relative off-diagonal threshold (float32 payloads do not need 1e-15)
 int eigh(ndmps_ctx* ctx, double* a_dev, int64_t n, double* evals_dev, double* evecs_dev, double tol_override = 0.0);
-int eigh_small_async(ndmps_ctx* ctx, double* a_dev, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev);
+// diag_tol > 0: a matrix whose off-diagonal entries are all below diag_tol x max |diagonal| is taken as diagonal
+int eigh_small_async(ndmps_ctx* ctx, double* a_dev, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev,
+                     double diag_tol = 0.0);
 // leading k eigenpairs (eig_topk.cu); out_dev: k Ritz values, trace(G), rank-loss count
 int eigh_topk(ndmps_ctx* ctx, const double* g_dev, int64_t n, int64_t k, double* out_dev, double* evecs_dev, int64_t ldu, bool* done);
 // Cooperative (grid-barrier) kernels of several contexts may be in flight at once (batch.py).  Their

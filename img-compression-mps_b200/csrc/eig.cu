@@ -933,7 +933,7 @@ pivoted_cholesky_cluster_kernel(const double* __restrict__ G, int n, int rows_pe
 template <int NR>
 __global__ void __launch_bounds__(512)
 eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol2, double stop_rel, float quad_stop2,
-                  double* __restrict__ evals, double* __restrict__ evecs, int* __restrict__ info) {
+                  double diag_tol, double* __restrict__ evals, double* __restrict__ evecs, int* __restrict__ info) {
     extern __shared__ double S[];                    // n columns of stride ld = n + 2 (the pad spreads columns over banks)
     const int ld = n + 2;
     __shared__ int piv[128];                         // piv[k] = original index eliminated at step k = slot of L's column k
@@ -945,6 +945,40 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     __shared__ int s_prow;
     __shared__ double cnorm[128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    // ---- already diagonal?  (Rayleigh-Ritz block of converged Ritz vectors, eig_topk.cu): every off-diagonal entry
+    // below diag_tol x the largest diagonal entry -> eigenvalues are the diagonal, eigenvectors a permutation.  The
+    // caller checks the residuals of what comes out, so a block that only looks diagonal cannot slip through. ----
+    if (diag_tol > 0.0) {
+        double off = 0.0, dg = 0.0;
+        for (int i = tid; i < n * n; i += blockDim.x) {
+            const int c = i / n, r = i - c * n;
+            const double v = fabs(G[i]);
+            if (c == r) dg = fmax(dg, v); else off = fmax(off, v);
+        }
+        off = warp_max(off);
+        dg = warp_max(dg);
+        if (lane == 0) { red_val[warp] = off; lcol[warp] = dg; }
+        __syncthreads();
+        off = 0.0; dg = 0.0;
+        for (int w = 0; w < W; w++) { off = fmax(off, red_val[w]); dg = fmax(dg, lcol[w]); }
+        __syncthreads();
+        if (off <= diag_tol * dg) {                      // uniform over the CTA
+            for (int c = warp; c < n; c += W) {
+                const double mine = G[(size_t)c * n + c];
+                int cnt = 0;
+                for (int k = lane; k < n; k += 32) {
+                    const double o = G[(size_t)k * n + k];
+                    cnt += (o > mine || (o == mine && k < c)) ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (lane == 0) evals[cnt] = mine;
+                for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + cnt] = i == c ? 1.0 : 0.0;
+            }
+            if (tid == 0) { info[0] = 0; info[1] = n; }
+            return;
+        }
+    }
     for (int i = tid; i < n * n; i += blockDim.x) { const int c = i / n, r = i - c * n; S[(size_t)c * ld + r] = G[i]; }
     if (tid < n) dead[tid] = 0;
     __syncthreads();
@@ -1262,7 +1296,8 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
 // Single-CTA solver for 2 <= n <= 64, no host synchronisation: *info_dev points at {sweeps (negative:
 // not converged), rank} on the device.  quad_stop2 > 0: also stop after a sweep whose largest rotated
 // off-diagonal, squared and relative, was below it.
-int eigh_small_async(ndmps_ctx* ctx, double* a_in, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev) {
+int eigh_small_async(ndmps_ctx* ctx, double* a_in, int n, double* evals_dev, double* evecs_dev, float quad_stop2, int** info_dev,
+                     double diag_tol) {
     NDMPS_REQUIRE(n >= 2 && n <= 64, "eigh_small_async: n = %d outside 2..64", n);
     const int max_sweeps = (int)ctx->opt_jacobi_max_sweeps;
     const double tol = jacobi_tol(n);
@@ -1274,7 +1309,7 @@ int eigh_small_async(ndmps_ctx* ctx, double* a_in, int n, double* evals_dev, dou
 #define NDMPS_SMALL(NRV)                                                                                              \
     do {                                                                                                            \
         NDMPS_TRY(raise_smem_minus(eigh_small_kernel<NRV>, ctx, 8192));                                           \
-        eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, quad_stop2, evals_dev, evecs_dev, info); \
+        eigh_small_kernel<NRV><<<1, 512, smem, ctx->stream>>>(a_in, n, max_sweeps, tol2, stop_rel, quad_stop2, diag_tol, evals_dev, evecs_dev, info); \
     } while (0)
     if (n <= 32) NDMPS_SMALL(4);
     else NDMPS_SMALL(8);

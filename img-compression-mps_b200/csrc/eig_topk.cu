@@ -1024,7 +1024,10 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     symmetrise_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(H, m);
     NDMPS_LAUNCH_CHECK(ctx);
     int* rr_info = nullptr;
-    if (m >= 2 && m <= 64) NDMPS_TRY(eigh_small_async(ctx, H, m, hev, W, 1e-16f, &rr_info));   // no host round trip
+    // no host round trip.  Converged Ritz vectors of separated eigenvalues give a diagonal H (off-diagonals at the
+    // residual level): then the block is passed through; clusters keep the Jacobi rotation.  Either way the residual
+    // check below decides whether the result is used.
+    if (m >= 2 && m <= 64) NDMPS_TRY(eigh_small_async(ctx, H, m, hev, W, 1e-16f, &rr_info, ctx->opt_topk_rr_skip ? 1e-13 : 0.0));
     else NDMPS_TRY(eigh(ctx, H, m, hev, W, 0.0));
     // Zt[c] = sum_r W[r][c] Q[r]
     combine_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8)), 128, 0, ctx->stream>>>(W, 1, m, Xa, m, n, Xb);
