@@ -84,6 +84,41 @@ int raise_dynamic_smem(const void* kernel, int device, int bytes) {
     return NDMPS_OK;
 }
 
+// Can one cluster of `cluster_ctas` CTAs of `kernel` be resident on `device`?  Sizes above the portable 8 need the
+// kernel's opt-in first.  Answer cached per (kernel, device, size).
+int cluster_fits(const void* kernel, int device, int cluster_ctas, int threads, bool* fits) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, std::pair<int, int>>, bool> known;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, std::make_pair(device, cluster_ctas));
+    auto it = known.find(key);
+    if (it != known.end()) { *fits = it->second; return NDMPS_OK; }
+    int cur = -1;
+    NDMPS_CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) NDMPS_CUDA_TRY(cudaSetDevice(device));
+    bool ok = cluster_ctas <= 16;
+    if (ok && cluster_ctas > 8) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)cluster_ctas);
+        cfg.blockDim = dim3((unsigned)threads);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cluster_ctas;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        ok = cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) == cudaSuccess && clusters >= 1;
+    }
+    cudaGetLastError();                                  // a refused size is an answer, not an error of the context
+    if (cur != device) cudaSetDevice(cur);
+    known[key] = ok;
+    *fits = ok;
+    return NDMPS_OK;
+}
+
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
     if (ctx->pinned_doubles >= doubles) return NDMPS_OK;
     if (ctx->pinned) {
@@ -271,6 +306,7 @@ int ndmps_ctx_get_stat(ndmps_ctx_t* ctx, const char* name, double* value_out, in
     if (!strcmp(name, "eig_flops")) { *value_out = ctx->eig_flops; if (reset) ctx->eig_flops = 0.0; }
     else if (!strcmp(name, "eig_calls")) { *value_out = (double)ctx->eig_calls; if (reset) ctx->eig_calls = 0; }
     else if (!strcmp(name, "workspace_bytes")) { *value_out = (double)ctx->ws.high_water; }
+    else if (!strcmp(name, "cluster_launches")) { *value_out = (double)ctx->cluster_launches; if (reset) ctx->cluster_launches = 0; }
     else if (!strcmp(name, "tc_launches")) { *value_out = (double)ctx->tc_launches; if (reset) ctx->tc_launches = 0; }
     else {
         set_error("ndmps_ctx_get_stat: unknown statistic '%s'", name);
@@ -295,6 +331,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "chol_rows")) ctx->opt_chol_rows = value;
     else if (!strcmp(name, "eig_topk")) ctx->opt_eig_topk = value;
     else if (!strcmp(name, "topk_one_row")) ctx->opt_topk_one_row = value;
+    else if (!strcmp(name, "topk_cluster")) ctx->opt_topk_cluster = value;
     else if (!strcmp(name, "topk_big_ctas")) ctx->opt_topk_big_ctas = value;
     else if (!strcmp(name, "topk_passes")) ctx->opt_topk_passes = value;
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;

@@ -164,6 +164,8 @@ struct ndmps_ctx {
     int64_t opt_eig_small = 1;            // n <= 128: single-CTA all-in-one solver
     int64_t opt_eig_cholesky = 1;         // pivoted-Cholesky preconditioning of the Jacobi solve
     int64_t opt_eig_topk = 1;             // bond cap set: leading-eigenpair solver (eig_topk.cu) instead of the full one
+    int64_t opt_topk_cluster = 1;         // 1: n <= 512 tridiagonalisation as one thread-block cluster (exchange through distributed shared memory)
+    int64_t cluster_launches = 0;
     int64_t opt_topk_one_row = 0;         // 1: one matrix row per warp in the register-resident reduction (default: two up to n = 512)
     int64_t opt_topk_big_ctas = 0;        // CTAs per SM of the L2-streamed tridiagonalisation (0: occupancy, at most 3)
     int64_t opt_topk_passes = 0;          // bisection passes (0: 8, each divides the bracket by 129)
@@ -241,6 +243,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* g_dev, int64_t n, int64_t k, double*
 // CTAs spin at barriers, so the sum of what is launched must fit the machine: a launch books the SMs
 // its grid needs (grid / resident CTAs per SM) in a process-wide gate and gives them back from a
 // stream callback when the kernel has finished; a launch that does not fit waits on the host.
+int cluster_fits(const void* kernel, int device, int cluster_ctas, int threads, bool* fits);
 int coop_launch(ndmps_ctx* ctx, const void* fn, dim3 grid, dim3 block, void** args, size_t smem);
 int minmax_device(ndmps_ctx* ctx, const void* x, int64_t n, int dtype, double* out_dev2);
 int permute(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, const void* src, void* dst, int dtype, double scale);

@@ -69,23 +69,68 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
     __syncthreads();
 }
 
-// sum over the CTA's 8 warps, same value (bitwise) in every thread; one __syncthreads
+// all threads of all CTAs of the cluster; release / acquire at cluster scope orders the remote shared-memory stores
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// sum over the CTA's 16 warps, same value (bitwise) in every thread; one __syncthreads; the partial sums are added
+// as a tree (4 dependent adds)
 __device__ __forceinline__ double block_sum_all(double v, double* scratch) {
+    static_assert(TDT == 512, "16 warps");
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
-    double s = 0.0;
+    double s[16];
 #pragma unroll
-    for (int w = 0; w < TDT / 32; w++) s += scratch[w];
-    return s;
+    for (int w = 0; w < 16; w++) s[w] = scratch[w];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int w = 0; w < o; w++) s[w] += s[w + o];
+    return s[0];
 }
 
+// per-phase cycle counts of one thread (build with -DNDMPS_TOPK_PROF): register accumulators, written once at the end
 #ifdef NDMPS_TOPK_PROF
 __device__ unsigned long long g_prof[8];
-#define PROF_MARK(i) do { if (tid == 224 && cta == 0) { long long now = clock64(); g_prof[i] += (unsigned long long)(now - t_last); t_last = now; } } while (0)
+#define PROF_DECL unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_last = clock64()
+#define PROF_MARK(i) do { long long now = clock64(); if (jn < NDMPS_TOPK_PROF) prof_acc[i] += (unsigned long long)(now - prof_last); prof_last = now; } while (0)
+#define PROF_FLUSH() do { if (tid == 224 && cta == 0) { for (int i_ = 0; i_ < 8; i_++) g_prof[i_] += prof_acc[i_]; } } while (0)
 #else
+#define PROF_DECL do { } while (0)
 #define PROF_MARK(i) do { } while (0)
+#define PROF_FLUSH() do { } while (0)
 #endif
+
+// The inner pass of the tridiagonalisation for the chunks Q0 .. NEQ-1 of a warp's RPW rows: A -= u w^T + w u^T on
+// these columns, acc += A u'.  No predicates and no branches: the loads of u, w, u' are hoisted ahead of the
+// dependent DFMA pairs by the compiler, which a per-chunk `if` prevented (each chunk then cost a full
+// shared-memory latency).
+template <int NEQ, int RPW, int Q0>
+__device__ __forceinline__ void fused_pass(double (&a)[RPW][NEQ], const double* __restrict__ u, const double* __restrict__ wv,
+                                           const double* __restrict__ un, int lane, const double (&ui)[RPW],
+                                           const double (&wi)[RPW], double (&acc)[RPW]) {
+    double acc1[RPW];
+#pragma unroll
+    for (int t = 0; t < RPW; t++) acc1[t] = 0.0;
+#pragma unroll
+    for (int q = Q0; q < NEQ; q++) {
+        const int k = lane + 32 * q;
+        const double wk = wv[k], uk = u[k], nk = un[k];
+#pragma unroll
+        for (int t = 0; t < RPW; t++) {
+            double v = a[t][q];
+            v = fma(-ui[t], wk, v);
+            v = fma(-wi[t], uk, v);
+            a[t][q] = v;
+            if (q & 1) acc1[t] = fma(v, nk, acc1[t]); else acc[t] = fma(v, nk, acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < RPW; t++) acc[t] += acc1[t];
+}
 
 // ---------------------------------------------------------------------------------------------
 // 1. Householder tridiagonalisation.  Rows are dealt cyclically to the CTAs and then to their warps,
@@ -99,13 +144,21 @@ __device__ unsigned long long g_prof[8];
 // pivot row, and meets the others at the barrier.  One barrier per column.
 // V row j = reflector j (unit at j+1, zero before), H_j = I - tau_j v_j v_j^T.
 // ---------------------------------------------------------------------------------------------
-template <int NEQ, int RPW>
+//
+// CL = true (n <= 512, two rows per warp): the <= 16 CTAs are ONE thread-block cluster and the per-column exchange
+// never leaves the SMs.  Every owner pushes (p_i, A[i][jn+1]) of its rows into the shared memory of all CTAs of
+// the cluster (st.shared::cluster; the pivot ROW of the global-memory variant is read as the pivot COLUMN, which
+// by symmetry each CTA already holds for its own rows) and the column ends in the hardware cluster barrier
+// instead of an L2 atomic + poll + reload.  Measured: 2.50 -> 2.28 ms per n = 512 problem (profiles/r02_summary.md
+// has the per-phase cycle counts and the two restructurings that did NOT pay).
+template <int NEQ, int RPW, bool CL>
 __global__ void __launch_bounds__(TDT)
 tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
                double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
     __shared__ double ub0[32 * NEQ], ub1[32 * NEQ], wv[32 * NEQ];
     __shared__ double red0[TDT / 32], red1[TDT / 32];
     __shared__ double s_alpha;
+    __shared__ double2 pcol[CL ? 2 * 32 * NEQ : 1];                                  // (p_k, A[k][pivot]) of both parities
     constexpr int KM = (32 * NEQ) / TDT > 0 ? (32 * NEQ) / TDT : 1;                 // vector elements per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
     // this warp's RPW rows, held in registers: lane l has columns l + 32 q.  Row t of the warp is row
@@ -127,9 +180,8 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
     double tau = 0.0;
     unsigned epoch = 0;
     __syncthreads();
-#ifdef NDMPS_TOPK_PROF
-    long long t_last = clock64();
-#endif
+    if constexpr (CL) cluster_barrier();                 // every CTA of the cluster is resident before the first remote store
+    PROF_DECL;
     for (int jn = 0; jn <= n - 2; jn++) {
         const int par = jn & 1;
         double r[KM];                                    // row jn of the current matrix, columns >= jn
@@ -140,17 +192,31 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
                 r[m] = k < n ? G[k] : 0.0;
             }
         } else {
-            const double* pb = pbuf + (size_t)(par ^ 1) * n;
-            const double* rb = rowbuf + (size_t)(par ^ 1) * n;
             double pf[KM], rj[KM];
+            double pj;
+            if constexpr (CL) {
+                const double2* pc = pcol + (par ^ 1) * 32 * NEQ;
 #pragma unroll
-            for (int m = 0; m < KM; m++) {
-                const int k = tid + m * TDT;
-                const bool on = k >= jn && k < n;
-                pf[m] = on ? __ldcg(pb + k) : 0.0;
-                rj[m] = on ? __ldcg(rb + k) : 0.0;
+                for (int m = 0; m < KM; m++) {
+                    const int k = tid + m * TDT;
+                    const bool on = k >= jn && k < n;
+                    const double2 v = on ? pc[k] : make_double2(0.0, 0.0);
+                    pf[m] = v.x;
+                    rj[m] = v.y;
+                }
+                pj = pc[jn].x;
+            } else {
+                const double* pb = pbuf + (size_t)(par ^ 1) * n;
+                const double* rb = rowbuf + (size_t)(par ^ 1) * n;
+#pragma unroll
+                for (int m = 0; m < KM; m++) {
+                    const int k = tid + m * TDT;
+                    const bool on = k >= jn && k < n;
+                    pf[m] = on ? __ldcg(pb + k) : 0.0;
+                    rj[m] = on ? __ldcg(rb + k) : 0.0;
+                }
+                pj = __ldcg(pb + jn);
             }
-            const double pj = __ldcg(pb + jn);
             double part = 0.0;
 #pragma unroll
             for (int m = 0; m < KM; m++) part = fma(pf[m], u[tid + m * TDT], part);
@@ -217,51 +283,87 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
         __syncthreads();
         PROF_MARK(4);
-        // fused rank-2 update (reflector jn-1) + product with reflector jn, this warp's rows, columns >= jn+1
+        // fused rank-2 update (reflector jn-1) + product with reflector jn, this warp's rows, column chunks >= jn+1.
+        // Straight-line code from the first live quarter of the chunks on (fused_pass): dead columns and dead rows
+        // are updated with whatever finite values the vectors hold there and multiply u'[k] = 0.
         {
             double* pw = pbuf + (size_t)par * n;
             double* rw = rowbuf + (size_t)par * n;
             const int q0 = (jn + 1) >> 5;
-            double acc[RPW];
+            double acc[RPW], colv[RPW], ui[RPW], wi[RPW];
             bool live[RPW];
+            bool any = false;
 #pragma unroll
             for (int t = 0; t < RPW; t++) {
                 live[t] = gi[t] >= jn + 1 && gi[t] < n;
+                any = any || live[t];
                 acc[t] = 0.0;
-                if (live[t]) {
-                    const bool pub = gi[t] == jn + 1;
-                    const double ui = u[gi[t]], wi = wv[gi[t]];   // zero while jn == 0
-                    double acc1 = 0.0;
+                colv[t] = 0.0;
+                ui[t] = live[t] ? u[gi[t]] : 0.0;        // zero while jn == 0
+                wi[t] = live[t] ? wv[gi[t]] : 0.0;
+            }
+            if (any) {
+                constexpr int QG = NEQ / 4;
+                switch (q0 / QG) {
+                    case 0: fused_pass<NEQ, RPW, 0>(a, u, wv, un, lane, ui, wi, acc); break;
+                    case 1: fused_pass<NEQ, RPW, QG>(a, u, wv, un, lane, ui, wi, acc); break;
+                    case 2: fused_pass<NEQ, RPW, 2 * QG>(a, u, wv, un, lane, ui, wi, acc); break;
+                    default: fused_pass<NEQ, RPW, 3 * QG>(a, u, wv, un, lane, ui, wi, acc); break;
+                }
+                if constexpr (CL) {
+                    // the pivot column jn+1 sits in chunk q0, lane (jn+1) % 32
 #pragma unroll
-                    for (int q = 0; q < NEQ; q++) {
-                        const int k = lane + 32 * q;
-                        if (q >= q0 && k >= jn + 1 && k < n) {
-                            double v = a[t][q];
-                            v = fma(-ui, wv[k], v);
-                            v = fma(-wi, u[k], v);
-                            a[t][q] = v;
-                            if (q & 1) acc1 = fma(v, un[k], acc1); else acc[t] = fma(v, un[k], acc[t]);
-                            if (pub) __stcg(rw + k, v);
+                    for (int t = 0; t < RPW; t++) {
+#pragma unroll
+                        for (int q = 0; q < NEQ; q++)
+                            if (q == q0) colv[t] = a[t][q];
+                        colv[t] = __shfl_sync(0xffffffffu, colv[t], (jn + 1) & 31);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < RPW; t++) {
+                        if (gi[t] == jn + 1) {
+#pragma unroll
+                            for (int q = 0; q < NEQ; q++) {
+                                const int k = lane + 32 * q;
+                                if (q >= q0 && k >= jn + 1 && k < n) __stcg(rw + k, a[t][q]);
+                            }
                         }
                     }
-                    acc[t] += acc1;
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)              // the RPW reductions interleaved
 #pragma unroll
                 for (int t = 0; t < RPW; t++) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+            if constexpr (CL) {
+                // lane l hands this warp's rows to CTA l of the cluster
+                const unsigned base = (unsigned)__cvta_generic_to_shared(pcol + par * 32 * NEQ);
 #pragma unroll
-            for (int t = 0; t < RPW; t++)
-                if (live[t] && lane == 0) __stcg(pw + gi[t], acc[t]);
+                for (int t = 0; t < RPW; t++)
+                    if (live[t] && lane < C) {
+                        unsigned remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + (unsigned)gi[t] * 16u), "r"(lane));
+                        asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote), "d"(acc[t]), "d"(colv[t]) : "memory");
+                    }
+            } else {
+#pragma unroll
+                for (int t = 0; t < RPW; t++)
+                    if (live[t] && lane == 0) __stcg(pw + gi[t], acc[t]);
+            }
         }
         PROF_MARK(5);
-        epoch++;
-        grid_barrier(ctrl, epoch * C);
+        if constexpr (CL) {
+            cluster_barrier();
+        } else {
+            epoch++;
+            grid_barrier(ctrl, epoch * C);
+        }
         PROF_MARK(6);
         double* t = u; u = un; un = t;
         tau = taun;
     }
+    PROF_FLUSH();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -987,8 +1089,36 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     } else {
         int n_arg = n, ldv_arg = ldv;
         void* args[] = {(void*)&G, &n_arg, &ldv_arg, &V, &tau, &d, &e, &pbuf, &rowbuf, &ctrl};
-        void* fn = n <= 512 ? (rpw == 2 ? (void*)tridiag_kernel<16, 2> : (void*)tridiag_kernel<16, 1>) : (void*)tridiag_kernel<32, 1>;
-        NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
+        bool clustered = false;
+        if (rpw == 2 && ctx->opt_topk_cluster) {
+            // one cluster of 2^x CTAs (CTAs past the last row only take part in the barriers)
+            int cc = 1;
+            while (cc < C) cc *= 2;
+            const void* cfn = (const void*)tridiag_kernel<16, 2, true>;
+            bool fits = false;
+            NDMPS_TRY(cluster_fits(cfn, ctx->device, cc, TDT, &fits));
+            if (fits) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)cc);
+                cfg.blockDim = dim3(TDT);
+                cfg.stream = ctx->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)cc;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                NDMPS_CUDA_TRY(cudaLaunchKernelExC(&cfg, cfn, args));
+                clustered = true;
+                ctx->cluster_launches++;
+            }
+        }
+        if (!clustered) {
+            void* fn = n <= 512 ? (rpw == 2 ? (void*)tridiag_kernel<16, 2, false> : (void*)tridiag_kernel<16, 1, false>)
+                                : (void*)tridiag_kernel<32, 1, false>;
+            NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
+        }
 #ifdef NDMPS_TOPK_PROF
         {
             unsigned long long h[8];

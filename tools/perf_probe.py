@@ -61,8 +61,12 @@ def main(which):
             k = 64
             gm = 0.5 * (gm + gm.T)
             try:
+                ctx.set_option("topk_cluster", 0)
+                ms_grid = timeit(lambda: _ops.eigh_topk(gm, k), reps=3, warm=1)
+                ctx.set_option("topk_cluster", 1)
                 ev, vec, tr, health = _ops.eigh_topk(gm, k)
                 ms = timeit(lambda: _ops.eigh_topk(gm, k), reps=3, warm=1)
+                name += f" (grid-barrier variant {ms_grid:.3f} ms, cluster launches {int(ctx.stat('cluster_launches'))})"
             except Exception as exc:
                 print(f"topk {name}: FAILED {exc}", flush=True)
                 continue
