@@ -278,7 +278,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
             const int k = tid + m * TDT;
             const double v = k == jn + 1 ? 1.0 : ((k >= jn + 2 && k < n) ? r[m] * scal : 0.0);
             un[k] = v;
-            if (cta == jn % C && k < n) V[(size_t)jn * ldv + k] = v;
+            if (cta == jn % C && k < ldv) V[(size_t)jn * ldv + k] = v;   // the pad element of an odd n too: rows are read in 16-byte chunks
         }
         if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
         __syncthreads();
@@ -875,7 +875,95 @@ __global__ void __launch_bounds__(256) symmetrise_kernel(double* H, int m) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 5. Back-transformation: one warp per Ritz vector (four per CTA, sharing the reflector rows
+// 5a. Back-transformation, n <= 1024: one warp (one CTA) per Ritz vector, TWO reflectors per dependent
+// reduction.  With d = v_j.z, e = v_{j-1}.z and g = v_{j-1}.v_j (three dot products of one pass, reduced by
+// interleaved butterflies),  H_{j-1} H_j z = z - tau_j d v_j - tau_{j-1} (e - tau_j d g) v_{j-1}:
+// (n - 2) / 2 reduction latencies instead of n - 2.  The reflector rows arrive through a cp.async ring of
+// PAIRS_AHEAD pairs in shared memory (only the 16-byte chunks right of the zero part), so the L2 latency of a row
+// is paid PAIRS_AHEAD pairs before it is used.  U[i * ldu + t] = z_i.
+// ---------------------------------------------------------------------------------------------
+constexpr int PAIRS_AHEAD = 4;
+
+__device__ __forceinline__ void bt_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+template <int NE>
+__global__ void __launch_bounds__(32)
+backtransform_pair_kernel(const double* __restrict__ V, int ldv, const double* __restrict__ tau_g, int n,
+                          const double* __restrict__ Zt, double* __restrict__ U, int64_t ldu) {
+    extern __shared__ __align__(16) double bt_ring[];    // [PAIRS_AHEAD][2][32 * NE], then tau[32 * NE]
+    constexpr int NV = 32 * NE;
+    double* tau_s = bt_ring + PAIRS_AHEAD * 2 * NV;
+    const int lane = threadIdx.x, t = blockIdx.x;
+    double z[NE];
+#pragma unroll
+    for (int q = 0; q < NE; q++) {
+        const int k = lane + 32 * q;
+        z[q] = k < n ? Zt[(size_t)t * n + k] : 0.0;
+    }
+    for (int c = lane; c < PAIRS_AHEAD * 2 * NV; c += 32) bt_ring[c] = 0.0;
+    for (int c = lane; c < NV; c += 32) tau_s[c] = c < n - 2 ? tau_g[c] : 0.0;   // a global load per pair would sit in the dependent chain
+    __syncwarp();
+    const int pairs = (n - 1) / 2;                       // reflectors n-3 .. 0, the last pair may be single
+    const int chunks = (n + 1) / 2;                      // 16-byte chunks of a row (ldv is even, rows start 16-byte aligned)
+    auto issue = [&](int p) {
+        if (p < pairs) {
+            const int ja = n - 3 - 2 * p, jb = ja - 1;
+            double* slot = bt_ring + (size_t)(p % PAIRS_AHEAD) * 2 * NV;
+            const int c0 = (jb < 0 ? ja : jb) / 2;       // both rows are zero left of column jb + 1 >= 2 c0
+            for (int c = c0 + lane; c < chunks; c += 32) {
+                bt_cp_async16(slot + 2 * c, V + (size_t)ja * ldv + 2 * c);
+                if (jb >= 0) bt_cp_async16(slot + NV + 2 * c, V + (size_t)jb * ldv + 2 * c);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    for (int p = 0; p < PAIRS_AHEAD - 1; p++) issue(p);
+    for (int p = 0; p < pairs; p++) {
+        issue(p + PAIRS_AHEAD - 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(PAIRS_AHEAD - 1));
+        __syncwarp();
+        const int ja = n - 3 - 2 * p, jb = ja - 1;
+        const double* va = bt_ring + (size_t)(p % PAIRS_AHEAD) * 2 * NV;
+        const double* vb = va + NV;
+        const double ta = tau_s[ja], tb = jb >= 0 ? tau_s[jb] : 0.0;
+        // no predicates: left of the copied chunks the ring still holds its initial zeros, the copied chunks hold the
+        // rows' own zeros up to the unit element, and an odd n reads the (zero) first element of the next row
+        double a[NE], b[NE];
+        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NE; q++) {
+            a[q] = va[lane + 32 * q];
+            b[q] = vb[lane + 32 * q];
+        }
+#pragma unroll
+        for (int q = 0; q < NE; q++) {
+            if (q & 1) { d1 = fma(a[q], z[q], d1); e1 = fma(b[q], z[q], e1); g1 = fma(a[q], b[q], g1); }
+            else { d0 = fma(a[q], z[q], d0); e0 = fma(b[q], z[q], e0); g0 = fma(a[q], b[q], g0); }
+        }
+        double d = d0 + d1, e = e0 + e1, g = g0 + g1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        const double ca = ta * d;
+        const double cb = tb * fma(-ca, g, e);
+#pragma unroll
+        for (int q = 0; q < NE; q++) z[q] = fma(-cb, b[q], fma(-ca, a[q], z[q]));
+        __syncwarp();                                    // the slot is refilled PAIRS_AHEAD - 1 pairs from now
+    }
+#pragma unroll
+    for (int q = 0; q < NE; q++) {
+        const int k = lane + 32 * q;
+        if (k < n) U[(size_t)k * ldu + t] = z[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5b. The previous form (kept for the option topk_bt_pairs = 0): one warp per Ritz vector (four per CTA, sharing the reflector rows
 // through L1), z <- H_0 H_1 ... H_{n-3} z.  The next reflector is loaded into registers while the
 // current one is applied; 32-column chunks that lie entirely in the zero part of a reflector
 // are skipped.  U[i * ldu + t] = z_i.
@@ -1167,7 +1255,16 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     ritz_residual_kernel<<<m, 128, 0, ctx->stream>>>(d, e, Xb, hev, n, res);
     NDMPS_LAUNCH_CHECK(ctx);
     // 5. back-transform
-    if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
+    if (n <= 1024 && ctx->opt_topk_bt_pairs) {
+        const size_t ring = (size_t)(PAIRS_AHEAD * 2 + 1) * (n <= 512 ? 512 : 1024) * sizeof(double);
+        if (n <= 512) {
+            NDMPS_TRY(raise_dynamic_smem((const void*)backtransform_pair_kernel<16>, ctx->device, (int)ring));
+            backtransform_pair_kernel<16><<<(unsigned)m, 32, ring, ctx->stream>>>(V, ldv, tau, n, Xb, U, ldu);
+        } else {
+            NDMPS_TRY(raise_dynamic_smem((const void*)backtransform_pair_kernel<32>, ctx->device, (int)ring));
+            backtransform_pair_kernel<32><<<(unsigned)m, 32, ring, ctx->stream>>>(V, ldv, tau, n, Xb, U, ldu);
+        }
+    } else if (n <= 512) backtransform_kernel<16><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
     else if (n <= 1024) backtransform_kernel<32><<<(unsigned)((m + 3) / 4), 128, 0, ctx->stream>>>(V, ldv, tau, n, Xb, m, U, ldu);
     else backtransform_big_kernel<<<m, TDT, 0, ctx->stream>>>(V, ldv, tau, n, Xb, U, ldu);
     NDMPS_LAUNCH_CHECK(ctx);
