@@ -80,6 +80,18 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
     s = c * t;
 }
 
+// The same rotation from cos 2theta = |beta - alpha| / h, h = hypot(beta - alpha, 2 gamma):
+// c = sqrt((1 + cos 2theta) / 2), s = sign(beta - alpha) 2 gamma / (2 h c).  Two reciprocal square roots in the
+// dependent chain instead of two reciprocals and two square roots; no cancellation anywhere (c^2 + s^2 = 1 to rounding).
+__device__ __forceinline__ void rotation_cs(double alpha, double beta, double gamma, double& c, double& s) {
+    const double d = beta - alpha, g2 = 2.0 * gamma;
+    const double r = rsqrt_refined(fma(d, d, g2 * g2));       // 1 / h
+    const double c2 = fma(0.5 * fabs(d), r, 0.5);
+    const double rc = rsqrt_refined(c2);
+    c = c2 * rc;
+    s = copysign(0.5, d) * g2 * r * rc;
+}
+
 // Orthogonalise columns x, y (length n, shared memory) with a group of LP lanes (LP = 32: one
 // pair per warp; LP = 8: four pairs per warp, for short columns where the butterfly
 // reductions and the redundant per-lane rotation math would otherwise dominate).
@@ -112,8 +124,8 @@ __device__ __forceinline__ bool rotate_group(double* x, double* y, int n, int li
     if (!valid || !(alpha > floor2) || !(beta > floor2)) return false;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;
     relmax = fmaxf(relmax, (float)(gamma * gamma * rcp_approx(alpha * beta)));
-    double c, s, t;
-    rotation(alpha, beta, gamma, c, s, t);
+    double c, s;
+    rotation_cs(alpha, beta, gamma, c, s);
 #pragma unroll
     for (int tt = 0; tt < NR; tt++) {
         const int i = li + LP * tt;
@@ -244,8 +256,10 @@ __device__ __forceinline__ void tournament_pair(int P, int lr, int w, int& s1, i
         s1 = m;
         s2 = lr;
     } else {
-        s1 = (lr + w) % m;
-        s2 = (lr - w + m) % m;
+        s1 = lr + w;                 // lr, w < m: no integer division (it cost ~450 cycles per round of the n <= 64 solver)
+        s1 = s1 >= m ? s1 - m : s1;
+        s2 = lr - w;
+        s2 = s2 < 0 ? s2 + m : s2;
     }
 }
 
@@ -1039,6 +1053,12 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
     int sweep = 0;
     int done = rank < 2 ? 1 : 0;
     float relmax = 0.f;
+#ifdef NDMPS_EIG_PROF
+    long long pt[4] = {0, 0, 0, 0}, pl = clock64();
+#define EPROF(i) do { long long now_ = clock64(); pt[i] += now_ - pl; pl = now_; } while (0)
+#else
+#define EPROF(i) do { } while (0)
+#endif
     while (!done && sweep < max_sweeps) {
         bool any = false;
         for (int lr = 0; lr < P - 1; lr++) {
@@ -1048,9 +1068,12 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
                 if (m < matches) tournament_pair(P, lr, m, s1, s2);
                 const bool valid = m < matches && s1 < rank && s2 < rank;
                 const int c1 = valid ? piv[s1] : 0, c2 = valid ? piv[s2] : 0;
+                EPROF(0);
                 any |= rotate_group<NR, 8>(S + (size_t)c1 * ld, S + (size_t)c2 * ld, n, li, valid, tol2, floor2, relmax);
+                EPROF(1);
             }
             __syncthreads();
+            EPROF(2);
         }
         sweep++;
         done = !__syncthreads_or(any ? 1 : 0);
@@ -1087,6 +1110,9 @@ eigh_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double to
         const double* col = S + (size_t)piv[c] * ld;
         for (int i = lane; i < n; i += 32) evecs[(size_t)i * n + cnt] = col[i] * invn;
     }
+#ifdef NDMPS_EIG_PROF
+    if (tid == 0) printf("[eig prof] n=%d rank=%d sweeps=%d cycles: pairing %lld rotate %lld sync %lld\n", n, rank, sweep, pt[0], pt[1], pt[2]);
+#endif
     if (tid == 0) { info[0] = done ? sweep : -(sweep + 1); info[1] = rank; }
 }
 

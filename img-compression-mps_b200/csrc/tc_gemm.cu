@@ -667,7 +667,7 @@ struct GemmSmem {
 // per-warp shared-memory transpose so that rows leave in 128-byte lines).
 // TMEM columns: [0, BN) h.h buffer 0, [BN, 2 BN) h.h buffer 1, [2 BN, 3 BN) corrections (one chain over all of k).
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool OUT_T, class TC>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, BN == 64 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t m, int64_t n,
                int64_t k, TC* __restrict__ C, int64_t ldc) {
     using S = GemmSmem<BN, STAGES>;
@@ -1063,7 +1063,12 @@ int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const
             else NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, false, double>(ctx, ma, mb, m, n, k, (double*)c, ldc)));             \
         }                                                                                                                      \
     } while (0)
-    if (bn == 64) {
+    if (k <= BK && n > 64 && !a_mn && b_mn && ctx->opt_tc_single_k) {
+        // one k-tile per output tile (the final contraction dense = X W, k = bond): nothing to pipeline inside a CTA, so
+        // 128 x 64 tiles with ONE stage (73 KB, 256 TMEM columns, 80 registers) put two CTAs on an SM and the load /
+        // MMA / drain phases of neighbours overlap
+        NDMPS_TC_GO(64, 1, false, true);
+    } else if (bn == 64) {
         if (a_mn && !b_mn) NDMPS_TC_GO(64, 3, true, false);
         else if (!a_mn && b_mn) NDMPS_TC_GO(64, 3, false, true);
         else if (!a_mn && !b_mn) NDMPS_TC_GO(64, 3, false, false);
