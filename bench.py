@@ -169,7 +169,7 @@ def algorithmic_work(dims, ranks):
         recon_flops += 2.0 * p * r[k] * dims[k] * r[k + 1]
         p *= dims[k]
     # Gram passes actually executed: sites are front-merged while the fused row count stays <= 512
-    executed = issued = proj_bytes_exec = gram_bytes_exec = 0.0
+    executed = issued = issued_i8 = i8_time_share = proj_bytes_exec = gram_bytes_exec = 0.0
     cols, i, rprev = n, 0, 1
     while i < L - 1:
         rows = rprev * dims[i]
@@ -183,13 +183,20 @@ def algorithmic_work(dims, ranks):
         executed += 2.0 * side * side * max(rows, cols)
         nt = -(-side // 128)                                  # gram_dmma computes the upper-triangle 128 x 128 tiles only
         issued += 2.0 * side * side * max(rows, cols) * ((nt + 1) / (2.0 * nt) if side >= 48 else 1.0)
+        # tc_gemm.cu gram_tc: float32 unfoldings with 64 <= rows <= 4096 and >= 2048 columns go through the integer
+        # tensor cores: 128 x 64 tiles that touch the upper triangle, 15 digit products (kind::i8) per 32-deep k-step
+        if rows <= cols and 64 <= rows <= 4096 and cols >= 2048:
+            ntr, ntc = -(-rows // 128), -(-rows // 64)
+            tiles = sum(max(ntc - 2 * ti, 0) for ti in range(ntr))
+            issued_i8 += 15.0 * 2.0 * tiles * 128 * 64 * cols
         gram_bytes_exec += 4.0 * rows * cols
         proj_bytes_exec += 4.0 * (rows * cols + r[i + k] * cols)
         rprev = r[i + k]
         i += k
     return {"encode_bytes": 8.0 * n, "decode_bytes": 8.0 * n, "sweep_bytes": sweep_bytes, "gram_flops": gram_flops,
             "gram_flops_executed": executed, "gram_flops_issued": issued, "gram_bytes_executed": gram_bytes_exec,
-            "project_bytes_executed": proj_bytes_exec,
+            "project_bytes_executed": proj_bytes_exec, "gram_i8_ops_issued": issued_i8,
+            "recon_bytes_executed": 4.0 * n + 4.0 * (int(np.prod(dims[: (L + 1) // 2])) + int(np.prod(dims[(L + 1) // 2:]))) * max(ranks),
             "project_flops": proj_flops, "project_bytes": proj_bytes, "recon_bytes": recon_bytes, "recon_flops": recon_flops}
 
 
@@ -525,11 +532,17 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
     if have("gram"):
         ms = stages_per_call["gram"][0]
         f = work["gram_flops_executed"]
-        if used_tc:
-            entry("gram", "gram_tc_kernel (tcgen05.mma kind::f16 on bf16x3 planes, 6 products, float64 drains) + plane split", "tensor",
-                  6.0 * f * work["gram_upper_fraction"] / (ms * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s", "gram_tc_kernel",
-                  {"algorithmic_fp32_flops_per_tensor": f, "issued_bf16_flops_per_tensor": 6.0 * f * work["gram_upper_fraction"],
-                   "note": "achieved = bf16 tensor-core flops actually issued (six products, upper-triangle tiles) / stage time"})
+        if used_tc and work.get("gram_i8_ops_issued"):
+            ops = work["gram_i8_ops_issued"]
+            entry("gram", "gram_i8_kernel (tcgen05.mma kind::i8 on five 7-bit digit planes, 15 products per k-step, int32 TMEM "
+                          "accumulators, float64 drain) + row_stats / split_i8 passes; small unfoldings on the FP64 tensor pipe",
+                  "tensor", ops / (ms * 1e-3) / 1e12, 2.0 * peaks["bf16_tflops"], "TOP/s (int8)", "gram_i8_kernel",
+                  {"algorithmic_fp32_flops_per_tensor": f, "issued_int8_ops_per_tensor": ops,
+                   "peak_note": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (kind::i8 issues at twice the kind::f16 rate; "
+                                "no measured int8 figure exists for this pool)",
+                   "note": "achieved = int8 tensor-core operations issued by gram_i8_kernel (tiles touching the upper triangle) / time of "
+                           "the whole Gram stage, which also holds the statistics and digit-split passes (HBM-bound) and the small "
+                           "Grams; profiles/r02_summary.md has the kernel alone (tensor pipe 49.8 % active under ncu)"})
         else:
             entry("gram", "gram_dmma_kernel (FP64 tensor pipe, mma.sync m8n8k4.f64)", "tensor", f * work["gram_upper_fraction"] / (ms * 1e-3) / 1e12,
                   fp64_tflops, "TFLOP/s (fp64)", "gram_dmma_kernel", {"algorithmic_fp32_flops_per_tensor": f})
@@ -541,9 +554,13 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
                "flops_per_tensor": work["project_flops"]})
     if have("contract"):
         ms = stages_per_call["contract"][0]
-        b = work["recon_bytes"]
-        entry("contract", "core chain + final product dense = X W", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
-              "gemm_tc_kernel" if used_tc else "gemm_dmma_kernel", {"algorithmic_bytes_per_tensor": b, "flops_per_tensor": work["recon_flops"]})
+        b = work["recon_bytes_executed"]
+        entry("contract", "core chain (bond-sized) + final product dense = X W (gemm_tc_kernel, bf16x3 on tcgen05)", "hbm",
+              b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s", "gemm_tc_kernel" if used_tc else "gemm_dmma_kernel",
+              {"algorithmic_bytes_per_tensor": b, "survey_bytes_per_tensor_site_by_site": work["recon_bytes"],
+               "flops_per_tensor": work["recon_flops"],
+               "note": "bytes = what this implementation has to move: the dense tensor written once plus the two half-chain factors "
+                       "(SURVEY 8(d) counts a site-by-site chain that re-reads the growing intermediate: kept for reference)"})
     if have("eig"):
         ms = stages_per_call["eig"][0]
         entry("eig", "bond eigenproblems: eig_topk.cu (tridiag_kernel, bisect, invit, Rayleigh-Ritz) for capped bonds, eig.cu Jacobi otherwise",

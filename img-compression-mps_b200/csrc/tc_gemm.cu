@@ -30,6 +30,8 @@
 
 #include <mutex>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ndmps {
@@ -658,18 +660,24 @@ struct GemmSmem {
     static constexpr int A_BYTES = 3 * PLANE_TILE;
     static constexpr int B_PLANE = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + 3 * B_PLANE;
-    static constexpr int BARRIER_OFF = STAGES * STAGE_BYTES;
+    static constexpr int XPOSE_OFF = STAGES * STAGE_BYTES;              // per-warp 32 x 32 float transposes (row-major output),
+    static constexpr int XPOSE_BYTES = (EPI_THREADS / 32) * 32 * 32 * 4;  // 16-byte chunks XOR-swizzled by the row
+    static constexpr int BARRIER_OFF = XPOSE_OFF + XPOSE_BYTES;
     static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;
 };
 
 // A_MN / B_MN: operand stored MN-major (planes are [k][mn]) instead of K-major ([mn][k]).
 // OUT_T: write C transposed (C[n][m], lanes = consecutive m: coalesced) instead of row-major (through a
 // per-warp shared-memory transpose so that rows leave in 128-byte lines).
-// TMEM columns: [0, BN) h.h buffer 0, [BN, 2 BN) h.h buffer 1, [2 BN, 3 BN) corrections (one chain over all of k).
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool OUT_T, class TC>
-__global__ void __launch_bounds__(THREADS, BN == 64 ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t m, int64_t n,
                int64_t k, TC* __restrict__ C, int64_t ldc) {
+    // PERSISTENT: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so the CTAs running at
+    // the same time share an A row block through L2 and write neighbouring column blocks of the same rows).  The stage
+    // ring, the h.h ping-pong and the two correction accumulators run on through the tile boundaries: while the drain
+    // warps write tile i, the copy thread is loading tile i + 1 / i + 2 and the MMA thread is up to two k-tiles ahead.
+    // TMEM columns: [0, BN) h.h buffer 0, [BN, 2 BN) h.h buffer 1, [2 BN, 3 BN) / [3 BN, 4 BN) corrections of even / odd tiles.
     using S = GemmSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -677,20 +685,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* empty = full + STAGES;
     uint64_t* hh_full = empty + STAGES;        // [2]
     uint64_t* hh_empty = hh_full + 2;          // [2]
-    uint64_t* rest_full = hh_empty + 2;        // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rest_full + 1);
+    uint64_t* rest_full = hh_empty + 2;        // [2]
+    uint64_t* rest_empty = rest_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rest_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * TILE, n0 = (int64_t)blockIdx.y * BN;
     const int nk = (int)((k + BK - 1) / BK);
-    constexpr uint32_t TMEM_COLS = BN == 64 ? 256 : 512;
+    const int64_t ntn = (n + BN - 1) / BN, n_tiles = ((m + TILE - 1) / TILE) * ntn;
+    constexpr uint32_t TMEM_COLS = 4 * BN;     // 256 or 512
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&hh_full[b], 1); mbar_init(&hh_empty[b], EPI_THREADS / 32); }
-        mbar_init(rest_full, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&hh_full[b], 1);
+            mbar_init(&hh_empty[b], EPI_THREADS / 32);
+            mbar_init(&rest_full[b], 1);
+            mbar_init(&rest_empty[b], EPI_THREADS / 32);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -700,27 +713,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        for (int kt = 0; kt < nk; kt++) {
-            const int s = kt % STAGES;
-            mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
-            mbar_expect_tx(&full[s], S::STAGE_BYTES);
-            uint8_t* st = smem + s * S::STAGE_BYTES;
-            const int k0 = kt * BK;
+        int g = 0;                                   // k-tiles issued so far (all tiles)
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t m0 = (tile / ntn) * TILE, n0 = (tile % ntn) * BN;
+            for (int kt = 0; kt < nk; kt++, g++) {
+                const int s = g % STAGES;
+                mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                uint8_t* st = smem + s * S::STAGE_BYTES;
+                const int k0 = kt * BK;
 #pragma unroll
-            for (int p = 0; p < 3; p++) {
-                uint8_t* a = st + p * PLANE_TILE;
-                if constexpr (A_MN) {      // two boxes of 64 k-rows x 64 mn-columns
-                    tma_load_3d(a, &map_a, &full[s], (int)m0, k0, p);
-                    tma_load_3d(a + PLANE_TILE / 2, &map_a, &full[s], (int)m0 + 64, k0, p);
-                } else {                   // one box of 128 mn-rows x 64 k-columns
-                    tma_load_3d(a, &map_a, &full[s], k0, (int)m0, p);
-                }
-                uint8_t* b = st + S::A_BYTES + p * S::B_PLANE;
-                if constexpr (B_MN) {
+                for (int p = 0; p < 3; p++) {
+                    uint8_t* a = st + p * PLANE_TILE;
+                    if constexpr (A_MN) {      // two boxes of 64 k-rows x 64 mn-columns
+                        tma_load_3d(a, &map_a, &full[s], (int)m0, k0, p);
+                        tma_load_3d(a + PLANE_TILE / 2, &map_a, &full[s], (int)m0 + 64, k0, p);
+                    } else {                   // one box of 128 mn-rows x 64 k-columns
+                        tma_load_3d(a, &map_a, &full[s], k0, (int)m0, p);
+                    }
+                    uint8_t* b = st + S::A_BYTES + p * S::B_PLANE;
+                    if constexpr (B_MN) {
 #pragma unroll
-                    for (int h = 0; h < BN / 64; h++) tma_load_3d(b + h * 8192, &map_b, &full[s], (int)n0 + 64 * h, k0, p);
-                } else {
-                    tma_load_3d(b, &map_b, &full[s], k0, (int)n0, p);
+                        for (int h = 0; h < BN / 64; h++) tma_load_3d(b + h * 8192, &map_b, &full[s], (int)n0 + 64 * h, k0, p);
+                    } else {
+                        tma_load_3d(b, &map_b, &full[s], k0, (int)n0, p);
+                    }
                 }
             }
         }
@@ -728,82 +745,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr uint32_t idesc = instr_desc(TILE, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
         constexpr uint32_t A_STEP = A_MN ? 2048 : 32, B_STEP = B_MN ? 2048 : 32;
         constexpr uint32_t A_LBO = A_MN ? 8192 : 16, B_LBO = B_MN ? 8192 : 16;
-        for (int kt = 0; kt < nk; kt++) {
-            const int s = kt % STAGES, hb = kt & 1;
-            mbar_wait(&hh_empty[hb], ((kt >> 1) & 1) ^ 1);
-            mbar_wait(&full[s], (kt / STAGES) & 1);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
-            const uint32_t d_hh = tmem_base + (uint32_t)hb * BN, d_rest = tmem_base + 2 * BN;
+        int g = 0, t_local = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t_local++) {
+            const int rb = t_local & 1;
+            mbar_wait(&rest_empty[rb], ((t_local >> 1) & 1) ^ 1);
+            for (int kt = 0; kt < nk; kt++, g++) {
+                const int s = g % STAGES, hb = g & 1;
+                mbar_wait(&hh_empty[hb], ((g >> 1) & 1) ^ 1);
+                mbar_wait(&full[s], (g / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
+                const uint32_t d_hh = tmem_base + (uint32_t)hb * BN, d_rest = tmem_base + (uint32_t)(2 + rb) * BN;
 #pragma unroll
-            for (int ks = 0; ks < BK / UK; ks++)
-                umma_bf16(d_hh, smem_desc(sa + ks * A_STEP, A_LBO, 1024), smem_desc(sb + ks * B_STEP, B_LBO, 1024), idesc, ks != 0);
-            umma_commit(&hh_full[hb]);
+                for (int ks = 0; ks < BK / UK; ks++)
+                    umma_bf16(d_hh, smem_desc(sa + ks * A_STEP, A_LBO, 1024), smem_desc(sb + ks * B_STEP, B_LBO, 1024), idesc, ks != 0);
+                umma_commit(&hh_full[hb]);
 #pragma unroll
-            for (int t = 0; t < 5; t++) {
+                for (int t = 0; t < 5; t++) {
 #pragma unroll
-                for (int ks = 0; ks < BK / UK; ks++) {
-                    const uint64_t da = smem_desc(sa + REST_A[t] * PLANE_TILE + ks * A_STEP, A_LBO, 1024);
-                    const uint64_t db = smem_desc(sb + REST_B[t] * S::B_PLANE + ks * B_STEP, B_LBO, 1024);
-                    umma_bf16(d_rest, da, db, idesc, (kt | t | ks) != 0);
+                    for (int ks = 0; ks < BK / UK; ks++) {
+                        const uint64_t da = smem_desc(sa + REST_A[t] * PLANE_TILE + ks * A_STEP, A_LBO, 1024);
+                        const uint64_t db = smem_desc(sb + REST_B[t] * S::B_PLANE + ks * B_STEP, B_LBO, 1024);
+                        umma_bf16(d_rest, da, db, idesc, (kt | t | ks) != 0);
+                    }
                 }
+                umma_commit(&empty[s]);
+                if (kt == nk - 1) umma_commit(&rest_full[rb]);
             }
-            umma_commit(&empty[s]);
-            if (kt == nk - 1) umma_commit(rest_full);
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
         constexpr int CPW = BN / 2;                       // columns per warp (the two halves split N)
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * CPW);
-        float acc[CPW];
+        // pointer arithmetic on the __shared__ array itself, so that the compiler keeps the address space (LDS / STS)
+        const uint32_t raw_addr = smem_u32(smem_raw);
+        float* xpose = reinterpret_cast<float*>(smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr) + S::XPOSE_OFF) + (warp - 4) * 32 * 32;
+        float4* xpose4 = reinterpret_cast<float4*>(xpose);
+        int g = 0, t_local = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t_local++) {
+            const int64_t m0 = (tile / ntn) * TILE, n0 = (tile % ntn) * BN;
+            const int rb = t_local & 1;
+            float acc[CPW];
 #pragma unroll
-        for (int i = 0; i < CPW; i++) acc[i] = 0.f;
-        for (int kt = 0; kt < nk; kt++) {
-            const int hb = kt & 1;
-            mbar_wait(&hh_full[hb], (kt >> 1) & 1);
+            for (int i = 0; i < CPW; i++) acc[i] = 0.f;
+            for (int kt = 0; kt < nk; kt++, g++) {
+                const int hb = g & 1;
+                mbar_wait(&hh_full[hb], (g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int gg = 0; gg < CPW / 32; gg++) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + (uint32_t)(hb * BN + gg * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[gg * 32 + i] += __uint_as_float(v[i]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hh_empty[hb]);
+            }
+            mbar_wait(&rest_full[rb], (t_local >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < CPW / 32; g++) {
+            for (int gg = 0; gg < CPW / 32; gg++) {
                 uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(hb * BN + g * 32), v);
+                tmem_ld32(lane_base + (uint32_t)((2 + rb) * BN + gg * 32), v);
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc[g * 32 + i] += __uint_as_float(v[i]);
+                for (int i = 0; i < 32; i++) acc[gg * 32 + i] += __uint_as_float(v[i]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&hh_empty[hb]);
-        }
-        mbar_wait(rest_full, 0);
-        tc_fence_after();
-        // every MMA has completed: the stage buffers are dead, reuse them for the per-warp transpose (33-float rows)
-        float* xpose = reinterpret_cast<float*>(smem) + (warp - 4) * 32 * 33;
-        const int64_t row = m0 + q * 32 + lane;
+            if (lane == 0) mbar_arrive(&rest_empty[rb]);     // the accumulator is in registers: the MMA thread may reuse it
+            const int64_t row = m0 + q * 32 + lane;
 #pragma unroll
-        for (int g = 0; g < CPW / 32; g++) {
-            uint32_t v[32];
-            const int col0 = half * CPW + g * 32;
-            tmem_ld32(lane_base + (uint32_t)(2 * BN + g * 32), v);
+            for (int gg = 0; gg < CPW / 32; gg++) {
+                const int col0 = half * CPW + gg * 32;
+                if constexpr (OUT_T) {
+                    if (row < m) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[g * 32 + i] += __uint_as_float(v[i]);
-            if constexpr (OUT_T) {
-                if (row < m) {
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const int64_t cn = n0 + col0 + i;
-                        if (cn < n) C[cn * ldc + row] = (TC)acc[g * 32 + i];
+                        for (int i = 0; i < 32; i++) {
+                            const int64_t cn = n0 + col0 + i;
+                            if (cn < n) C[cn * ldc + row] = (TC)acc[gg * 32 + i];
+                        }
                     }
-                }
-            } else {
+                } else {
+                    // lane = row writes its 32 columns as eight 16-byte chunks, chunk j at slot j ^ (row & 7): conflict-free
+                    // both for these stores and for the row-segment loads below
 #pragma unroll
-                for (int i = 0; i < 32; i++) xpose[lane * 33 + i] = acc[g * 32 + i];
-                __syncwarp();
-                const int64_t cn = n0 + col0 + lane;
+                    for (int j = 0; j < 8; j++)
+                        xpose4[lane * 8 + (j ^ (lane & 7))] =
+                            make_float4(acc[gg * 32 + 4 * j], acc[gg * 32 + 4 * j + 1], acc[gg * 32 + 4 * j + 2], acc[gg * 32 + 4 * j + 3]);
+                    __syncwarp();
+                    const bool interior = m0 + TILE <= m && n0 + BN <= n;
+                    if (std::is_same<TC, float>::value && interior && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+                        // a quarter-warp writes one 128-byte row segment, the warp four rows per instruction
+                        const int c4 = lane & 7;
+                        float* crow = reinterpret_cast<float*>(C) + (m0 + q * 32 + (lane >> 3)) * ldc + n0 + col0 + 4 * c4;
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) {
+                            const int r = jj * 4 + (lane >> 3);
+                            const float4 v = xpose4[r * 8 + (c4 ^ (r & 7))];
+                            __stcs(reinterpret_cast<float4*>(crow), v);
+                            crow += 4 * ldc;
+                        }
+                    } else {
+                        const int64_t cn = n0 + col0 + lane;
+                        const int chunk = lane >> 2, within = lane & 3;
 #pragma unroll 4
-                for (int r = 0; r < 32; r++) {
-                    const int64_t rr = m0 + q * 32 + r;
-                    if (rr < m && cn < n) C[rr * ldc + cn] = (TC)xpose[r * 33 + lane];
+                        for (int r = 0; r < 32; r++) {
+                            const int64_t rr = m0 + q * 32 + r;
+                            if (rr < m && cn < n) C[rr * ldc + cn] = (TC)xpose[r * 32 + ((chunk ^ (r & 7)) << 2) + within];
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
@@ -1020,7 +1074,8 @@ static int launch_gemm(ndmps_ctx* ctx, const CUtensorMap& ma, const CUtensorMap&
     using S = GemmSmem<BN, STAGES>;
     auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, OUT_T, TC>;
     NDMPS_TRY(raise_dynamic_smem((const void*)kern, ctx->device, S::TOTAL));
-    dim3 grid((unsigned)((m + TILE - 1) / TILE), (unsigned)((n + BN - 1) / BN));
+    const int64_t tiles = ((m + TILE - 1) / TILE) * ((n + BN - 1) / BN);
+    const unsigned grid = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);      // one persistent CTA per SM
     kern<<<grid, THREADS, S::TOTAL, ctx->stream>>>(ma, mb, m, n, k, c, ldc);
     NDMPS_LAUNCH_CHECK(ctx);
     ctx->tc_launches++;
@@ -1063,16 +1118,11 @@ int gemm_tc(ndmps_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const
             else NDMPS_TRY((launch_gemm<BN, ST, AMN, BMN, false, double>(ctx, ma, mb, m, n, k, (double*)c, ldc)));             \
         }                                                                                                                      \
     } while (0)
-    if (k <= BK && n > 64 && !a_mn && b_mn && ctx->opt_tc_single_k) {
-        // one k-tile per output tile (the final contraction dense = X W, k = bond): nothing to pipeline inside a CTA, so
-        // 128 x 64 tiles with ONE stage (73 KB, 256 TMEM columns, 80 registers) put two CTAs on an SM and the load /
-        // MMA / drain phases of neighbours overlap
-        NDMPS_TC_GO(64, 1, false, true);
-    } else if (bn == 64) {
-        if (a_mn && !b_mn) NDMPS_TC_GO(64, 3, true, false);
-        else if (!a_mn && b_mn) NDMPS_TC_GO(64, 3, false, true);
-        else if (!a_mn && !b_mn) NDMPS_TC_GO(64, 3, false, false);
-        else NDMPS_TC_GO(64, 3, true, true);
+    if (bn == 64) {
+        if (a_mn && !b_mn) NDMPS_TC_GO(64, 2, true, false);
+        else if (!a_mn && b_mn) NDMPS_TC_GO(64, 2, false, true);
+        else if (!a_mn && !b_mn) NDMPS_TC_GO(64, 2, false, false);
+        else NDMPS_TC_GO(64, 2, true, true);
     } else {
         if (a_mn && !b_mn) NDMPS_TC_GO(128, 2, true, false);
         else if (!a_mn && b_mn) NDMPS_TC_GO(128, 2, false, true);
