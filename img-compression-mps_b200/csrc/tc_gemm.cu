@@ -263,6 +263,26 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t desc_a, uint64
         : "memory");
 }
 
+// The digit products of one k-step.  A_p . B_q^T belongs to accumulator p + q, the accumulators are consecutive blocks of
+// 64 TMEM columns and the B digit planes are consecutive 64-row blocks of shared memory, so for a fixed p the products
+// with q = 0 .. 4 - p are ONE MMA of N = 64 (5 - p) on the stacked planes into columns [64 p, 320): six instructions
+// instead of fifteen (N <= 256 splits p = 0 in two), and every A plane is fetched from shared memory once or twice instead
+// of 5 - p times - the operand fetch, not the arithmetic, bounded the 15-instruction form (tensor pipe 50 % active).
+// `first` = these are the first products of an accumulator chain (p = 0 writes every accumulator first).
+template <class DescA>
+__device__ __forceinline__ void digit_products(uint32_t tmem_base, DescA desc_a, uint32_t b_planes, int ks, uint32_t idesc_flags, bool first) {
+    const uint32_t i64 = instr_desc_i8(TILE, 64) | idesc_flags, i128 = instr_desc_i8(TILE, 128) | idesc_flags;
+    const uint32_t i192 = instr_desc_i8(TILE, 192) | idesc_flags, i256 = instr_desc_i8(TILE, 256) | idesc_flags;
+    const uint64_t b0 = smem_desc_sw64(b_planes + ks * 32);                        // planes 0 .. (N / 64 - 1)
+    const uint64_t b4 = smem_desc_sw64(b_planes + 4 * I8_BOX_BYTES + ks * 32);     // plane 4 alone
+    umma_i8(tmem_base, desc_a(0), b0, i256, first ? 0u : 1u);                      // s = 0 .. 3
+    umma_i8(tmem_base + 4 * I8_TN, desc_a(0), b4, i64, first ? 0u : 1u);           // s = 4
+    umma_i8(tmem_base + 1 * I8_TN, desc_a(1), b0, i256, 1u);                       // s = 1 .. 4
+    umma_i8(tmem_base + 2 * I8_TN, desc_a(2), b0, i192, 1u);                       // s = 2 .. 4
+    umma_i8(tmem_base + 3 * I8_TN, desc_a(3), b0, i128, 1u);                       // s = 3, 4
+    umma_i8(tmem_base + 4 * I8_TN, desc_a(4), b0, i64, 1u);                        // s = 4
+}
+
 // tile t -> (row tile of 128, column tile of 64) over the tiles that touch the upper triangle: tj >= 2 ti
 __device__ __forceinline__ void upper_tile_i8(int t, int ntc, int& ti, int& tj) {
     int row = 0, left = t;
@@ -417,7 +437,6 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int ntc, int m, int64_t 
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer ----
-        constexpr uint32_t idesc = instr_desc_i8(TILE, I8_TN);
         for (int kt = 0; kt < nk; kt++) {
             const int s = kt % GramI8Smem::STAGES;
             const int chain = kt / I8_MAX_CHAIN_TILES, within = kt - chain * I8_MAX_CHAIN_TILES;
@@ -429,19 +448,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map, int ntc, int m, int64_t 
             tc_fence_after();
             const uint32_t st = smem_u32(smem + s * GramI8Smem::STAGE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
-#pragma unroll
-                for (int p = 0; p < I8_PLANES; p++) {
-#pragma unroll
-                    for (int q = 0; q < I8_PLANES; q++) {
-                        if (p + q >= I8_PLANES) continue;
-                        const uint64_t da = smem_desc_sw64(st + (2 * p) * I8_BOX_BYTES + ks * 32);
-                        const uint64_t db = smem_desc_sw64(st + GramI8Smem::A_BYTES + q * I8_BOX_BYTES + ks * 32);
-                        // the first product into each accumulator of a chain overwrites: (0, s) comes first for every s
-                        umma_i8(tmem_base + (uint32_t)((p + q) * I8_TN), da, db, idesc, !(within == 0 && ks == 0 && p == 0));
-                    }
-                }
-            }
+            for (int ks = 0; ks < I8_BK / I8_UK; ks++)
+                digit_products(tmem_base, [&](int p) { return smem_desc_sw64(st + (2 * p) * I8_BOX_BYTES + ks * 32); },
+                               st + GramI8Smem::A_BYTES, ks, 0u, within == 0 && ks == 0);
             umma_commit(&empty[s]);
             if (within == I8_MAX_CHAIN_TILES - 1 || kt == nk - 1) umma_commit(acc_full);
         }
@@ -578,26 +587,16 @@ proj_i8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant_
             }
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = instr_desc_i8(TILE, I8_TN) | (1u << 15);        // A is MN-major
-        for (int kt = 0; kt < nk; kt++) {
+        for (int kt = 0; kt < nk; kt++) {                                           // A is MN-major: bit 15 of the descriptor
             const int s = kt % ProjI8Smem::STAGES;
             mbar_wait(&full[s], (kt / ProjI8Smem::STAGES) & 1);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + s * ProjI8Smem::STAGE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < I8_BK / I8_UK; ks++) {
-#pragma unroll
-                for (int p = 0; p < I8_PLANES; p++) {
-#pragma unroll
-                    for (int q = 0; q < I8_PLANES; q++) {
-                        if (p + q >= I8_PLANES) continue;
-                        // A: 32 k-rows of 128 bytes per k-step (4096 B), 8-row groups 1024 B apart, one 128-byte atom along c
-                        const uint64_t da = smem_desc(st + p * ProjI8Smem::A_PLANE + ks * 4096, 8192, 1024);
-                        const uint64_t db = smem_desc_sw64(st + ProjI8Smem::A_BYTES + q * I8_BOX_BYTES + ks * 32);
-                        umma_i8(tmem_base + (uint32_t)((p + q) * I8_TN), da, db, idesc, !(kt == 0 && ks == 0 && p == 0));
-                    }
-                }
-            }
+            for (int ks = 0; ks < I8_BK / I8_UK; ks++)
+                // A: 32 k-rows of 128 bytes per k-step (4096 B), 8-row groups 1024 B apart, one 128-byte atom along c
+                digit_products(tmem_base, [&](int p) { return smem_desc(st + p * ProjI8Smem::A_PLANE + ks * 4096, 8192, 1024); },
+                               st + ProjI8Smem::A_BYTES, ks, 1u << 15, kt == 0 && ks == 0);
             umma_commit(&empty[s]);
             if (kt == nk - 1) umma_commit(acc_full);
         }
