@@ -613,6 +613,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for --impl ours")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner / debug lines stay off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
