@@ -265,7 +265,22 @@ int ndmps_ctx_destroy(ndmps_ctx_t* ctx) {
 
 int ndmps_ctx_set_stream(ndmps_ctx_t* ctx, void* cuda_stream) {
     NDMPS_REQUIRE(ctx != nullptr, "ndmps_ctx_set_stream: ctx is NULL");
-    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t next = static_cast<cudaStream_t>(cuda_stream);
+    if (next != ctx->stream) {
+        // one context = one workspace arena, reused call after call in stream order: work still queued on the old stream
+        // may be reading it, so the new stream starts behind everything the old one has been given
+        cudaEvent_t ev = nullptr;
+        NDMPS_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (cudaEventRecord(ev, ctx->stream) == cudaSuccess) {
+            cudaError_t e = cudaStreamWaitEvent(next, ev, 0);
+            cudaEventDestroy(ev);
+            NDMPS_CUDA_TRY(e);
+        } else {                                         // the old stream no longer exists: nothing of it can be pending
+            cudaGetLastError();
+            cudaEventDestroy(ev);
+        }
+        ctx->stream = next;
+    }
     return NDMPS_OK;
 }
 

@@ -58,6 +58,8 @@ int         ndmps_version(void);
 const char* ndmps_last_error(void);
 int ndmps_ctx_create(ndmps_ctx_t** out);
 int ndmps_ctx_destroy(ndmps_ctx_t* ctx);
+/* One context = one stream at a time = one workspace arena reused in stream order.  Changing the stream makes the new
+ * one wait (event) for everything already queued on the old one. */
 int ndmps_ctx_set_stream(ndmps_ctx_t* ctx, void* cuda_stream);
 int ndmps_ctx_sync(ndmps_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
