@@ -34,6 +34,7 @@ namespace topk {
 // reduction then sits on half as many SMs, which leaves room for the register-hungry Gram / GEMM CTAs of the
 // other volumes in flight (batch throughput +8 %)
 constexpr int TDT = 512;
+constexpr int MID_NT = 352;   // threads per CTA of the 1024 < n <= 1536 register-resident reduction
 constexpr int NMAX = 4096; // largest matrix of this path (registers up to 1024, L2-resident working copy beyond)
 constexpr int BIS = 128;   // shifts per pass and eigenvalue in the bisection
 
@@ -75,16 +76,17 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// sum over the CTA's 16 warps, same value (bitwise) in every thread; one __syncthreads; the partial sums are added
+// sum over the CTA's NW warps, same value (bitwise) in every thread; one __syncthreads; the partial sums are added
 // as a tree (4 dependent adds)
+template <int NW = TDT / 32>
 __device__ __forceinline__ double block_sum_all(double v, double* scratch) {
-    static_assert(TDT == 512, "16 warps");
+    static_assert(NW <= 16, "at most 16 warps");
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     double s[16];
 #pragma unroll
-    for (int w = 0; w < 16; w++) s[w] = scratch[w];
+    for (int w = 0; w < 16; w++) s[w] = w < NW ? scratch[w] : 0.0;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
@@ -151,15 +153,17 @@ __device__ __forceinline__ void fused_pass(double (&a)[RPW][NEQ], const double* 
 // by symmetry each CTA already holds for its own rows) and the column ends in the hardware cluster barrier
 // instead of an L2 atomic + poll + reload.  Measured: 2.50 -> 2.28 ms per n = 512 problem (profiles/r02_summary.md
 // has the per-phase cycle counts and the two restructurings that did NOT pay).
-template <int NEQ, int RPW, bool CL>
-__global__ void __launch_bounds__(TDT)
+// NT threads per CTA: 512 up to n = 1024; 352 (11 warps, one 48-chunk row each, up to 186 registers) for
+// 1024 < n <= 1536, where ceil(n / 11) <= 140 CTAs put the whole matrix into the register files of the chip.
+template <int NEQ, int RPW, bool CL, int NT>
+__global__ void __launch_bounds__(NT)
 tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict__ V, double* __restrict__ tau_g,
                double* __restrict__ d_g, double* __restrict__ e_g, double* pbuf, double* rowbuf, unsigned* ctrl) {
     __shared__ double ub0[32 * NEQ], ub1[32 * NEQ], wv[32 * NEQ];
-    __shared__ double red0[TDT / 32], red1[TDT / 32];
+    __shared__ double red0[NT / 32], red1[NT / 32];
     __shared__ double s_alpha;
     __shared__ double2 pcol[CL ? 2 * 32 * NEQ : 1];                                  // (p_k, A[k][pivot]) of both parities
-    constexpr int KM = (32 * NEQ) / TDT > 0 ? (32 * NEQ) / TDT : 1;                 // vector elements per thread
+    constexpr int KM = (32 * NEQ + NT - 1) / NT;                 // vector elements per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x, C = gridDim.x;
     // this warp's RPW rows, held in registers: lane l has columns l + 32 q.  Row t of the warp is row
     // (t * warps + warp) * C + cta of the matrix (cyclic over CTAs first, so live rows stay spread to the end)
@@ -167,14 +171,14 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
     double a[RPW][NEQ];
 #pragma unroll
     for (int t = 0; t < RPW; t++) {
-        gi[t] = (t * (TDT / 32) + warp) * C + cta;
+        gi[t] = (t * (NT / 32) + warp) * C + cta;
 #pragma unroll
         for (int q = 0; q < NEQ; q++) {
             const int k = lane + 32 * q;
             a[t][q] = (gi[t] < n && k < n) ? G[(size_t)gi[t] * n + k] : 0.0;
         }
     }
-    for (int c = tid; c < 32 * NEQ; c += TDT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
+    for (int c = tid; c < 32 * NEQ; c += NT) { ub0[c] = 0.0; ub1[c] = 0.0; wv[c] = 0.0; }
     double* u = ub0;
     double* un = ub1;
     double tau = 0.0;
@@ -188,7 +192,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         if (jn == 0) {
 #pragma unroll
             for (int m = 0; m < KM; m++) {
-                const int k = tid + m * TDT;
+                const int k = tid + m * NT;
                 r[m] = k < n ? G[k] : 0.0;
             }
         } else {
@@ -198,7 +202,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
                 const double2* pc = pcol + (par ^ 1) * 32 * NEQ;
 #pragma unroll
                 for (int m = 0; m < KM; m++) {
-                    const int k = tid + m * TDT;
+                    const int k = tid + m * NT;
                     const bool on = k >= jn && k < n;
                     const double2 v = on ? pc[k] : make_double2(0.0, 0.0);
                     pf[m] = v.x;
@@ -210,7 +214,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
                 const double* rb = rowbuf + (size_t)(par ^ 1) * n;
 #pragma unroll
                 for (int m = 0; m < KM; m++) {
-                    const int k = tid + m * TDT;
+                    const int k = tid + m * NT;
                     const bool on = k >= jn && k < n;
                     pf[m] = on ? __ldcg(pb + k) : 0.0;
                     rj[m] = on ? __ldcg(rb + k) : 0.0;
@@ -219,15 +223,15 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
             }
             double part = 0.0;
 #pragma unroll
-            for (int m = 0; m < KM; m++) part = fma(pf[m], u[tid + m * TDT], part);
+            for (int m = 0; m < KM; m++) part = fma(pf[m], u[tid + m * NT], part);
             PROF_MARK(0);
-            const double s = block_sum_all(part, red0);
+            const double s = block_sum_all<NT / 32>(part, red0);
             PROF_MARK(1);
             const double K = -0.5 * tau * tau * s;
             const double wj = fma(tau, pj, K);           // u[jn] = 1
 #pragma unroll
             for (int m = 0; m < KM; m++) {
-                const int k = tid + m * TDT;
+                const int k = tid + m * NT;
                 r[m] = 0.0;
                 if (k >= jn && k < n) {
                     const double uk = u[k];
@@ -239,7 +243,7 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         }
 #pragma unroll
         for (int m = 0; m < KM; m++) {
-            const int k = tid + m * TDT;
+            const int k = tid + m * NT;
             if (k == jn && cta == 0) d_g[jn] = r[m];
             if (k == jn + 1) s_alpha = r[m];
         }
@@ -259,11 +263,11 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         double part = 0.0;
 #pragma unroll
         for (int m = 0; m < KM; m++) {
-            const int k = tid + m * TDT;
+            const int k = tid + m * NT;
             if (k >= jn + 2 && k < n) part = fma(r[m], r[m], part);
         }
         PROF_MARK(2);
-        const double sigma = block_sum_all(part, red1);  // the barrier inside also publishes s_alpha and wv
+        const double sigma = block_sum_all<NT / 32>(part, red1);  // the barrier inside also publishes s_alpha and wv
         PROF_MARK(3);
         const double alpha = s_alpha;
         double beta = alpha, taun = 0.0, scal = 0.0;
@@ -275,9 +279,9 @@ tridiag_kernel(const double* __restrict__ G, int n, int ldv, double* __restrict_
         }
 #pragma unroll
         for (int m = 0; m < KM; m++) {
-            const int k = tid + m * TDT;
+            const int k = tid + m * NT;
             const double v = k == jn + 1 ? 1.0 : ((k >= jn + 2 && k < n) ? r[m] * scal : 0.0);
-            un[k] = v;
+            if (k < 32 * NEQ) un[k] = v;
             if (cta == jn % C && k < ldv) V[(size_t)jn * ldv + k] = v;   // the pad element of an odd n too: rows are read in 16-byte chunks
         }
         if (cta == 0 && tid == 0) { e_g[jn] = beta; tau_g[jn] = taun; }
@@ -1119,11 +1123,13 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     *done = false;
     if (n64 < 96 || n64 > NMAX || k64 < 1 || k64 > 128 || 2 * k64 > n64) return NDMPS_OK;
     const int n = (int)n64, m = (int)k64;
-    const bool big = n > 1024;
+    // 1024 < n <= 1536: still register-resident, 11 warps x one row per CTA, if that many CTAs fit the device
+    const bool mid = n > 1024 && n <= 1536 && (n + MID_NT / 32 - 1) / (MID_NT / 32) <= ctx->sm_count && ctx->opt_topk_mid;
+    const bool big = n > 1024 && !mid;
     // register route: RPW rows per warp.  Two rows per warp up to n = 512 (the row pair still fits the register
     // file) halve the SMs a reduction sits on, which is what the other volumes in flight need
     const int rpw = (n <= 512 && !ctx->opt_topk_one_row) ? 2 : 1;
-    const int C = big ? ctx->sm_count : (n + rpw * (TDT / 32) - 1) / (rpw * (TDT / 32));
+    const int C = big ? ctx->sm_count : (mid ? (n + MID_NT / 32 - 1) / (MID_NT / 32) : (n + rpw * (TDT / 32) - 1) / (rpw * (TDT / 32)));
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
     const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
@@ -1182,7 +1188,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
             // one cluster of 2^x CTAs (CTAs past the last row only take part in the barriers)
             int cc = 1;
             while (cc < C) cc *= 2;
-            const void* cfn = (const void*)tridiag_kernel<16, 2, true>;
+            const void* cfn = (const void*)tridiag_kernel<16, 2, true, TDT>;
             bool fits = false;
             NDMPS_TRY(cluster_fits(cfn, ctx->device, cc, TDT, &fits));
             if (fits) {
@@ -1203,9 +1209,13 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
             }
         }
         if (!clustered) {
-            void* fn = n <= 512 ? (rpw == 2 ? (void*)tridiag_kernel<16, 2, false> : (void*)tridiag_kernel<16, 1, false>)
-                                : (void*)tridiag_kernel<32, 1, false>;
-            NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
+            if (n > 1024) {
+                NDMPS_TRY(coop_launch(ctx, (const void*)tridiag_kernel<48, 1, false, MID_NT>, dim3(C), dim3(MID_NT), args, 0));
+            } else {
+                void* fn = n <= 512 ? (rpw == 2 ? (void*)tridiag_kernel<16, 2, false, TDT> : (void*)tridiag_kernel<16, 1, false, TDT>)
+                                    : (void*)tridiag_kernel<32, 1, false, TDT>;
+                NDMPS_TRY(coop_launch(ctx, fn, dim3(C), dim3(TDT), args, 0));
+            }
         }
 #ifdef NDMPS_TOPK_PROF
         {
