@@ -347,6 +347,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "eig_topk")) ctx->opt_eig_topk = value;
     else if (!strcmp(name, "topk_one_row")) ctx->opt_topk_one_row = value;
     else if (!strcmp(name, "topk_cluster")) ctx->opt_topk_cluster = value;
+    else if (!strcmp(name, "tc_waves")) ctx->opt_tc_waves = value;
     else if (!strcmp(name, "topk_mid")) ctx->opt_topk_mid = value;
     else if (!strcmp(name, "topk_bt_pairs")) ctx->opt_topk_bt_pairs = value;
     else if (!strcmp(name, "topk_big_ctas")) ctx->opt_topk_big_ctas = value;

@@ -166,6 +166,7 @@ struct ndmps_ctx {
     int64_t opt_eig_topk = 1;             // bond cap set: leading-eigenpair solver (eig_topk.cu) instead of the full one
     int64_t opt_topk_cluster = 1;         // 1: n <= 512 tridiagonalisation as one thread-block cluster (exchange through distributed shared memory)
     int64_t cluster_launches = 0;
+    int64_t opt_tc_waves = 1;             // waves of gram_i8 CTAs (split-K factor = waves x SMs / tiles)
     int64_t opt_topk_mid = 1;             // 1: 1024 < n <= 1536 tridiagonalisation stays in the register files (140 CTAs x 11 warps)
     int64_t opt_topk_bt_pairs = 1;        // 1: back-transformation applies the reflectors in pairs (one reduction per pair)
     int64_t opt_topk_one_row = 0;         // 1: one matrix row per warp in the register-resident reduction (default: two up to n = 512)

@@ -997,7 +997,9 @@ int gram_tc(ndmps_ctx* ctx, const void* mat, int64_t rows, int64_t cols, int64_t
     const int m = (int)rows, ntr = (m + TILE - 1) / TILE, ntc = (m + I8_TN - 1) / I8_TN;
     int ntiles = 0;
     for (int ti = 0; ti < ntr; ti++) ntiles += ntc - 2 * ti > 0 ? ntc - 2 * ti : 0;
-    int64_t splits = (int64_t)ctx->sm_count / ntiles;          // whole waves of one CTA per SM
+    // one CTA per SM and wave; more than one wave of shorter CTAs packs better beside the eigen-solver CTAs of the other
+    // volumes in flight (option tc_waves)
+    int64_t splits = (int64_t)ctx->sm_count * (ctx->opt_tc_waves > 0 ? ctx->opt_tc_waves : 1) / ntiles;
     if (splits < 1) splits = 1;
     int64_t k_per = (cols + splits - 1) / splits;
     k_per = ((k_per + I8_BK - 1) / I8_BK) * I8_BK;
