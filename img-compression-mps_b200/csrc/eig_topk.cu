@@ -748,12 +748,16 @@ combine_rows_kernel(const double* __restrict__ Cf, int64_t crs, int64_t ccs, con
 // back to the full solver) and regularised so the kernel terminates.  The inverse is then one
 // forward substitution per column, four accumulators deep.
 __global__ void __launch_bounds__(128)
-chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Linv, int* __restrict__ info) {
+chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Linv, int* __restrict__ info, double* __restrict__ Yg) {
+    // Yg == nullptr: both m x (m + 1) matrices live in shared memory (m <= ~118).  Otherwise (m up to 128) only Lm does:
+    // the series path keeps E^2 in the global scratch Yg (m x m; independent loads), the Cholesky path inverts L in place.
     extern __shared__ double sm[];
     double* Lm = sm;                         // m x (m + 1), lower triangle = L
-    double* Y = sm + (size_t)m * (m + 1);    // m x (m + 1)
+    double* Y = Yg ? Yg : sm + (size_t)m * (m + 1);
+    const int ldy = Yg ? m : m + 1;
     __shared__ int s_bad;
     __shared__ double diag0[128];
+    __shared__ double s_piv;
     const int tid = threadIdx.x, ld = m + 1;
     if (tid == 0) s_bad = 0;
     double dev = 0.0;                                    // max |S - I|
@@ -782,14 +786,14 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
             const int r = e / m, c = e - r * m;
             double acc = 0.0;
             for (int q = 0; q < m; q++) acc = fma(Lm[r * ld + q], Lm[q * ld + c], acc);
-            Y[r * ld + c] = acc;
+            Y[r * ldy + c] = acc;
         }
         __syncthreads();
         for (int e = tid; e < m * m; e += 128) {          // Linv = I - E/2 + 3/8 E^2 - 5/16 E E^2
             const int r = e / m, c = e - r * m;
             double acc = 0.0;
-            for (int q = 0; q < m; q++) acc = fma(Lm[r * ld + q], Y[q * ld + c], acc);
-            Linv[e] = (r == c ? 1.0 : 0.0) - 0.5 * Lm[r * ld + c] + 0.375 * Y[r * ld + c] - 0.3125 * acc;
+            for (int q = 0; q < m; q++) acc = fma(Lm[r * ld + q], Y[q * ldy + c], acc);
+            Linv[e] = (r == c ? 1.0 : 0.0) - 0.5 * Lm[r * ld + c] + 0.375 * Y[r * ldy + c] - 0.3125 * acc;
         }
         return;
     }
@@ -813,9 +817,9 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
             for (; q < j; q++) v0 = fma(lr[q], lj[q], v0);
         }
         const double mine = (r >= j && r < m) ? Lm[r * ld + j] - ((v0 + v1) + (v2 + v3)) : 0.0;
-        if (r == j) Y[0] = mine;                          // pivot candidate
+        if (r == j) s_piv = mine;                         // pivot candidate
         __syncthreads();
-        double piv = Y[0];
+        double piv = s_piv;
         const double floor_j = 2.220446049250313e-16 * m * diag0[j];
         if (!(piv > floor_j)) {
             if (tid == 0) s_bad++;
@@ -825,6 +829,36 @@ chol_inverse_kernel(const double* __restrict__ S, int m, double* __restrict__ Li
         if (r == j) Lm[r * ld + j] = piv * inv_root;
         else if (r > j && r < m) Lm[r * ld + j] = mine * inv_root;
         __syncthreads();
+    }
+    if (Yg) {
+        // in place, row by row: X[i][j] = -(1 / L[i][i]) sum_{q = j}^{i - 1} L[i][q] X[q][j]; rows above i already hold X,
+        // row i still holds L.  Thread j owns column j (conflict-free column reads, broadcast row reads).
+        for (int i = 0; i < m; i++) {
+            const double inv_ii = rcp_fast(Lm[i * ld + i]);
+            double x = 0.0;
+            if (tid < i) {
+                double a0 = 0.0, a1 = 0.0;
+                const double* li = Lm + i * ld;
+                int q = tid;
+                for (; q + 1 < i; q += 2) {
+                    a0 = fma(li[q], Lm[q * ld + tid], a0);
+                    a1 = fma(li[q + 1], Lm[(q + 1) * ld + tid], a1);
+                }
+                if (q < i) a0 = fma(li[q], Lm[q * ld + tid], a0);
+                x = -(a0 + a1) * inv_ii;
+            } else if (tid == i) {
+                x = inv_ii;
+            }
+            __syncthreads();
+            if (tid <= i) Lm[i * ld + tid] = x;
+            __syncthreads();
+        }
+        for (int e = tid; e < m * m; e += 128) {
+            const int rr = e / m, c = e - rr * m;
+            Linv[e] = c <= rr ? Lm[rr * ld + c] : 0.0;
+        }
+        if (tid == 0) atomicAdd(info, s_bad);
+        return;
     }
     // column c of Y = L^-1 e_c by forward substitution, one thread per column
     if (tid < m) {
@@ -1102,10 +1136,14 @@ finish_kernel(const double* __restrict__ G, int n, const double* __restrict__ he
     }
 }
 
-static int orthonormalise(ndmps_ctx* ctx, const double* Xin, int m, int n, double* S, double* Linv, int* info, double* Xout) {
+// two m x (m + 1) float64 matrices in shared memory while they fit; beyond that one, with a global scratch (chol_inverse_kernel)
+static inline bool chol_two_buffers(const ndmps_ctx* ctx, int m) { return (size_t)2 * m * (m + 1) * sizeof(double) + 4096 <= ctx->smem_optin; }
+
+static int orthonormalise(ndmps_ctx* ctx, const double* Xin, int m, int n, double* S, double* Linv, int* info, double* Xout, double* Yg) {
     rows_dot_kernel<<<m, 256, (size_t)n * sizeof(double), ctx->stream>>>(Xin, Xin, m, n, S);
     NDMPS_LAUNCH_CHECK(ctx);
-    chol_inverse_kernel<<<1, 128, (size_t)2 * m * (m + 1) * sizeof(double), ctx->stream>>>(S, m, Linv, info);
+    const bool two = chol_two_buffers(ctx, m);
+    chol_inverse_kernel<<<1, 128, (size_t)(two ? 2 : 1) * m * (m + 1) * sizeof(double), ctx->stream>>>(S, m, Linv, info, two ? nullptr : Yg);
     NDMPS_LAUNCH_CHECK(ctx);
     combine_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8)), 128, 0, ctx->stream>>>(Linv, m, 1, Xin, m, n, Xout);
     NDMPS_LAUNCH_CHECK(ctx);
@@ -1131,7 +1169,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     const int rpw = (n <= 512 && !ctx->opt_topk_one_row) ? 2 : 1;
     const int C = big ? ctx->sm_count : (mid ? (n + MID_NT / 32 - 1) / (MID_NT / 32) : (n + rpw * (TDT / 32) - 1) / (rpw * (TDT / 32)));
     const size_t smem_iv = (size_t)6 * n * sizeof(double) + (size_t)n + 16;
-    const size_t smem_ch = (size_t)2 * m * (m + 1) * sizeof(double);
+    const size_t smem_ch = (size_t)(chol_two_buffers(ctx, m) ? 2 : 1) * m * (m + 1) * sizeof(double);
     if (smem_ch + 2048 > ctx->smem_optin) return NDMPS_OK;
     {   // fixed ceilings, set once per device: contexts on several host threads share these function attributes
         const int ceiling = (int)ctx->smem_optin - 2048;
@@ -1155,6 +1193,8 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * n, &Xb));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &S));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &Linv));
+    double* Yg = nullptr;
+    NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &Yg));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * n, &TQ));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m * m, &H));
     NDMPS_TRY(ctx->ws.get<double>((size_t)m, &hev));
@@ -1240,10 +1280,10 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
     for (int it = 0; it < iters; it++) {
         invit_kernel<<<m, 32, smem_iv, ctx->stream>>>(d, e, n, lam, bounds, rhs, Xa, factors, it > 0 ? 1 : 0);
         NDMPS_LAUNCH_CHECK(ctx);
-        NDMPS_TRY(orthonormalise(ctx, Xa, m, n, S, Linv, info, Xb));
+        NDMPS_TRY(orthonormalise(ctx, Xa, m, n, S, Linv, info, Xb, Yg));
         rhs = Xb;
     }
-    NDMPS_TRY(orthonormalise(ctx, Xb, m, n, S, Linv, info, Xa));       // Q = Xa
+    NDMPS_TRY(orthonormalise(ctx, Xb, m, n, S, Linv, info, Xa, Yg));       // Q = Xa
     // 4. Rayleigh-Ritz on span(Q)
     tridiag_apply_kernel<<<(unsigned)(((int64_t)m * n + 255) / 256), 256, 0, ctx->stream>>>(d, e, Xa, m, n, TQ);
     NDMPS_LAUNCH_CHECK(ctx);
@@ -1300,7 +1340,7 @@ int ndmps_eigh_topk(ndmps_ctx_t* ctx, const double* a_dev, int64_t n, int64_t k,
     bool done = false;
     NDMPS_TRY(eigh_topk(ctx, a_dev, n, k, evals_dev, evecs_dev, k, &done));
     if (!done) {
-        set_error("ndmps_eigh_topk: shape n = %lld, k = %lld is outside the leading-eigenpair path (96 <= n <= 4096, 2k <= n, k <= ~100)",
+        set_error("ndmps_eigh_topk: shape n = %lld, k = %lld is outside the leading-eigenpair path (96 <= n <= 4096, 2k <= n, k <= 128)",
                   (long long)n, (long long)k);
         return NDMPS_ERR_INVALID;
     }

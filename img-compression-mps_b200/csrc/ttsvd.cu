@@ -236,7 +236,7 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
                        double* U, std::vector<double>& sv, int64_t* n_out, double* f_out, bool* capped) {
     *capped = false;
     const int64_t k = opt.max_bond;
-    if (!ctx->opt_eig_topk || k <= 0 || mj < 4 * k || mj < 192 || nmax <= k) return NDMPS_OK;
+    if (!ctx->opt_eig_topk || k <= 0 || mj < 4 * k || mj < 96 || nmax <= k) return NDMPS_OK;
     const bool sum2 = opt.mode == NDMPS_CUT_SUM2 || opt.mode == NDMPS_CUT_RSUM2;
     if (opt.cutoff > 0.0 && !sum2) return NDMPS_OK;
     if (opt.renorm != 0 && opt.renorm != 2) return NDMPS_OK;

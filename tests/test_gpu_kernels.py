@@ -162,11 +162,28 @@ def _topk_check(ops, g, k, res_tol=1e-12):
     return evals, evecs
 
 
-@pytest.mark.parametrize("n,k", [(96, 16), (200, 64), (256, 64), (357, 64), (512, 64), (512, 100), (1000, 64), (1025, 64), (1536, 64), (2560, 64)])
+@pytest.mark.parametrize("n,k", [(96, 16), (200, 64), (256, 64), (357, 64), (512, 64), (512, 100), (512, 128), (1000, 64), (1024, 128), (1025, 64), (1536, 64), (2560, 64)])
 def test_eigh_topk_random_gram(ops, n, k):
     rng = np.random.default_rng(7 * n + k)
     a = rng.standard_normal((n, 2 * n + 3))
     _topk_check(ops, a @ a.T, k)
+
+
+@pytest.mark.parametrize("option,n", [("topk_cluster", 357), ("topk_cluster", 512), ("topk_bt_pairs", 357), ("topk_bt_pairs", 1000),
+                                      ("topk_mid", 1100), ("topk_mid", 1536), ("topk_rr_skip", 512)])
+def test_eigh_topk_alternative_routes(ops, option, n):
+    """The routes that are not the default any more (grid-barrier tridiagonalisation instead of the thread-block cluster,
+    one reflector per reduction in the back-transformation, the L2-streaming kernel for 1024 < n <= 1536, Rayleigh-Ritz
+    always through the Jacobi solver) stay correct: they are the fallbacks when a cluster does not fit the device."""
+    from imgcompressionmps import _native
+    ctx = _native.context()
+    rng = np.random.default_rng(3 * n + len(option))
+    a = rng.standard_normal((n, 2 * n + 1)) * np.logspace(0, -3, n)[:, None]
+    ctx.set_option(option, 0)
+    try:
+        _topk_check(ops, a @ a.T, 64)
+    finally:
+        ctx.set_option(option, 1)
 
 
 @pytest.mark.parametrize("n", [256, 512])
