@@ -158,6 +158,16 @@ cudaError_t stream_wait(ndmps_ctx* ctx) {
     }
     cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
     if (e != cudaSuccess) return e;
+    if (ctx->opt_blocking_sync == 2) {
+        // polite polling: the waits of the sweep are 5 - 500 us long; sleeping in the driver costs a wake-up (50 - 100 us)
+        // per wait, spinning needs a core per waiter.  Poll, and hand the core over between polls.
+        for (int spins = 0;; spins++) {
+            e = cudaEventQuery(ctx->sync_event);
+            if (e != cudaErrorNotReady) return e;
+            if (spins < 64) continue;
+            std::this_thread::yield();
+        }
+    }
     return cudaEventSynchronize(ctx->sync_event);
 }
 

@@ -175,7 +175,7 @@ struct ndmps_ctx {
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
     int64_t opt_topk_rr_skip = 1;         // pass an already diagonal Rayleigh-Ritz block through without the Jacobi solve
     int64_t opt_ssim_exact = 0;           // 1: float64 SSIM arithmetic for float32 inputs too (default: shifted / normalised float32)
-    int64_t opt_blocking_sync = 0;        // host waits sleep on a blocking event instead of spinning (many host threads per core)
+    int64_t opt_blocking_sync = 0;        // host waits: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking event, 2 poll + yield
     int64_t opt_verbose = 0;
     cudaEvent_t sync_event = nullptr;     // created on first blocking wait
     // stats of the last eigensolve / sweep (for tests and profiling)

@@ -63,7 +63,8 @@ class VolumePipeline:
     * a worker synchronises its stream before its future resolves.
     """
 
-    def __init__(self, workers: int = 3, device: Optional[int] = None, blocking_sync: Optional[bool] = None):
+    def __init__(self, workers: int = 3, device: Optional[int] = None, blocking_sync: Optional[bool] = None,
+                 wait_mode: Optional[int] = None):
         import torch
         if workers < 1:
             raise ValueError("workers must be >= 1")
@@ -83,6 +84,12 @@ class VolumePipeline:
             # a spinning waiter per worker of every rank of the node, plus the ranks' main threads, must each find a core
             blocking_sync = (self.workers + 1) * ranks_here > max(1, usable - 1)
         self.blocking_sync = bool(blocking_sync)
+        # how a worker's native context waits inside the sweep (ndmps option blocking_sync): 0 spin, 1 sleep, 2 poll + yield.
+        # Oversubscribed nodes poll and yield: the sweep's waits are short, a driver sleep costs a wake-up per wait
+        env_mode = os.environ.get("NDMPS_WAIT_MODE")
+        if wait_mode is None and env_mode is not None:
+            wait_mode = int(env_mode)
+        self.wait_mode = int(wait_mode) if wait_mode is not None else (2 if self.blocking_sync else 0)
         self._ctx_lock = threading.Lock()
         self._contexts = []                             # the workers' native contexts (for launch counts / options)
         self._queues = [queue.SimpleQueue() for _ in range(self.workers)]
@@ -102,8 +109,8 @@ class VolumePipeline:
         stream = torch.cuda.Stream(device=self.device)
         done = torch.cuda.Event(blocking=self.blocking_sync)
         ctx = _native.context()
-        if self.blocking_sync:                          # sleep, do not spin, while the GPU works
-            ctx.set_option("blocking_sync", 1)
+        if self.wait_mode:
+            ctx.set_option("blocking_sync", self.wait_mode)
         with self._ctx_lock:
             self._contexts.append(ctx)
         self._ready.wait()
