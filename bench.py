@@ -534,15 +534,16 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
         f = work["gram_flops_executed"]
         if used_tc and work.get("gram_i8_ops_issued"):
             ops = work["gram_i8_ops_issued"]
-            entry("gram", "gram_i8_kernel (tcgen05.mma kind::i8 on five 7-bit digit planes, 15 products per k-step, int32 TMEM "
-                          "accumulators, float64 drain) + row_stats / split_i8 passes; small unfoldings on the FP64 tensor pipe",
+            entry("gram", "gram_i8_kernel (tcgen05.mma kind::i8 on five 7-bit digit planes: 15 digit products per k-step issued as 6 "
+                          "stacked-plane MMAs, int32 TMEM accumulators, float64 drain) + row_stats / split_i8 passes; small "
+                          "unfoldings on the FP64 tensor pipe",
                   "tensor", ops / (ms * 1e-3) / 1e12, 2.0 * peaks["bf16_tflops"], "TOP/s (int8)", "gram_i8_kernel",
                   {"algorithmic_fp32_flops_per_tensor": f, "issued_int8_ops_per_tensor": ops,
                    "peak_note": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (kind::i8 issues at twice the kind::f16 rate; "
                                 "no measured int8 figure exists for this pool)",
                    "note": "achieved = int8 tensor-core operations issued by gram_i8_kernel (tiles touching the upper triangle) / time of "
                            "the whole Gram stage, which also holds the statistics and digit-split passes (HBM-bound) and the small "
-                           "Grams; profiles/r02_summary.md has the kernel alone (tensor pipe 49.8 % active under ncu)"})
+                           "Grams; profiles/r02_summary.md has the kernel alone (tensor pipe 77 % active under ncu)"})
         else:
             entry("gram", "gram_dmma_kernel (FP64 tensor pipe, mma.sync m8n8k4.f64)", "tensor", f * work["gram_upper_fraction"] / (ms * 1e-3) / 1e12,
                   fp64_tflops, "TFLOP/s (fp64)", "gram_dmma_kernel", {"algorithmic_fp32_flops_per_tensor": f})
