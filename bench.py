@@ -205,10 +205,12 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:                 # NVML queries take driver-wide locks: one sampler per node, not one per rank
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -664,7 +666,7 @@ def run_ours(args):
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = pipe.launch_count()
     barrier()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         for i in range(args.steps):
             flush_buf.fill_(i & 0xFF)                                # evict L2 (outside the event pair)
             starts[i].record()

@@ -150,8 +150,37 @@ int profile_collect(ndmps_ctx* ctx) {
 }
 
 
+// mode 3: the stream writes a sequence number into pinned host memory (one-thread kernel, system-scope store) and the
+// host watches that word: no driver call - and so no driver lock shared with the threads that are launching - while
+// waiting.  Yields between looks; asks the driver now and then so that a faulted stream cannot hang the wait.
+__global__ void wait_flag_kernel(volatile unsigned* flag, unsigned seq) {
+    *flag = seq;
+    __threadfence_system();
+}
+
+static cudaError_t flag_wait(ndmps_ctx* ctx) {
+    if (!ctx->wait_flag) {
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(const_cast<unsigned**>(&ctx->wait_flag)), 64, cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        *ctx->wait_flag = 0;
+    }
+    const unsigned seq = ++ctx->wait_seq;
+    wait_flag_kernel<<<1, 1, 0, ctx->stream>>>(ctx->wait_flag, seq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    for (unsigned looks = 1;; looks++) {
+        if (*ctx->wait_flag == seq) return cudaSuccess;
+        if ((looks & 15) == 0) std::this_thread::yield();
+        if ((looks & 0xFFFFF) == 0) {
+            e = cudaStreamQuery(ctx->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return e;
+        }
+    }
+}
+
 cudaError_t stream_wait(ndmps_ctx* ctx) {
     if (!ctx->opt_blocking_sync) return cudaStreamSynchronize(ctx->stream);
+    if (ctx->opt_blocking_sync == 3) return flag_wait(ctx);
     if (!ctx->sync_event) {
         cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
         if (e != cudaSuccess) return e;
@@ -268,6 +297,7 @@ int ndmps_ctx_destroy(ndmps_ctx_t* ctx) {
     stream_wait(ctx);
     ctx->ws.release();
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+    if (ctx->wait_flag) cudaFreeHost(const_cast<unsigned*>(ctx->wait_flag));
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
     return NDMPS_OK;

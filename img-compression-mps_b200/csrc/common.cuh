@@ -175,9 +175,12 @@ struct ndmps_ctx {
     int64_t opt_topk_iters = 0;           // inverse-iteration steps (0: 3)
     int64_t opt_topk_rr_skip = 1;         // pass an already diagonal Rayleigh-Ritz block through without the Jacobi solve
     int64_t opt_ssim_exact = 0;           // 1: float64 SSIM arithmetic for float32 inputs too (default: shifted / normalised float32)
-    int64_t opt_blocking_sync = 0;        // host waits: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking event, 2 poll + yield
+    int64_t opt_blocking_sync = 0;        // host waits: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking event, 2 poll the
+                                          // event + yield, 3 watch a pinned word the stream writes (no driver calls) + yield
     int64_t opt_verbose = 0;
     cudaEvent_t sync_event = nullptr;     // created on first blocking wait
+    volatile unsigned* wait_flag = nullptr;   // pinned word the stream writes its sequence numbers into (wait mode 3)
+    unsigned wait_seq = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
     int last_eig_sweeps = 0;
     double eig_flops = 0.0;        // 7 n per rotation x pairs x sweeps (+ n r^2 for the Cholesky), accumulated
