@@ -53,6 +53,20 @@ struct TilePlan {
     std::vector<DevTables> dev;          // guarded by the upload mutex in permute.cu; read through upload_tile_plan only
 };
 
+// Register-only form of one permutation direction for shapes whose every factor is a power of two (permute.cu):
+// the permutation is then a permutation of the BITS of the element offset.  A thread owns the eight elements spanned by
+// destination bits {0, 1, pair}: two 16-byte loads (source rows 1 << row_shift apart), two 16-byte stores
+// (1 << pair_shift apart).  The other bits index the thread: [0,5) lane, [5,8) warp, [8,10) unrolled steps, the rest CTA.
+struct BitPlan {
+    bool ok = false;
+    int nbits = 0;                       // log2(elements)
+    int row_shift = 0;                   // source bit of destination bit 1
+    int pair_shift = 0;                  // destination bit that holds source bit 1
+    int n_idx = 0;                       // nbits - 3
+    int8_t dst_bit[48] = {0};            // index bit t -> destination bit
+    int8_t src_bit[48] = {0};            // index bit t -> source bit
+};
+
 struct ndmps_plan {
     int ndim = 0, levels = 0;
     int64_t shape[8] = {0};
@@ -63,6 +77,7 @@ struct ndmps_plan {
     DigitList dec = {};                 // destination = volume, source = site order
     bool identity = false;
     TilePlan enc_tile, dec_tile;
+    BitPlan enc_bits, dec_bits;
 };
 
 namespace ndmps {
@@ -154,7 +169,8 @@ struct ndmps_ctx {
     bool tc_sweep = false;          // set by the sweep while the tcgen05 Gram / projection are admissible (float32, bond cap)
     int64_t opt_jacobi_block = 0;   // 0: auto
     int64_t opt_gemm_path = 0;      // 0: FP64 tensor pipe for large row-major products, 2: SIMT only
-    int64_t opt_permute_path = 0;   // 0: ld/st tiles through shared memory; 3: bulk-copy (TMA-class) tiles; 2: gather kernel
+    int64_t opt_permute_path = 0;   // 0: register bit-permutation when the shape allows, else ld/st tiles through shared
+                                    // memory; 1: tiles always; 3: bulk-copy (TMA-class) tiles; 2: gather kernel
     int64_t opt_permute_ctas = 0;   // grid cap of the tiled kernel in CTAs per SM (0: 64)
     int64_t opt_merge_cap = 512;    // max rows of a merged front group in the sweep
     int64_t opt_jacobi_max_sweeps = 40;

@@ -291,6 +291,142 @@ permute_bulk_kernel(const T* __restrict__ src, T* __restrict__ dst, const BulkAr
     if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-only permutation for power-of-two shapes (256^3, 512^3, 2^k images): every factor is a power of two, so
+// the voxel -> site map permutes the BITS of the element offset (a Morton-style interleave).  No shared memory, no
+// tables, no barrier.  In both directions destination bit 0 is source bit 0 (the last axis' lowest digit); a thread
+// owns the 8 elements spanned by destination bits {0, 1, pair}, where `pair` is the destination bit that holds source
+// bit 1: it reads two 16-byte vectors (source bits {0, 1}, rows selected by destination bit 1) and writes two 16-byte
+// vectors (destination bits {0, 1}, selected by `pair`) - a 2 x 2 transposition of 8-byte pairs in registers.  Lanes take
+// the bits that complete the 128-byte lines on both sides, warps / unrolled steps / CTAs the following ones (alternately
+// the next source and the next destination bit), so one CTA moves 8192 elements in KB-sized runs on both sides.
+// ---------------------------------------------------------------------------------------------
+constexpr int BITS_THREADS = 256;      // 5 lane bits + 3 warp bits
+constexpr int BITS_UNROLL = 4;         // 2 bits: independent load pairs in flight per thread
+constexpr int BITS_FIXED_IDX = 10;     // lane + warp + unroll index bits; the others select the CTA
+
+struct BitArgs {
+    int row_shift, pair_shift, n_cta;
+    int8_t tdst[8], tsrc[8];           // thread index bits
+    int8_t cdst[40], csrc[40];         // CTA index bits
+    int64_t u_src[BITS_UNROLL], u_dst[BITS_UNROLL];
+};
+
+// element offsets (source, destination) of the first of the eight elements thread `tid` of CTA `block` moves in
+// unrolled step 0; shared by the kernel and by the host-side walk of the plan (ndmps_plan_debug_apply_bits)
+__host__ __device__ __forceinline__ void bits_offsets(const BitArgs& ba, unsigned tid, unsigned block, int64_t& so, int64_t& dofs_out) {
+    int64_t s = 0, d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int64_t on = (tid >> k) & 1u;
+        s += on << ba.tsrc[k];
+        d += on << ba.tdst[k];
+    }
+    for (int k = 0; k < ba.n_cta; k++) {
+        const int64_t on = (block >> k) & 1u;
+        s += on << ba.csrc[k];
+        d += on << ba.cdst[k];
+    }
+    so = s;
+    dofs_out = d;
+}
+
+__global__ void __launch_bounds__(BITS_THREADS, 4)
+permute_bits_kernel(const float* __restrict__ src, float* __restrict__ dst, const BitArgs ba, float scale, bool do_scale) {
+    int64_t so, dofs;
+    bits_offsets(ba, threadIdx.x, blockIdx.x, so, dofs);
+    const int64_t row = int64_t(1) << ba.row_shift, pair = int64_t(1) << ba.pair_shift;
+    float4 lo[BITS_UNROLL], hi[BITS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BITS_UNROLL; u++) {
+        const float* p = src + so + ba.u_src[u];
+        lo[u] = __ldcs(reinterpret_cast<const float4*>(p));
+        hi[u] = __ldcs(reinterpret_cast<const float4*>(p + row));
+    }
+#pragma unroll
+    for (int u = 0; u < BITS_UNROLL; u++) {
+        float4 a = make_float4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+        float4 b = make_float4(lo[u].z, lo[u].w, hi[u].z, hi[u].w);
+        if (do_scale) {
+            a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+            b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
+        }
+        float* q = dst + dofs + ba.u_dst[u];
+        __stcs(reinterpret_cast<float4*>(q), a);
+        __stcs(reinterpret_cast<float4*>(q + pair), b);
+    }
+}
+
+static void fill_bit_args(const BitPlan& bp, BitArgs& ba) {
+    ba.row_shift = bp.row_shift;
+    ba.pair_shift = bp.pair_shift;
+    ba.n_cta = bp.n_idx - BITS_FIXED_IDX;
+    for (int k = 0; k < 5; k++) { ba.tdst[k] = bp.dst_bit[k]; ba.tsrc[k] = bp.src_bit[k]; }
+    for (int k = 0; k < 3; k++) { ba.tdst[5 + k] = bp.dst_bit[5 + k]; ba.tsrc[5 + k] = bp.src_bit[5 + k]; }
+    for (int u = 0; u < BITS_UNROLL; u++) {
+        ba.u_src[u] = ba.u_dst[u] = 0;
+        for (int k = 0; k < 2; k++)
+            if ((u >> k) & 1) {
+                ba.u_src[u] += int64_t(1) << bp.src_bit[8 + k];
+                ba.u_dst[u] += int64_t(1) << bp.dst_bit[8 + k];
+            }
+    }
+    for (int k = 0; k < ba.n_cta; k++) { ba.cdst[k] = bp.dst_bit[BITS_FIXED_IDX + k]; ba.csrc[k] = bp.src_bit[BITS_FIXED_IDX + k]; }
+}
+
+// Bit form of a digit list (host).  ok = false unless every extent and stride is a power of two, the volume has at
+// least 2^13 elements, and the low bits have the pattern the kernel's register transposition assumes.
+static void build_bit_plan(const DigitList& dl, int64_t total, BitPlan& bp) {
+    bp.ok = false;
+    int sigma[64];                       // destination bit -> source bit
+    int n = 0;
+    for (int j = dl.n - 1; j >= 0; j--) {
+        if (dl.shift[j] < 0) return;
+        const int64_t st = dl.stride[j];
+        if (dl.shift[j] > 0 && (st <= 0 || (st & (st - 1)) != 0)) return;
+        for (int b = 0; b < dl.shift[j]; b++) {
+            if (n >= 40 + 3) return;
+            sigma[n++] = __builtin_ctzll((unsigned long long)st) + b;
+        }
+    }
+    if (n < BITS_FIXED_IDX + 3 || (int64_t(1) << n) != total) return;
+    int inv[64];
+    for (int k = 0; k < n; k++) inv[k] = -1;
+    for (int k = 0; k < n; k++) {
+        if (sigma[k] < 0 || sigma[k] >= n || inv[sigma[k]] >= 0) return;     // not a permutation of the bits
+        inv[sigma[k]] = k;
+    }
+    if (sigma[0] != 0 || sigma[1] < 2) return;
+    const int pair = inv[1];
+    if (pair < 2) return;
+    bool used[64] = {false};
+    used[0] = used[1] = used[pair] = true;
+    int order[64], cnt = 0;
+    // lane bits: alternately the lowest free source bit and the lowest free destination bit (128-byte lines on both
+    // sides of a warp); warp and unroll bits: whichever side has the shorter contiguous run so far (source on a tie),
+    // as the tile planner does - long runs on BOTH sides keep DRAM pages open
+    int ps = 2, pd = 2;
+    bool src_turn = true;
+    while (cnt < BITS_FIXED_IDX) {
+        while (ps < n && used[inv[ps]]) ps++;     // lowest source bit not covered = log2 of the source run
+        while (pd < n && used[pd]) pd++;          // same on the destination side
+        if (ps >= n && pd >= n) return;
+        if (cnt >= 5) src_turn = ps <= pd;
+        int pick = (src_turn && ps < n) || pd >= n ? inv[ps] : pd;
+        used[pick] = true;
+        order[cnt++] = pick;
+        src_turn = !src_turn;
+    }
+    for (int k = 0; k < n; k++) if (!used[k]) order[cnt++] = k;               // CTA bits, ascending destination order
+    if (cnt != n - 3 || cnt - BITS_FIXED_IDX > 31) return;
+    bp.nbits = n;
+    bp.row_shift = sigma[1];
+    bp.pair_shift = pair;
+    bp.n_idx = cnt;
+    for (int t = 0; t < cnt; t++) { bp.dst_bit[t] = (int8_t)order[t]; bp.src_bit[t] = (int8_t)sigma[order[t]]; }
+    bp.ok = true;
+}
+
 // Build the tiled form of a digit list (host).  Returns ok = false when the shape does not tile
 // (no unit-stride source digit, or the united digit set is too large): the gather kernel is used.
 static void build_tile_plan(const DigitList& dl, TilePlan& tp) {
@@ -527,6 +663,17 @@ static int permute_typed(ndmps_ctx* ctx, const ndmps_plan* plan, bool inverse, c
         return NDMPS_OK;
     }
     NDMPS_REQUIRE(src != dst, "ndmps permute: in-place permutation is not supported");
+    if (std::is_same<T, float>::value && ctx->opt_permute_path == 0) {
+        const BitPlan& bp = inverse ? plan->dec_bits : plan->enc_bits;
+        if (bp.ok && reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0) {
+            BitArgs ba;
+            fill_bit_args(bp, ba);
+            permute_bits_kernel<<<1u << ba.n_cta, BITS_THREADS, 0, ctx->stream>>>((const float*)src, (float*)dst, ba, (float)scale,
+                                                                                 do_scale);
+            NDMPS_LAUNCH_CHECK(ctx);
+            return NDMPS_OK;
+        }
+    }
     TilePlan& tp = const_cast<TilePlan&>(inverse ? plan->dec_tile : plan->enc_tile);
     if (tp.ok && ctx->opt_permute_path != 2) return permute_tiled<T>(ctx, tp, src, dst, scale, do_scale);
     const DigitList& dl = inverse ? plan->dec : plan->enc;
@@ -606,6 +753,8 @@ int ndmps_plan_create(int ndim, const int64_t* shape, int levels, const int64_t*
     if (!p->identity) {
         build_tile_plan(p->enc, p->enc_tile);
         build_tile_plan(p->dec, p->dec_tile);
+        build_bit_plan(p->enc, p->total, p->enc_bits);
+        build_bit_plan(p->dec, p->total, p->dec_bits);
     }
     *out = p;
     return NDMPS_OK;
@@ -694,6 +843,54 @@ int ndmps_plan_debug_apply_tiled(const ndmps_plan_t* plan, int inverse, const in
             }
         }
     }
+    return NDMPS_OK;
+}
+
+int ndmps_plan_debug_bit_info(const ndmps_plan_t* plan, int inverse, int64_t* info_out) {
+    NDMPS_REQUIRE(plan && info_out, "ndmps_plan_debug_bit_info: NULL argument");
+    const BitPlan& bp = inverse ? plan->dec_bits : plan->enc_bits;
+    info_out[0] = bp.ok ? 1 : 0;
+    info_out[1] = bp.nbits;
+    info_out[2] = bp.row_shift;
+    info_out[3] = bp.pair_shift;
+    info_out[4] = bp.ok ? (int64_t(1) << (bp.n_idx - BITS_FIXED_IDX)) : 0;
+    // contiguous run (elements) one CTA covers on the destination / source side
+    int64_t run[2] = {0, 0};
+    if (bp.ok) {
+        for (int side = 0; side < 2; side++) {
+            bool have[64] = {false};
+            have[0] = have[1] = true;
+            have[side == 0 ? bp.pair_shift : bp.row_shift] = true;
+            for (int t = 0; t < BITS_FIXED_IDX; t++) have[side == 0 ? bp.dst_bit[t] : bp.src_bit[t]] = true;
+            int k = 0;
+            while (k < bp.nbits && have[k]) k++;
+            run[side] = int64_t(1) << k;
+        }
+    }
+    info_out[5] = run[0];
+    info_out[6] = run[1];
+    return NDMPS_OK;
+}
+
+int ndmps_plan_debug_apply_bits(const ndmps_plan_t* plan, int inverse, const int32_t* src_host, int32_t* dst_host) {
+    NDMPS_REQUIRE(plan && src_host && dst_host, "ndmps_plan_debug_apply_bits: NULL argument");
+    const BitPlan& bp = inverse ? plan->dec_bits : plan->enc_bits;
+    NDMPS_REQUIRE(bp.ok, "ndmps_plan_debug_apply_bits: this shape has no bit plan");
+    BitArgs ba;
+    fill_bit_args(bp, ba);
+    const int64_t row = int64_t(1) << ba.row_shift, pair = int64_t(1) << ba.pair_shift;
+    for (unsigned block = 0; block < (1u << ba.n_cta); block++)
+        for (unsigned tid = 0; tid < (unsigned)BITS_THREADS; tid++) {
+            int64_t so, d0;
+            bits_offsets(ba, tid, block, so, d0);
+            for (int u = 0; u < BITS_UNROLL; u++) {
+                const int32_t* lo = src_host + so + ba.u_src[u];
+                const int32_t* hi = lo + row;
+                int32_t* q = dst_host + d0 + ba.u_dst[u];
+                q[0] = lo[0]; q[1] = lo[1]; q[2] = hi[0]; q[3] = hi[1];
+                q[pair] = lo[2]; q[pair + 1] = lo[3]; q[pair + 2] = hi[2]; q[pair + 3] = hi[3];
+            }
+        }
     return NDMPS_OK;
 }
 

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "ndmps_plan_debug_offsets": (ci, [vp, ci, i64, i64, p_i64]),
     "ndmps_plan_debug_tile_info": (ci, [vp, ci, p_i64]),
     "ndmps_plan_debug_apply_tiled": (ci, [vp, ci, vp, vp]),
+    "ndmps_plan_debug_bit_info": (ci, [vp, ci, p_i64]),
+    "ndmps_plan_debug_apply_bits": (ci, [vp, ci, vp, vp]),
     "ndmps_encode": (ci, [vp, vp, vp, vp, ci, f64]),
     "ndmps_decode": (ci, [vp, vp, vp, vp, ci]),
     "ndmps_sumsq": (ci, [vp, vp, i64, ci, p_f64]),
@@ -240,6 +242,18 @@ class Plan:
         dst = np.full(src.shape, -1, dtype=np.int32)
         check(self.lib.ndmps_plan_debug_apply_tiled(self.handle, int(bool(inverse)), src.ctypes.data_as(C.c_void_p),
                                                     dst.ctypes.data_as(C.c_void_p)), "ndmps_plan_debug_apply_tiled")
+        return dst
+
+    def bit_info(self, inverse: bool) -> dict:
+        out = (C.c_int64 * 7)()
+        check(self.lib.ndmps_plan_debug_bit_info(self.handle, int(bool(inverse)), out), "ndmps_plan_debug_bit_info")
+        return dict(zip(("bits", "nbits", "row_shift", "pair_shift", "ctas", "dst_run", "src_run"), (int(v) for v in out)))
+
+    def apply_bits_host(self, inverse: bool, src: np.ndarray) -> np.ndarray:
+        src = np.ascontiguousarray(src, dtype=np.int32).reshape(-1)
+        dst = np.full(src.shape, -1, dtype=np.int32)
+        check(self.lib.ndmps_plan_debug_apply_bits(self.handle, int(bool(inverse)), src.ctypes.data_as(C.c_void_p),
+                                                   dst.ctypes.data_as(C.c_void_p)), "ndmps_plan_debug_apply_bits")
         return dst
 
     def __del__(self):

@@ -104,6 +104,12 @@ int ndmps_plan_debug_offsets(const ndmps_plan_t* plan, int inverse, int64_t firs
  * apply_tiled walks the tile tables on int32 host arrays exactly as the kernel does. */
 int ndmps_plan_debug_tile_info(const ndmps_plan_t* plan, int inverse, int64_t* info_out);
 int ndmps_plan_debug_apply_tiled(const ndmps_plan_t* plan, int inverse, const int32_t* src_host, int32_t* dst_host);
+/* host-only checks of the register bit-permutation used for power-of-two shapes (no device work):
+ * info_out[7] = {has a bit plan?, log2(elements), source bit of destination bit 1, destination bit of source bit 1, CTAs,
+ * contiguous destination run per CTA, contiguous source run per CTA}; apply_bits moves int32 host arrays with the
+ * kernel's own thread -> offset function and register shuffle. */
+int ndmps_plan_debug_bit_info(const ndmps_plan_t* plan, int inverse, int64_t* info_out);
+int ndmps_plan_debug_apply_bits(const ndmps_plan_t* plan, int inverse, const int32_t* src_host, int32_t* dst_host);
 /* dst[site order] = scale * src[volume order]   (scale folds the 1/||x|| of core/ndmps.py:60-61) */
 int ndmps_encode(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void* src, void* dst, int dtype, double scale);
 /* dst[volume order] = src[site order] */

@@ -86,3 +86,31 @@ def test_tiled_permutation_tables_match_oracle(shape):
     assert enc["tile"] <= 8192 and enc["tile"] * enc["tiles"] == ramp.size
     assert np.array_equal(plan.apply_tiled_host(False, ramp), want)
     assert np.array_equal(plan.apply_tiled_host(True, want), ramp.reshape(-1))
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 128, 128), (256, 256), (256, 128), (512, 512), (32, 32, 32),
+                                   (16, 16, 16, 16), (1024, 16), (4096, 4), (32, 16, 8, 32), (64, 64, 32, 32)])
+def test_bit_permutation_plan_matches_oracle(shape):
+    """Power-of-two shapes take the register bit-permutation kernel: its thread -> offset function and its 2 x 2
+    register transposition, walked on the host exactly as the kernel runs them, reproduce the oracle's permutation."""
+    from oracle import encoding as OE
+    factors, _ = get_factorlist(shape)
+    plan = N.Plan(shape, factors)
+    ramp = np.arange(int(np.prod(shape)), dtype=np.int32).reshape(shape)
+    want = OE.encode(ramp).reshape(-1)
+    for inverse in (False, True):
+        info = plan.bit_info(inverse)
+        assert info["bits"] and (1 << info["nbits"]) == ramp.size and info["ctas"] * 8192 == ramp.size
+        assert info["dst_run"] >= 32 and info["src_run"] >= 32          # whole 128-byte lines on both sides
+    assert np.array_equal(plan.apply_bits_host(False, ramp), want)
+    assert np.array_equal(plan.apply_bits_host(True, want), ramp.reshape(-1))
+
+
+@pytest.mark.parametrize("shape", [(8, 9), (30, 40, 50), (512, 680), (8, 8, 8), (16, 1024), (64, 64, 32, 400)])
+def test_bit_permutation_plan_declines_other_shapes(shape):
+    """Non-power-of-two factors, volumes below one CTA's 8192 elements and low-bit patterns the register
+    transposition does not cover keep the tiled kernel."""
+    factors, _ = get_factorlist(shape)
+    plan = N.Plan(shape, factors)
+    assert not plan.bit_info(False)["bits"] and not plan.bit_info(True)["bits"]
+    assert plan.tile_info(False)["tiled"]

@@ -42,6 +42,29 @@ def test_encode_decode_bit_exact(ops, shape, dtype):
     assert np.array_equal(back.cpu().numpy(), x)
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 256), (256, 128), (32, 16, 8, 32), (128, 128, 128), (1024, 16)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_permutation_kernels_agree(ops, shape):
+    """Power-of-two shapes: the register bit-permutation (default), the shared-memory tiles (permute_path = 1) and
+    the gather kernel (2) give the oracle's permutation bit for bit, with and without the folded scale."""
+    from imgcompressionmps import _native
+    from imgcompressionmps.utils.core import get_factorlist
+    factors, _ = get_factorlist(shape)
+    assert _native.Plan(shape, factors).bit_info(False)["bits"]
+    ctx = _native.context()
+    x = np.random.default_rng(12).standard_normal(shape).astype(np.float32)
+    want = OE.encode(x)
+    try:
+        for path in (0, 1, 2):
+            ctx.set_option("permute_path", path)
+            got = ops.encode(dev(x))
+            assert np.array_equal(got.cpu().numpy(), want), path
+            assert np.array_equal(ops.decode(got, shape).cpu().numpy(), x), path
+            assert np.array_equal(ops.encode(dev(x), 0.375).cpu().numpy(), want * np.float32(0.375)), path
+    finally:
+        ctx.set_option("permute_path", 0)
+
+
 def test_encode_golden_ramp(ops, golden_encoding):
     """Device permutation of a ramp == the reference's own scatter (fixtures made by running it)."""
     import hashlib
