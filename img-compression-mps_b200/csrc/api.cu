@@ -128,8 +128,36 @@ int ensure_pinned(ndmps_ctx* ctx, size_t doubles) {
         ctx->pinned_doubles = 0;
     }
     size_t want = doubles < 16384 ? 16384 : doubles;
-    NDMPS_CUDA_TRY(cudaMallocHost(&ctx->pinned, want * sizeof(double)));
+    // mapped: the read-back kernel below stores into it from the SMs (same pointer on both sides under unified addressing)
+    NDMPS_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinned), want * sizeof(double), cudaHostAllocMapped));
     ctx->pinned_doubles = want;
+    return NDMPS_OK;
+}
+
+// Small device -> host read-backs (eigenvalues, flags, scalars: 4 bytes ... a few hundred KB) leave through the SMs, not
+// through the copy engine: a cudaMemcpyAsync queues behind whatever the device-to-host engine is moving for ANOTHER
+// stream, and with volumes in flight through host buffers that is a 537 MB reconstruction (10 ms) - every one of the
+// eight waits of a sweep stood behind one.  A few warps storing into mapped pinned memory do not queue behind anything.
+__global__ void __launch_bounds__(256) readback_kernel(const unsigned* __restrict__ src, unsigned* dst_host, int64_t words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+        dst_host[i] = src[i];
+    __threadfence_system();
+}
+
+int readback(ndmps_ctx* ctx, void* pinned_dst, const void* dev_src, size_t bytes) {
+    if (bytes == 0) return NDMPS_OK;
+    const bool in_scratch = ctx->pinned && (const char*)pinned_dst >= (const char*)ctx->pinned &&
+                            (const char*)pinned_dst + bytes <= (const char*)(ctx->pinned + ctx->pinned_doubles);
+    const bool words = bytes % 4 == 0 && reinterpret_cast<uintptr_t>(pinned_dst) % 4 == 0 && reinterpret_cast<uintptr_t>(dev_src) % 4 == 0;
+    if (ctx->opt_readback == 0 && in_scratch && words && bytes <= (size_t(8) << 20)) {
+        const int64_t n = (int64_t)(bytes / 4);
+        int64_t grid = (n + 1023) / 1024;
+        if (grid > 32) grid = 32;
+        readback_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>((const unsigned*)dev_src, (unsigned*)pinned_dst, n);
+        NDMPS_LAUNCH_CHECK(ctx);
+        return NDMPS_OK;
+    }
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(pinned_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return NDMPS_OK;
 }
 
@@ -395,6 +423,7 @@ int ndmps_ctx_set_option(ndmps_ctx_t* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "topk_iters")) ctx->opt_topk_iters = value;
     else if (!strcmp(name, "topk_rr_skip")) ctx->opt_topk_rr_skip = value;
     else if (!strcmp(name, "blocking_sync")) ctx->opt_blocking_sync = value;
+    else if (!strcmp(name, "readback")) ctx->opt_readback = value;
     else if (!strcmp(name, "verbose")) ctx->opt_verbose = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
     else if (!strcmp(name, "ssim_exact")) ctx->opt_ssim_exact = value;

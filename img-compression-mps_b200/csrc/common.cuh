@@ -195,6 +195,8 @@ struct ndmps_ctx {
                                           // event + yield, 3 watch a pinned word the stream writes (no driver calls) + yield
     int64_t opt_verbose = 0;
     cudaEvent_t sync_event = nullptr;     // created on first blocking wait
+    int64_t opt_readback = 0;                 // small device -> host read-backs: 0 stores from the SMs into mapped pinned
+                                              // memory, 1 cudaMemcpyAsync (copy engine)
     volatile unsigned* wait_flag = nullptr;   // pinned word the stream writes its sequence numbers into (wait mode 3)
     unsigned wait_seq = 0;
     // stats of the last eigensolve / sweep (for tests and profiling)
@@ -213,6 +215,8 @@ struct ndmps_ctx {
 namespace ndmps {
 
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
+// small device -> host copy into the pinned scratch, enqueued on the context's stream (api.cu: SM stores, not the copy engine)
+int readback(ndmps_ctx* ctx, void* pinned_dst, const void* dev_src, size_t bytes);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it to `bytes` once per
 // (kernel, device), from any host thread (the largest value set so far is remembered under a mutex).
 int raise_dynamic_smem(const void* kernel, int device, int bytes);

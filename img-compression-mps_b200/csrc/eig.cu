@@ -1184,7 +1184,7 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
             case 16: NDMPS_TRY(run_persistent<16>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
             default: NDMPS_TRY(run_persistent<0>(ctx, A, n, ncols, b, nb, max_sweeps, ctrl, tol2, floor2, smem, quad_stop2)); break;
         }
-        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_TRY(readback(ctx, host_flag, ctrl + 1, sizeof(int)));
         NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] <= 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, cols = %d, b = %d)", max_sweeps, n, ncols, b);
@@ -1200,7 +1200,7 @@ static int jacobi_columns(ndmps_ctx* ctx, double* A, int n, int ncols, double to
             NDMPS_TRY(run_round<0>(ctx, A, n, ncols, b, nb, round, flag, tol2, floor2, smem));
         *sweeps_used = s + 1;
         if (s >= 3) {
-            NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            NDMPS_TRY(readback(ctx, host_flag, flag, sizeof(int)));
             NDMPS_CUDA_TRY(stream_wait(ctx));
             converged = host_flag[0] == 0;
         }
@@ -1252,7 +1252,7 @@ static int pivoted_cholesky_cluster(ndmps_ctx* ctx, const double* G, int n, doub
     usable.store(1);
     ctx->launches++;
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, rank_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, host_flag, rank_dev, sizeof(int)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     *done = true;
@@ -1279,7 +1279,7 @@ static int pivoted_cholesky_blocked(ndmps_ctx* ctx, const double* G, int n, doub
     void* args[] = {&G, &n, &rows_per, &Lcol, &diag_g, &rows_g, &ctrl, &stop_rel};
     NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_blocked_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, host_flag, ctrl + 1, sizeof(int)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     *done = true;
@@ -1313,7 +1313,7 @@ static int pivoted_cholesky(ndmps_ctx* ctx, const double* G, int n, double* Lcol
     void* args[] = {&G, &n, &rows_per, &Lcol, &cand_rows, &cand, &ctrl, &stop_rel};
     NDMPS_TRY(coop_launch(ctx, (const void*)pivoted_cholesky_kernel, dim3(ncta), dim3(256), args, smem));
     int* host_flag = reinterpret_cast<int*>(ctx->pinned);
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, host_flag, ctrl + 1, sizeof(int)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     *rank_out = host_flag[0];
     return NDMPS_OK;
@@ -1366,7 +1366,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         int* info = nullptr;
         NDMPS_TRY(eigh_small_async(ctx, a_in, n, evals_dev, evecs_dev, tol_override > 0.0 ? 1e-14f : 0.f, &info));
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
-        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_TRY(readback(ctx, host_flag, info, 2 * sizeof(int)));
         NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] < 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d, single-CTA solver)", max_sweeps, n);
@@ -1405,7 +1405,7 @@ int eigh(ndmps_ctx* ctx, double* a_in, int64_t n64, double* evals_dev, double* e
         int warps = (matches + 3) / 4;                        // four pairs per warp
         NDMPS_TRY(run_single<4>(ctx, cols, n, warps, max_sweeps, ctrl, tol2, floor2, (size_t)n * n * sizeof(double)));
         int* host_flag = reinterpret_cast<int*>(ctx->pinned);
-        NDMPS_CUDA_TRY(cudaMemcpyAsync(host_flag, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_TRY(readback(ctx, host_flag, ctrl + 1, sizeof(int)));
         NDMPS_CUDA_TRY(stream_wait(ctx));
         if (host_flag[0] <= 0) {
             set_error("eigh: Jacobi did not converge in %d sweeps (n = %d)", max_sweeps, n);

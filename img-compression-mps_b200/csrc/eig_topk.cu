@@ -1340,7 +1340,7 @@ int eigh_topk(ndmps_ctx* ctx, const double* G, int64_t n64, int64_t k64, double*
             rr_passthrough_kernel<<<1, 512, 0, ctx->stream>>>(H, m, 1e-13, hev, W, flag);
             NDMPS_LAUNCH_CHECK(ctx);
             NDMPS_TRY(ensure_pinned(ctx, 64));
-            NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            NDMPS_TRY(readback(ctx, ctx->pinned, flag, sizeof(int)));
             NDMPS_CUDA_TRY(stream_wait(ctx));
             passed = *reinterpret_cast<const int*>(ctx->pinned) == 1;
         }

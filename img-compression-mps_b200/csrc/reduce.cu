@@ -196,7 +196,7 @@ int ndmps_sumsq(ndmps_ctx_t* ctx, const void* x, int64_t n, int dtype, double* o
     double* out_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
     NDMPS_TRY(reduce_dispatch<0>(ctx, x, nullptr, n, dtype, out_dev));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, 2 * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     out_host[0] = ctx->pinned[0];
     return NDMPS_OK;
@@ -215,8 +215,7 @@ int ndmps_minmax(ndmps_ctx_t* ctx, const void* const* arrays, const int64_t* siz
         NDMPS_REQUIRE(arrays[i] && sizes[i] > 0, "ndmps_minmax: array %d is empty", i);
         NDMPS_TRY(reduce_dispatch<1>(ctx, arrays[i], nullptr, sizes[i], dtype, out_dev + 2 * i));
     }
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * (size_t)count * sizeof(double), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, 2 * (size_t)count * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     memcpy(out_host, ctx->pinned, 2 * (size_t)count * sizeof(double));
     return NDMPS_OK;
@@ -230,7 +229,7 @@ int ndmps_psnr_terms(ndmps_ctx_t* ctx, const void* a, const void* b, int64_t n, 
     double* out_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
     { StageScope sc(ctx, ST_METRIC); NDMPS_TRY(reduce_dispatch<2>(ctx, a, b, n, dtype, out_dev)); }
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, 2 * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     out_host[0] = ctx->pinned[0];
     out_host[1] = ctx->pinned[1];

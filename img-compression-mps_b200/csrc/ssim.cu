@@ -582,7 +582,7 @@ static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const Slice
         NDMPS_TRY(launch_stream(ctx, a, b, f, p, range, partial));
         ssim_slice_kernel<<<(unsigned)f.S, 128, 0, ctx->stream>>>(partial, (int)p.per_slice, 1.0 / ((double)ih * (double)iw), scores);
         NDMPS_LAUNCH_CHECK(ctx);
-        NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, scores, (size_t)f.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        NDMPS_TRY(readback(ctx, ctx->pinned, scores, (size_t)f.S * sizeof(double)));
         NDMPS_CUDA_TRY(stream_wait(ctx));
         memcpy(scores_host, ctx->pinned, (size_t)f.S * sizeof(double));
         return NDMPS_OK;
@@ -599,7 +599,7 @@ static int ssim_slices_typed(ndmps_ctx* ctx, const T* a, const T* b, const Slice
     NDMPS_TRY(launch_ssim_tile<T>(ctx, a, b, f, range, ty, tx, nt, partial));
     ssim_slice_kernel<<<(unsigned)f.S, 128, 0, ctx->stream>>>(partial, ty * tx, 1.0 / ((double)ih * (double)iw), scores);
     NDMPS_LAUNCH_CHECK(ctx);
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, scores, (size_t)f.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, scores, (size_t)f.S * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     memcpy(scores_host, ctx->pinned, (size_t)f.S * sizeof(double));
     return NDMPS_OK;
@@ -673,7 +673,7 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
     }
     ssim_final_kernel<<<nfam, 256, 0, ctx->stream>>>(partial, bounds_dev, scale_dev, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, 4 * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));   // also covers the two small H2D copies from the stack
     double m = 0.0;
     for (int k = 0; k < nfam; k++) m += ctx->pinned[k];

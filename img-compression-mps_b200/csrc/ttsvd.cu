@@ -194,7 +194,7 @@ static double renorm_factor(const double* s, int64_t n, int64_t keep, int power)
 static int fetch_exact_flag(ndmps_ctx* ctx, size_t slot) {
     auto& dg = ctx->tc_digits;
     if (dg.use_exact == nullptr || dg.gen != ctx->ws.generation || dg.exact_host >= 0) return NDMPS_OK;
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned + slot, dg.use_exact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned + slot, dg.use_exact, sizeof(int)));
     dg.exact_host = -2;                                  // in flight
     return NDMPS_OK;
 }
@@ -206,7 +206,7 @@ static void note_exact_flag(ndmps_ctx* ctx, size_t slot) {
 // copy n eigenvalues to the host, return sqrt(max(l, 0)) in sv (host vector)
 static int fetch_svals(ndmps_ctx* ctx, const double* evals_dev, int64_t n, std::vector<double>& sv) {
     NDMPS_TRY(ensure_pinned(ctx, (size_t)n + 64));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, evals_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, evals_dev, (size_t)n * sizeof(double)));
     NDMPS_TRY(fetch_exact_flag(ctx, (size_t)n + 8));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     note_exact_flag(ctx, (size_t)n + 8);
@@ -246,7 +246,7 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     { StageScope sc(ctx, ST_EIG); NDMPS_TRY(eigh_topk(ctx, Gj, mj, k, out, U, mj, &done)); }
     if (!done) return NDMPS_OK;
     NDMPS_TRY(ensure_pinned(ctx, (size_t)k + 64));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out, (size_t)(k + 2) * sizeof(double)));
     NDMPS_TRY(fetch_exact_flag(ctx, (size_t)k + 8));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     note_exact_flag(ctx, (size_t)k + 8);
@@ -746,7 +746,7 @@ int ndmps_overlap(ndmps_ctx_t* ctx, const void* const* cores_a, const int64_t* r
     double* out_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<double>(2, &out_dev));
     NDMPS_TRY(overlap(ctx, cores_a, ranks_a, dtype_a, cores_b, ranks_b, dtype_b, levels, dims, out_dev));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     out_host[0] = ctx->pinned[0];
     return NDMPS_OK;
@@ -807,7 +807,7 @@ int ndmps_roundtrip_host(ndmps_ctx_t* ctx, const ndmps_plan_t* plan, const void*
     NDMPS_TRY(permute(ctx, plan, true, dense, vol, dtype, 1.0));
     NDMPS_CUDA_TRY(cudaMemcpyAsync(dst_host, vol, (size_t)N * esz, cudaMemcpyDefault, ctx->stream));
     NDMPS_TRY(ensure_pinned(ctx, 2 * (size_t)L + 2));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, extras, (2 * (size_t)L + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NDMPS_TRY(readback(ctx, ctx->pinned, extras, (2 * (size_t)L + 2) * sizeof(double)));
     NDMPS_CUDA_TRY(stream_wait(ctx));
     if (boundaries_out_host)
         for (int i = 0; i < 2 * L; i++) boundaries_out_host[i] = ctx->pinned[i];

@@ -248,6 +248,31 @@ def test_roundtrip_host_entry():
     assert np.linalg.norm(rec - ro) / np.linalg.norm(ro) < 1e-5
 
 
+def test_readback_routes_agree():
+    """Small device -> host read-backs (eigenvalues, flags, scalars) leave through SM stores into mapped pinned memory
+    by default and through cudaMemcpyAsync with readback = 1: same bytes either way, under every host wait mode."""
+    from imgcompressionmps import _native, _ops
+    from imgcompressionmps.utils.metrics import compute_psnr, compute_ssim_by_dim
+    x = phantom((64, 64, 64), seed=6, background=0.01).astype(np.float32)
+    ctx = _native.context()
+    results = []
+    try:
+        for readback, wait in ((1, 0), (0, 0), (0, 3), (0, 2), (0, 1)):
+            ctx.set_option("readback", readback)
+            ctx.set_option("blocking_sync", wait)
+            extras = {}
+            rec, ranks = _ops.roundtrip_host(x, max_bond=16, extras=extras)
+            results.append((rec, ranks, extras["norm"], extras["boundary_list"], compute_ssim_by_dim(rec, x), compute_psnr(rec, x)))
+    finally:
+        ctx.set_option("readback", 0)
+        ctx.set_option("blocking_sync", 0)
+    for r in results[1:]:
+        assert r[1] == results[0][1]
+        assert np.array_equal(r[0], results[0][0])
+        assert r[2] == results[0][2] and np.array_equal(r[3], results[0][3])
+        assert r[4] == results[0][4] and r[5] == results[0][5]
+
+
 # ---- capped bonds: leading-eigenpair solver vs the full solver ---------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
 def test_capped_sweep_same_as_full_solver(NDMPS, dtype):
