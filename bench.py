@@ -506,7 +506,7 @@ def ncu_traffic(kernel_substring):
     return None
 
 
-def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, eig_flops, used_tc):
+def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, eig_flops, used_tc, bit_permute=False):
     """stage -> roofline entry.  stages_per_call: {stage: (ms per tensor, calls per tensor)}."""
     out = {}
 
@@ -529,8 +529,10 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
     if have("permute"):
         ms = stages_per_call["permute"][0]
         b = work["encode_bytes"] + work["decode_bytes"]
-        entry("permute", "permute_tiled_kernel<float,4> (encode + decode)", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
-              "permute_tiled_kernel", {"algorithmic_bytes_per_tensor": b})
+        name = ("permute_bits_kernel (power-of-two shape: register bit-permutation, two 16-byte loads + two 16-byte stores per "
+                "thread, no shared memory; encode + decode)") if bit_permute else "permute_tiled_kernel<float,4> (encode + decode)"
+        entry("permute", name, "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
+              "permute_bits_kernel" if bit_permute else "permute_tiled_kernel", {"algorithmic_bytes_per_tensor": b})
     if have("gram"):
         ms = stages_per_call["gram"][0]
         f = work["gram_flops_executed"]
@@ -756,7 +758,9 @@ def run_ours(args):
     per_call = {k: (v[0] / p_steps, v[1] / p_steps) for k, v in stages.items()}
     work = work_for(workload, info, nvox)
     used_tc = bool(ctx.stat("tc_launches")) if _has_stat(ctx, "tc_launches") else False
-    rooflines = build_rooflines(per_call, single_ms, work, nvox, peaks, fp64_tflops, eig_flops, used_tc)
+    from imgcompressionmps import _ops as _ops_mod
+    bit_permute = bool(_ops_mod.plan_for(tuple(WORKLOADS[workload]["shape"])).bit_info(False)["bits"])
+    rooflines = build_rooflines(per_call, single_ms, work, nvox, peaks, fp64_tflops, eig_flops, used_tc, bit_permute)
     shares = {k: round(v[0] / single_ms, 4) for k, v in per_call.items() if v[1]}
     dominant = max(shares, key=shares.get) if shares else None
     roof = dict(rooflines.get(dominant) or {})

@@ -144,6 +144,23 @@ __global__ void __launch_bounds__(256) readback_kernel(const unsigned* __restric
     __threadfence_system();
 }
 
+// device -> device copies of bond-sized data: the same few warps instead of a copy-engine descriptor (which shares its
+// engine's queue with the other streams' transfers)
+int copy_small(ndmps_ctx* ctx, void* dev_dst, const void* dev_src, size_t bytes) {
+    if (bytes == 0) return NDMPS_OK;
+    const bool words = bytes % 4 == 0 && reinterpret_cast<uintptr_t>(dev_dst) % 4 == 0 && reinterpret_cast<uintptr_t>(dev_src) % 4 == 0;
+    if (ctx->opt_readback == 0 && words && bytes <= (size_t(8) << 20)) {
+        const int64_t n = (int64_t)(bytes / 4);
+        int64_t grid = (n + 1023) / 1024;
+        if (grid > 64) grid = 64;
+        readback_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>((const unsigned*)dev_src, (unsigned*)dev_dst, n);
+        NDMPS_LAUNCH_CHECK(ctx);
+        return NDMPS_OK;
+    }
+    NDMPS_CUDA_TRY(cudaMemcpyAsync(dev_dst, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NDMPS_OK;
+}
+
 int readback(ndmps_ctx* ctx, void* pinned_dst, const void* dev_src, size_t bytes) {
     if (bytes == 0) return NDMPS_OK;
     const bool in_scratch = ctx->pinned && (const char*)pinned_dst >= (const char*)ctx->pinned &&

@@ -217,6 +217,7 @@ namespace ndmps {
 int ensure_pinned(ndmps_ctx* ctx, size_t doubles);
 // small device -> host copy into the pinned scratch, enqueued on the context's stream (api.cu: SM stores, not the copy engine)
 int readback(ndmps_ctx* ctx, void* pinned_dst, const void* dev_src, size_t bytes);
+int copy_small(ndmps_ctx* ctx, void* dev_dst, const void* dev_src, size_t bytes);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it to `bytes` once per
 // (kernel, device), from any host thread (the largest value set so far is remembered under a mutex).
 int raise_dynamic_smem(const void* kernel, int device, int bytes);

@@ -480,14 +480,14 @@ ssim_slice_kernel_f32(const float* __restrict__ a, const float* __restrict__ b, 
 }  // namespace stream
 
 // out[fam] = sum(partial[begin..end)) * scale, one CTA per family
-__global__ void __launch_bounds__(256) ssim_final_kernel(const double* __restrict__ partial, const int64_t* __restrict__ bounds,
-                                                          const double* __restrict__ scale, double* __restrict__ out) {
+struct FinalArgs { int64_t bounds[4]; double scale[3]; };   // by value: no host -> device copy behind other streams' uploads
+__global__ void __launch_bounds__(256) ssim_final_kernel(const double* __restrict__ partial, const FinalArgs fa, double* __restrict__ out) {
     __shared__ double scratch[32];
     const int fam = blockIdx.x;
     double acc = 0.0;
-    for (int64_t i = bounds[fam] + threadIdx.x; i < bounds[fam + 1]; i += blockDim.x) acc += partial[i];
+    for (int64_t i = fa.bounds[fam] + threadIdx.x; i < fa.bounds[fam + 1]; i += blockDim.x) acc += partial[i];
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) out[fam] = acc * scale[fam];
+    if (threadIdx.x == 0) out[fam] = acc * fa.scale[fam];
 }
 
 // scores[s] = sum of the slice's tile partials * scale, one CTA per slice
@@ -642,15 +642,13 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         scale_h[k] = 1.0 / ((double)f.S * (double)ih * (double)iw);
         total_slices += f.S;
     }
-    double *range = nullptr, *partial = nullptr, *out_dev = nullptr, *scale_dev = nullptr;
-    int64_t* bounds_dev = nullptr;
+    double *range = nullptr, *partial = nullptr, *out_dev = nullptr;
     NDMPS_TRY(ctx->ws.get<double>((size_t)total_slices, &range));
     NDMPS_TRY(ctx->ws.get<double>((size_t)total_tiles, &partial));
     NDMPS_TRY(ctx->ws.get<double>(4, &out_dev));
-    NDMPS_TRY(ctx->ws.get<double>(4, &scale_dev));
-    NDMPS_TRY(ctx->ws.get<int64_t>(4, &bounds_dev));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(bounds_dev, bounds_h, sizeof(bounds_h), cudaMemcpyHostToDevice, ctx->stream));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(scale_dev, scale_h, sizeof(scale_h), cudaMemcpyHostToDevice, ctx->stream));
+    FinalArgs fa;
+    for (int k = 0; k < 4; k++) fa.bounds[k] = bounds_h[k];
+    for (int k = 0; k < 3; k++) fa.scale[k] = scale_h[k];
     int64_t slice_off = 0;
     for (int k = 0; k < nfam; k++) {
         const SliceFamily& f = fams[k];
@@ -671,10 +669,10 @@ static int ssim_typed(ndmps_ctx* ctx, const T* a, const T* b, int nfam, const Sl
         }
         slice_off += f.S;
     }
-    ssim_final_kernel<<<nfam, 256, 0, ctx->stream>>>(partial, bounds_dev, scale_dev, out_dev);
+    ssim_final_kernel<<<nfam, 256, 0, ctx->stream>>>(partial, fa, out_dev);
     NDMPS_LAUNCH_CHECK(ctx);
     NDMPS_TRY(readback(ctx, ctx->pinned, out_dev, 4 * sizeof(double)));
-    NDMPS_CUDA_TRY(stream_wait(ctx));   // also covers the two small H2D copies from the stack
+    NDMPS_CUDA_TRY(stream_wait(ctx));
     double m = 0.0;
     for (int k = 0; k < nfam; k++) m += ctx->pinned[k];
     out_host[0] = m / nfam;

@@ -269,7 +269,7 @@ static int capped_eigh(ndmps_ctx* ctx, const double* Gj, int64_t mj, int64_t nma
     *n_out = k;
     *f_out = opt.renorm == 2 ? sqrt(trace / kept) : 1.0;
     // the kept eigenvalues also on the device, where the column-side branch scales by them
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(evals_dev, out, (size_t)k * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    NDMPS_TRY(copy_small(ctx, evals_dev, out, (size_t)k * sizeof(double)));
     *capped = true;
     return NDMPS_OK;
 }
@@ -477,7 +477,7 @@ static int ttsvd(ndmps_ctx* ctx, const void* dense, int dtype, int L, const int6
         set_error("ttsvd: last core needs %lld elements, capacity %lld", (long long)last, (long long)core_cap[L - 1]);
         return NDMPS_ERR_CAPACITY;
     }
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(cores_out[L - 1], M, (size_t)last * esz, cudaMemcpyDeviceToDevice, ctx->stream));
+    NDMPS_TRY(copy_small(ctx, cores_out[L - 1], M, (size_t)last * esz));
     return NDMPS_OK;
 }
 
@@ -540,7 +540,7 @@ static int compress_bond(ndmps_ctx* ctx, const void* t1, const void* t2, int dty
     NDMPS_TRY(gemm(ctx, a, n, r, 1.0, t1, dtype, r, 1, Z, NDMPS_F64, n, 1, t1tmp, dtype, n));
     NDMPS_TRY(col_scale(ctx, sig2, r, 2, rf, 1e-8, sc));
     NDMPS_TRY(scale_convert(ctx, t2tmp, n, b, b, sc, nullptr, 1.0, t2_out, dtype, b));
-    NDMPS_CUDA_TRY(cudaMemcpyAsync(t1_out, t1tmp, (size_t)(a * n) * dtype_size(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
+    NDMPS_TRY(copy_small(ctx, t1_out, t1tmp, (size_t)(a * n) * dtype_size(dtype)));
     return NDMPS_OK;
 }
 
