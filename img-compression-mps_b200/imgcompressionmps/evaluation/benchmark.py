@@ -9,7 +9,13 @@ is issued: the original tensors are put on the device once, every (tensor, cutof
 reconstructed ONCE and that reconstruction serves both SSIM and PSNR (the reference calls
 ``to_tensor()`` per metric), nothing but scalars comes back to the host, and the tensors of a
 list are independent, so they run several at a time (``batch.VolumePipeline``); uploads are
-prefetched through pinned buffers (``loader.prefetch_to_device``).  Plotting stays out."""
+prefetched through pinned buffers (``loader.prefetch_to_device``).  Plotting stays out.
+
+The module keeps the reference module's GLOBAL names as well (``nib``, ``NDMPS``, ``get_num_bits``, ``find_specific_files``,
+``get_shapes``, ``mri_to_slices``, ``compute_ssim_by_dim``, ``compute_psnr``, ``compute_overlap``) and every function reaches
+them through the module, so code that replaces them - the reference's own ``tests/evaluation/test_benchmark.py`` does, with
+a stand-in ``NDMPS`` class - gets the reference's plain loop on whatever objects it supplies; the device path is taken
+when the items are this package's ``NDMPS`` objects."""
 from __future__ import annotations
 
 import json
@@ -19,17 +25,41 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ..utils.filetools import find_specific_files, get_shapes, mri_to_slices
+from ..core.ndmps import NDMPS
+from ..utils.filetools import find_specific_files, get_num_bits, get_shapes, mri_to_slices
 from ..utils.metrics import compute_overlap, compute_psnr, compute_ssim_by_dim
-from .loader import conv_to_mps_streamed, load_tensors          # noqa: F401  (load_tensors is part of this module's API)
+from . import loader as _loader
+from .loader import conv_to_mps_streamed
+
+nib = _loader.nifti_module()             # nibabel when installed, else the NIfTI-1 reader of loader.py behind ``nib.load``
+_DeviceNDMPS = NDMPS                     # the class whose objects take the device path below
 
 _METRICS = ("ssim", "compression_ratio", "bond_dims", "psnr", "fidelity", "storage", "gzip_bytes", "gzip_ratio")
 
 
+def load_tensors(files, ending, shape=None):
+    """``(data_list, bitsize_list)`` of a list of ``.npz`` (key ``"sequence"``) or NIfTI ``.gz`` files, optionally
+    cropped to ``shape = (B, H, W)`` (``benchmark.py:16-55``)."""
+    return _loader.load_tensors(files, ending, shape, nib=nib, num_bits=get_num_bits)
+
+
 def conv_to_mps(data_list, mode="DCT", *, max_bond=None, cutoff: float = 1e-10):
     """``NDMPS.from_tensor(data, norm=False, mode=mode)`` for every tensor (``benchmark.py:58-79``), one progress line
-    each; the host-to-device copies run ahead of the encoding."""
-    return conv_to_mps_streamed(data_list, mode, max_bond=max_bond, cutoff=cutoff)
+    each; with this package's class the host-to-device copies run ahead of the encoding."""
+    if len(data_list) == 0:
+        return []
+    if NDMPS is _DeviceNDMPS:
+        return conv_to_mps_streamed(data_list, mode, max_bond=max_bond, cutoff=cutoff)
+    extras = {}
+    if max_bond is not None:
+        extras["max_bond"] = max_bond
+    if cutoff != 1e-10:
+        extras["cutoff"] = cutoff
+    mps_list = []
+    for index, data in enumerate(data_list):
+        print(f"Converting file {index + 1}/{len(data_list)}")
+        mps_list.append(NDMPS.from_tensor(data, norm=False, mode=mode, **extras))
+    return mps_list
 
 
 def conv_to_tensors(mps_list):
@@ -49,6 +79,11 @@ def compress_list(mps_list, compression_factors):
         mps.compress(compression_factors)
 
 
+def _reconstruction(mps):
+    """On the device when the object can keep it there, else ``to_tensor()`` as the reference calls it."""
+    return mps.to_tensor_device() if hasattr(mps, "to_tensor_device") else mps.to_tensor()
+
+
 def _one_metric(mps, ref, metric: str, dtype, rec=None):
     if metric == "compression_ratio":
         return mps.compression_ratio()
@@ -59,9 +94,9 @@ def _one_metric(mps, ref, metric: str, dtype, rec=None):
     if metric == "gzip_ratio":
         return mps.compression_ratio_on_disk(dtype=dtype, replace=True)       # replace=True as the reference does
     if metric == "ssim":
-        return compute_ssim_by_dim(mps.to_tensor_device() if rec is None else rec, ref)
+        return compute_ssim_by_dim(_reconstruction(mps) if rec is None else rec, ref)
     if metric == "psnr":
-        return compute_psnr(mps.to_tensor_device() if rec is None else rec, ref)
+        return compute_psnr(_reconstruction(mps) if rec is None else rec, ref)
     if metric == "bond_dims":
         return mps.bond_sizes()
     if metric == "shape":
@@ -104,6 +139,8 @@ def run_benchmark(mps_list, original_tensors_list, cutoff_list, *, workers: Opti
     (``bond_dims`` stays ``[level][tensor]``)."""
     if len(original_tensors_list) != len(mps_list):
         raise IndexError("Length mismatch: reference_list and mps_list must have the same length.")
+    if not (len(mps_list) and all(isinstance(m, _DeviceNDMPS) for m in mps_list)):
+        return _run_benchmark_plain(mps_list, original_tensors_list, cutoff_list, dtype)
     originals = [_to_device(t) for t in original_tensors_list]
     original_mps_list = deepcopy(mps_list)
     results: Dict[str, List] = {name: [] for name in _METRICS}
@@ -132,6 +169,26 @@ def run_benchmark(mps_list, original_tensors_list, cutoff_list, *, workers: Opti
     finally:
         if pipe:
             pipe.close()
+    return {name: _layout(name, levels) for name, levels in results.items()}
+
+
+def _run_benchmark_plain(mps_list, original_tensors_list, cutoff_list, dtype):
+    """The reference's own loop (``benchmark.py:149-194``) for objects that are not this package's ``NDMPS`` (a stand-in
+    class, another implementation of the same interface) and for empty lists: every metric through ``benchmark_metric``
+    before compression and after each cutoff, same order of calls, same result layout."""
+    original_mps_list = deepcopy(mps_list)
+    references = {"ssim": original_tensors_list, "psnr": original_tensors_list, "fidelity": original_mps_list}
+    results: Dict[str, List] = {name: [] for name in _METRICS}
+
+    def measure():
+        for name in _METRICS:
+            results[name].append(benchmark_metric(mps_list, references.get(name), metric=name, dtype=dtype))
+
+    measure()
+    for i, cutoff in enumerate(cutoff_list):
+        print(f"Status: {100 * (i + 1) / len(cutoff_list):.2f}% - Cutoff: {cutoff}")
+        compress_list(mps_list, cutoff)
+        measure()
     return {name: _layout(name, levels) for name, levels in results.items()}
 
 

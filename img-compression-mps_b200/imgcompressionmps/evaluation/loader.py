@@ -58,33 +58,66 @@ def read_nifti(path) -> Tuple[np.ndarray, np.dtype]:
     return data, np.dtype(_NIFTI_DTYPES[datatype])
 
 
-def _load_one(path, ending: str):
-    if ending.endswith(".gz"):
-        try:
-            import nibabel as nib
-            img = nib.load(path)
-            return img.get_fdata(), img.header.get_data_dtype()
-        except ImportError:
-            return read_nifti(path)
-    with np.load(path) as archive:
-        data = archive["sequence"]
-        return data, data.dtype
+class _NiftiHeader:
+    def __init__(self, stored):
+        self._stored = stored
+
+    def get_data_dtype(self):
+        return self._stored
 
 
-def load_tensors(files, ending, shape=None):
+class _NiftiImage:
+    """The two things the reference asks of a nibabel image (``evaluation/benchmark.py:41-43``)."""
+
+    def __init__(self, path):
+        self._data, stored = read_nifti(path)
+        self.header = _NiftiHeader(stored)
+
+    def get_fdata(self):
+        return self._data
+
+
+class _NiftiModule:
+    """Stands where the reference's module-level ``nib`` stands when nibabel is not installed: ``nib.load(path)``."""
+
+    @staticmethod
+    def load(path):
+        return _NiftiImage(path)
+
+
+def nifti_module():
+    """nibabel when it is installed, else the NIfTI-1 reader above behind the same ``load`` call."""
+    try:
+        import nibabel
+        return nibabel
+    except ImportError:
+        return _NiftiModule()
+
+
+def load_tensors(files, ending, shape=None, *, nib=None, num_bits=None):
     """Load every file of ``files`` (``evaluation/benchmark.py:16-55``): returns ``(data_list, bitsize_list)``.
-    ``shape = (B, H, W)`` crops the first three axes; ``ending`` must end in ``.gz`` or ``.npz``."""
+    ``shape = (B, H, W)`` crops the first three axes; ``ending`` must end in ``.gz`` or ``.npz``.  ``nib`` / ``num_bits``
+    let ``evaluation.benchmark`` hand in its own module-level ``nib`` and ``get_num_bits`` (the names the reference's
+    module has, and the ones its tests replace)."""
     if not (ending.endswith(".gz") or ending.endswith(".npz")):
         raise ValueError(f"Unsupported file extension: {ending}")
+    nib = nib if nib is not None else nifti_module()
+    num_bits = num_bits if num_bits is not None else get_num_bits
     crop = tuple(slice(None, n) for n in shape) if shape else None
     data_list, bitsize_list = [], []
     for index, path in enumerate(files):
         print(f"Loading file {index + 1}/{len(files)}")
-        data, stored = _load_one(path, ending)
+        if ending.endswith(".gz"):
+            img = nib.load(path)
+            data, stored = img.get_fdata(), img.header.get_data_dtype()
+        else:
+            with np.load(path) as archive:
+                data = archive["sequence"]
+                stored = data.dtype
         if crop:
             data = data[crop]
         data_list.append(data)
-        bitsize_list.append(get_num_bits(stored))
+        bitsize_list.append(num_bits(stored))
     return data_list, bitsize_list
 
 
