@@ -1,5 +1,5 @@
-"""Generate tests/golden/reference_class.npz and reference_metrics.npz by EXECUTING the reference's own
-``core/ndmps.py`` and ``utils/metrics.py``.
+"""Generate tests/golden/reference_class.npz, reference_metrics.npz and reference_benchmark.npz by EXECUTING the
+reference's own ``core/ndmps.py``, ``utils/metrics.py`` and ``evaluation/benchmark.py``.
 
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden_reference_exec.py
@@ -124,6 +124,9 @@ def install_stand_ins():
     skm.structural_similarity = lambda a, b, data_range=None, win_size=7: OM.structural_similarity(a, b, data_range, win_size)
     skimage.metrics = skm
     sys.modules["skimage"], sys.modules["skimage.metrics"] = skimage, skm
+    nib = types.ModuleType("nibabel")          # evaluation/benchmark.py imports it at the top; the loop below never loads a file
+    nib.load = lambda path: (_ for _ in ()).throw(RuntimeError("nibabel stand-in: no files are read here"))
+    sys.modules["nibabel"] = nib
 
 
 def smooth(shape, seed):
@@ -232,7 +235,22 @@ def main():
     met["mean_std/all_prime_is_nan"] = np.array([np.isnan(m2) and np.isnan(s2)])
     met["mean_std/all_prime_grid"] = np.asarray(g2)
     np.savez_compressed(OUT / "reference_metrics.npz", **met)
-    print("wrote", OUT / "reference_class.npz", OUT / "reference_metrics.npz")
+
+    # the reference's cutoff sweep (evaluation/benchmark.py:149-194) on three small volumes: every metric before compression
+    # and after each cutoff, including the in-place uint16 quantisation its gzip_ratio metric performs at every level
+    from imgcompressionmps.evaluation import benchmark as ref_bm
+    vols = [smooth((18, 12, 8), 300 + i) + 0.1 for i in range(3)]
+    cutoffs = np.array([0.02, 0.1])
+    with contextlib.redirect_stdout(io.StringIO()) as printed:
+        res = ref_bm.run_benchmark(ref_bm.conv_to_mps(vols, mode="Std"), vols, cutoffs)
+    bench = {"volumes": np.stack(vols), "cutoffs": cutoffs, "printed": np.array(printed.getvalue())}
+    for key, value in res.items():
+        if key == "bond_dims":
+            bench["bond_dims"] = np.array([[b for b in level] for level in value])      # [level][tensor][bond]
+        else:
+            bench[key] = np.asarray(value)
+    np.savez_compressed(OUT / "reference_benchmark.npz", **bench)
+    print("wrote", OUT / "reference_class.npz", OUT / "reference_metrics.npz", OUT / "reference_benchmark.npz")
 
 
 if __name__ == "__main__":

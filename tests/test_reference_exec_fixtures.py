@@ -1,6 +1,7 @@
-"""Oracle vs outputs of the REFERENCE'S OWN ``core/ndmps.py`` and ``utils/metrics.py``, executed in the build container
-with stand-ins for quimb / scikit-image built on the oracle's restatement of those libraries
-(``tests/golden/make_golden_reference_exec.py`` -> ``reference_class.npz``, ``reference_metrics.npz``).
+"""Oracle vs outputs of the REFERENCE'S OWN ``core/ndmps.py``, ``utils/metrics.py`` and ``evaluation/benchmark.py``,
+executed in the build container with stand-ins for quimb / scikit-image built on the oracle's restatement of those
+libraries (``tests/golden/make_golden_reference_exec.py`` -> ``reference_class.npz``, ``reference_metrics.npz``,
+``reference_benchmark.npz``).
 
 Pinned by these fixtures: everything the reference's code does around the third-party cores - scatter / gather through
 its encoding map, norm / DCT options, boundary list, norm value, the compress loop, counts and ratios, quantisation with
@@ -119,3 +120,38 @@ def test_package_compute_mean_std_equals_the_executed_reference(ref_metrics):
     m2, s2, g2 = compute_mean_std(primes, 4)
     assert np.isnan(m2) and np.isnan(s2) and bool(m["mean_std/all_prime_is_nan"][0])
     assert np.allclose(g2, m["mean_std/all_prime_grid"], **TIGHT)
+
+
+def test_oracle_cutoff_sweep_equals_the_executed_reference_run_benchmark():
+    """evaluation/benchmark.py:149-194 executed from the reference's source (stand-ins as above) on three volumes and two
+    cutoffs, against the same loop written on the oracle - the loop the GPU test of the package's ``run_benchmark``
+    compares with (tests/test_gpu_ndmps.py).  Pins the order of the metric calls inside a level, in particular that the
+    ``gzip_ratio`` metric quantises the cores IN PLACE (uint16) after the level's SSIM / PSNR / fidelity were taken, and
+    that the SECOND argument of the SSIM call - the original - is the one clipped at 0."""
+    import copy
+    b = np.load(GOLDEN / "reference_benchmark.npz")
+    vols = [v for v in b["volumes"]]
+    assert min(v.min() for v in vols) < 0                       # originals with negative voxels: the clip matters
+    cutoffs = [float(c) for c in b["cutoffs"]]
+    objs = [OracleNDMPS.from_tensor(v.copy(), norm=False, mode="Std") for v in vols]
+    refs = copy.deepcopy(objs)
+    want = {k: [] for k in ("ssim", "compression_ratio", "bond_dims", "psnr", "fidelity", "storage", "gzip_bytes", "gzip_ratio")}
+    for level in [None] + cutoffs:
+        if level is not None:
+            for o in objs:
+                o.compress(level)
+        want["ssim"].append([OM.compute_ssim_by_dim(o.to_tensor(), v) for o, v in zip(objs, vols)])
+        want["compression_ratio"].append([o.compression_ratio() for o in objs])
+        want["bond_dims"].append([o.bond_sizes() for o in objs])
+        want["psnr"].append([OM.compute_psnr(o.to_tensor(), v) for o, v in zip(objs, vols)])
+        want["fidelity"].append([OM.compute_overlap(o.cores, o.norm_value, r.cores, r.norm_value) for o, r in zip(objs, refs)])
+        want["storage"].append([o.get_storage_space(np.uint16) for o in objs])
+        want["gzip_bytes"].append([o.get_bytesize_on_disk(dtype=np.uint16) for o in objs])
+        want["gzip_ratio"].append([o.compression_ratio_on_disk(dtype=np.uint16, replace=True) for o in objs])
+    assert np.array_equal(np.array(want["bond_dims"]), b["bond_dims"])
+    for key in ("compression_ratio", "storage", "gzip_bytes", "gzip_ratio"):
+        assert np.array_equal(np.array(want[key]).T, b[key]), key
+    for key in ("ssim", "psnr", "fidelity"):
+        assert np.allclose(np.array(want[key]).T, b[key], rtol=1e-11, atol=1e-12), key
+    assert b["ssim"].shape == (3, 3) and np.all(b["ssim"][:, 0] < 1.0)      # lossless level, SSIM below 1: the clipped original
+    assert str(b["printed"]).count("Converting file") == 3 and "Status: 100.00% - Cutoff: 0.1" in str(b["printed"])
