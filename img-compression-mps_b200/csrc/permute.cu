@@ -7,8 +7,11 @@
 // digits of all axes.  So   dst_digits(l, a)  <->  src_digits(a, l).
 //
 // Here the plan stores, for each direction, the destination's digit extents (in
-// C order) and the source stride of every digit; kernels walk destination
-// offsets (coalesced writes) and gather the source.
+// C order) and the source stride of every digit.  Three kernels, chosen per shape:
+//   permute_bits_kernel    every factor a power of two (256^3, 512^3, 2^k images), float32: the map permutes the BITS
+//                          of the offset; two 16-byte loads, a register transposition, two 16-byte stores per thread
+//   permute_tiled_kernel   every other shape that tiles: contiguous runs on both sides through shared memory
+//   permute_gather_kernel  the rest: walk destination offsets (coalesced writes), gather the source
 #include <algorithm>
 #include <type_traits>
 
