@@ -574,8 +574,12 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
     if have("eig"):
         ms = stages_per_call["eig"][0]
         entry("eig", "bond eigenproblems: eig_topk.cu (tridiag_kernel, bisect, invit, Rayleigh-Ritz) for capped bonds, eig.cu Jacobi otherwise",
-              "latency (float64 SIMT; neither hbm nor tensor)", eig_flops / (ms * 1e-3) / 1e12, fp64_tflops, "TFLOP/s (fp64)", "tridiag_kernel",
-              {"flops_per_tensor": eig_flops, "peak_source": "cuBLAS DGEMM 4096^3 timed in this run"})
+              "tensor", eig_flops / (ms * 1e-3) / 1e12, fp64_tflops, "TFLOP/s (fp64)", "tridiag_kernel",
+              {"flops_per_tensor": eig_flops, "peak_source": "cuBLAS DGEMM 4096^3 timed in this run (FP64 tensor pipe)",
+               "bound_note": "latency-bound in fact: float64 SIMT work in chains of dependent steps (n - 2 Householder columns of ~2.6 us "
+                             "per 512 x 512 bond matrix, each two block reductions + a cluster-wide exchange); neither HBM traffic (2 MB per "
+                             "solve) nor a tensor pipe limits it.  The FP64 rate is the only roofline its flops can be put against, "
+                             "so `frac` says how far a dependency chain is from a throughput bound, not how well a pipe is fed"})
     if have("metric"):
         ms = stages_per_call["metric"][0]
         b = work.get("metric_bytes", 0.0)
