@@ -559,8 +559,9 @@ def build_rooflines(stages_per_call, single_ms, work, nvox, peaks, fp64_tflops, 
     if have("project"):
         ms = stages_per_call["project"][0]
         b = work["project_bytes_executed"]
-        entry("project", "projection T = P^T M (one pass per front-merged group)", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
-              "gemm_tc_kernel" if used_tc else "gemm_dmma_kernel", {"algorithmic_bytes_per_tensor": b, "survey_bytes_per_tensor_one_pass_per_site": work["project_bytes"],
+        entry("project", "projection T = P^T M (one pass per front-merged group; proj_i8_kernel on the Gram's int8 digit planes)" if used_tc
+              else "projection T = P^T M (one pass per front-merged group)", "hbm", b / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s",
+              "proj_i8_kernel" if used_tc else "gemm_dmma_kernel", {"algorithmic_bytes_per_tensor": b, "survey_bytes_per_tensor_one_pass_per_site": work["project_bytes"],
                "flops_per_tensor": work["project_flops"]})
     if have("contract"):
         ms = stages_per_call["contract"][0]
