@@ -4,6 +4,8 @@ import subprocess
 import sys
 from pathlib import Path
 
+import pytest
+
 ROOT = Path(__file__).resolve().parents[1]
 
 
@@ -57,3 +59,30 @@ def test_algorithmic_work_matches_survey_table():
     assert abs(bytes_per_voxel - 70.9) < 0.2
     assert abs(flops_per_voxel - 1895) < 5
     assert w["gram_flops_issued"] < w["gram_flops_executed"]
+
+
+def test_roofline_entries_follow_the_contract():
+    """Every stage entry: ``bound`` from the contract's enum, ``frac`` = achieved / peak, ``traffic`` read from an ncu CSV
+    committed under profiles/ (the row of the kernel that really runs the stage), algorithmic figures beside it."""
+    import bench
+    info = {"site_dims": [8] * 9, "bond_dims": [8, 37, 64, 64, 64, 64, 64, 8]}
+    nvox = 512 ** 3
+    work = bench.work_for("cfg3", info, nvox)
+    per_call = {"permute": (0.36, 2), "gram": (1.0, 6), "eig": (8.2, 8), "project": (0.32, 4), "contract": (0.23, 1)}
+    peaks = {"hbm_gbs": 6559.4, "bf16_tflops": 1648.0}
+    roof = bench.build_rooflines(per_call, 11.2, work, nvox, peaks, 35.3, 1.1e9, True, True)
+    assert set(roof) == set(per_call)
+    for stage, e in roof.items():
+        assert e["bound"] in ("hbm", "tensor"), stage
+        assert e["frac"] == pytest.approx(e["achieved"] / e["peak"])
+        assert e["traffic"] and e["traffic_source"].startswith("profiles/r0"), stage
+        assert e["share_of_tensor_time"] == pytest.approx(per_call[stage][0] / 11.2)
+    # the permutation of a power-of-two volume is the register kernel: 2 x 8 B/voxel in 0.36 ms against the measured copy peak
+    assert "permute_bits_kernel" in roof["permute"]["kernel"] and roof["permute"]["traffic_source"].endswith("r02b_kernels_raw.csv")
+    assert roof["permute"]["algorithmic_bytes_per_tensor"] == 16 * nvox and roof["permute"]["frac"] == pytest.approx(0.909, abs=2e-3)
+    # ncu's DRAM traffic of ONE launch (encode or decode: 8 B/voxel) = the algorithmic bytes of that launch
+    assert roof["permute"]["calls_per_tensor"] == 2 and roof["permute"]["traffic"] == pytest.approx(8 * nvox, rel=0.06)
+    assert "proj_i8_kernel" in roof["project"]["kernel"] and roof["project"]["traffic"] > 6e8
+    assert "latency-bound" in roof["eig"]["bound_note"]
+    tiles = bench.build_rooflines(per_call, 11.2, work, nvox, peaks, 35.3, 1.1e9, True, False)
+    assert "permute_tiled_kernel" in tiles["permute"]["kernel"]
