@@ -114,3 +114,31 @@ def test_bit_permutation_plan_declines_other_shapes(shape):
     plan = N.Plan(shape, factors)
     assert not plan.bit_info(False)["bits"] and not plan.bit_info(True)["bits"]
     assert plan.tile_info(False)["tiled"]
+
+
+def test_bit_permutation_plan_random_power_of_two_shapes():
+    """400 random power-of-two shapes (2-D ... 5-D, 2^13 ... 2^21 elements, axes of extent 1 and 2 included): wherever the
+    planner accepts a shape, the kernel's thread -> offset function and register transposition reproduce the oracle's
+    permutation in both directions, both directions are accepted together, and every warp covers whole 128-byte lines."""
+    from oracle import encoding as OE
+    rng = np.random.default_rng(123)
+    seen, accepted = set(), 0
+    while len(seen) < 400:
+        exps = rng.integers(0, 9, size=int(rng.integers(2, 6)))
+        shape = tuple(int(2 ** e) for e in exps)
+        if not 13 <= exps.sum() <= 21 or shape in seen:
+            continue
+        seen.add(shape)
+        factors, _ = get_factorlist(shape)
+        plan = N.Plan(shape, factors)
+        enc, dec = plan.bit_info(False), plan.bit_info(True)
+        assert enc["bits"] == dec["bits"], shape
+        if not enc["bits"]:
+            continue
+        accepted += 1
+        ramp = np.arange(int(np.prod(shape)), dtype=np.int32).reshape(shape)
+        want = OE.encode(ramp).reshape(-1)
+        assert np.array_equal(plan.apply_bits_host(False, ramp), want), shape
+        assert np.array_equal(plan.apply_bits_host(True, want), ramp.reshape(-1)), shape
+        assert min(enc["dst_run"], enc["src_run"], dec["dst_run"], dec["src_run"]) >= 32, shape
+    assert accepted >= 50
